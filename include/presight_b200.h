@@ -1,0 +1,159 @@
+/*
+ * presight_b200 — C-ABI of the B200-native NeRF inner loop (libpresight_b200.so).
+ *
+ * Drop-in boundary for the reference's `implementation` switch: where the reference calls
+ * `self.tcnn_encoding(x)` (field_components/encodings.py:386-389, mlp.py:176-179) or the torch
+ * fallbacks, a binding calls these entry points instead.  All paths below are relative to
+ * /root/reference/nerfstudio-0.3.3/nerfstudio.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - buffers are allocated and owned by the caller (torch); kernels never allocate;
+ *   - gradients of parameters are ACCUMULATED into caller-zeroed fp32 buffers;
+ *   - `stream` is a cudaStream_t passed as void*; launches are stream-ordered and re-entrant;
+ *   - return value: 0 = ok, non-zero = error (message: ps_last_error(), thread-local);
+ *   - nothing throws across the ABI, no torch types in any signature.
+ */
+#ifndef PRESIGHT_B200_H
+#define PRESIGHT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PS_MAX_LEVELS 32
+#define PS_MAX_MLP_LAYERS 6
+#define PS_MAX_FIELDS 32
+
+/* activation codes for MLP outputs */
+#define PS_ACT_NONE 0
+#define PS_ACT_RELU 1
+#define PS_ACT_SIGMOID 2
+
+const char* ps_last_error(void);
+int ps_abi_version(void);
+/* number of kernels launched by this library in the calling process (for bench `gpu_launches`) */
+int64_t ps_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Kernel #1 — multiresolution hash encoding.
+ * Replaces HashEncoding.pytorch_fwd (+ its autograd), field_components/encodings.py:343-384;
+ * hash of encodings.py:324-341 evaluated in uint32 wrap-around arithmetic (bit-exact for T=2^k).
+ *   x01      [P,3]   fp32 positions (normally in [0,1]; any value is hashed like the reference)
+ *   table    [L*T,F] fp32, T = 1<<log2_T, F in {1,2,4,8}
+ *   scalings_host[L] fp32 per-level scales (encodings.py:282-284), HOST pointer
+ *   out      [P,L*F] fp32, level-major channels (encodings.py:384)
+ */
+int ps_hash_fwd(const float* x01, int64_t P, const float* table, const float* scalings_host, int L, int F,
+                int log2_T, float* out, void* stream);
+/* dtable [L*T,F] += scatter of dout [P,L*F];  dx [P,3] (nullable, caller-zeroed) += d/dx01.  */
+int ps_hash_bwd(const float* x01, int64_t P, const float* table, const float* scalings_host, int L, int F,
+                int log2_T, const float* dout, float* dtable, float* dx, void* stream);
+/* Parity probe: the 8 corner rows (incl. level*T) in the reference's corner order h0..h7
+ * (encodings.py:354-361) and the fractional offsets.  idx [P,L,8] int64, offset [P,L,3] fp32 (nullable). */
+int ps_hash_indices(const float* x01, int64_t P, const float* scalings_host, int L, int log2_T, int64_t* idx,
+                    float* offset, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Position prologue: aabb normalisation, L-inf scene contraction, selector.
+ * Replaces fields/PreSight/utils.py:6-10, field_components/spatial_distortions.py:66-69 (order=inf),
+ * fields/PreSight/ingp_field.py:169-177 (= prop_density_field.py:130-138).
+ *   pos [P,3] world -> x01 [P,3] (masked points moved to the origin), selector [P] uint8
+ *   aabb_host[6] = {min xyz, max xyz}; contract!=0 applies the contraction, else plain SceneBox normalisation.
+ */
+int ps_normalize_positions(const float* pos, int64_t P, const float* aabb_host, int contract, float* x01,
+                           uint8_t* selector, void* stream);
+/* Frustums.get_positions (cameras/rays.py:49-58): pos[n,s,:] = o[n] + d[n]*(bins[n,s]+bins[n,s+1])/2 */
+int ps_sample_positions(const float* origins, const float* dirs, const float* eu_bins, int64_t N, int S,
+                        float* pos, void* stream);
+/* SHEncoding(levels=4).pytorch_fwd on (d+1)/2 (utils/math.py:27-74, fields/base_field.py:136-142).
+ * dirs [P,3]; mapped == 0: raw directions (the kernel applies (d+1)/2), mapped != 0: already (d+1)/2; out [P,16]. */
+int ps_sh4(const float* dirs, int64_t P, int mapped, float* out, void* stream);
+/* nearest-centroid routing (fields/PreSight/ingp_field_ms.py:97): assign[p] = argmin_j |pos_p - c_j| */
+int ps_nearest_centroid(const float* pos, int64_t P, const float* centroids, int nf, int32_t* assign, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Kernel #2 — fused MLP (Linear+ReLU stack, optional output activation).
+ * Replaces MLP.pytorch_fwd (field_components/mlp.py:157-174) and its autograd.
+ *   x [P,dims[0]] -> y [P,dims[n_layers]];  W_host[i] -> device fp32 [dims[i+1], dims[i]] (nn.Linear layout),
+ *   b_host[i] -> device fp32 [dims[i+1]].  W_host/b_host/dims_host are HOST arrays.
+ *   Hidden activations are never written to HBM; backward recomputes them.
+ *   precision: 0 = fp32 CUDA cores (1e-3 parity), 1 = bf16 tensor-core MMA with fp32 accumulate (1e-2 parity).
+ */
+int ps_mlp_fwd(const float* x, int64_t P, const float* const* W_host, const float* const* b_host,
+               const int* dims_host, int n_layers, int out_act, int precision, float* y, void* stream);
+/* dx [P,dims[0]] (nullable) written; dW_host[i]/db_host[i] device buffers accumulated. y = forward output
+ * (needed for the sigmoid derivative; nullable when out_act == PS_ACT_NONE). */
+int ps_mlp_bwd(const float* x, const float* y, const float* dy, int64_t P, const float* const* W_host,
+               const float* const* b_host, const int* dims_host, int n_layers, int out_act, int precision,
+               float* dx, float* const* dW_host, float* const* db_host, void* stream);
+/* trunc_exp (field_components/activations.py:28-41) fused with the selector multiply
+ * (ingp_field.py:189-190): y = exp(x)*sel ; dx = dy*sel*exp(clamp(x,-15,15)). sel nullable. */
+int ps_trunc_exp_fwd(const float* x, const uint8_t* sel, int64_t P, int64_t x_stride, float* y, void* stream);
+int ps_trunc_exp_bwd(const float* x, const uint8_t* sel, const float* dy, int64_t P, int64_t x_stride,
+                     float* dx, int64_t dx_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Kernel #3 — samplers.
+ * ps_spaced_bins replaces SpacedSampler.generate_ray_samples (model_components/ray_samplers.py:98-128)
+ * with PreSight's piecewise spacing (models/PreSight/nerfacto_nusc_ms.py:312-317).
+ *   lin_bins [S+1] = torch.linspace(0,1,S+1) (device);  t_rand [N] single jitter, NULL in eval
+ *   -> sp_bins [N,S+1] in [0,1], eu_bins [N,S+1] euclidean
+ */
+int ps_spaced_bins(const float* nears, const float* fars, const float* lin_bins, const float* t_rand, int64_t N,
+                   int S, float thr, float* sp_bins, float* eu_bins, void* stream);
+/* ps_pdf_resample replaces PDFSampler.generate_ray_samples (ray_samplers.py:305-362, include_original=False)
+ * including the annealing pow of ProposalNetworkSampler (ray_samplers.py:597).
+ *   weights [N,S_in]; sp_in [N,S_in+1]; u_base [S_out+1] = linspace(0,1-1/nb,nb) (device);
+ *   rand [N] single jitter (train) or NULL (eval: u = u_base + 1/(2 nb));
+ *   -> sp_out/eu_out [N,S_out+1]; optional probes inds [N,S_out+1] int64, cdf [N,S_in+1] fp32, u [N,S_out+1].
+ *   S_in <= 1024.
+ */
+int ps_pdf_resample(const float* weights, const float* sp_in, const float* u_base, const float* rand,
+                    const float* nears, const float* fars, int64_t N, int S_in, int S_out, float padding, float eps,
+                    float anneal, float thr, float* sp_out, float* eu_out, int64_t* inds, float* cdf, float* u,
+                    void* stream);
+/* searchsorted(cdf, u, side="right") alone — the bit-exact bin-index probe (ray_samplers.py:345). */
+int ps_searchsorted_right(const float* cdf, const float* u, int64_t N, int n_cdf, int n_u, int64_t* inds,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Kernel #4 — volumetric compositing.
+ * ps_weights_* replace RaySamples.get_weights (cameras/rays.py:128-150) and its autograd.
+ *   deltas, density [N,S] -> weights [N,S].   S <= 1024.
+ */
+int ps_weights_fwd(const float* deltas, const float* density, int64_t N, int S, float* weights, void* stream);
+int ps_weights_bwd(const float* deltas, const float* density, const float* dweights, int64_t N, int S,
+                   float* ddensity, void* stream);
+/* Weighted sum along the ray: out[n,c] = sum_s w[n,s] * v[n,s,c]  (v NULL => v=1, C=1).
+ * Replaces RGBRenderer.combine_rgb (model_components/renderers.py:102-103), AccumulationRenderer
+ * (:313), the numerator of DepthRenderer "expected" (:377) and the semantics sum
+ * (models/PreSight/nerfacto_nusc_ms.py:530). */
+int ps_render_fwd(const float* weights, const float* values, int64_t N, int S, int C, float* out, void* stream);
+/* dweights [N,S] ACCUMULATED (+=), dvalues [N,S,C] written (nullable). */
+int ps_render_bwd(const float* weights, const float* values, const float* dout, int64_t N, int S, int C,
+                  float* dweights, float* dvalues, void* stream);
+/* DepthRenderer "threshold" (renderers.py:352-362): first sample with cumsum(w) >= thr. */
+int ps_depth_threshold(const float* weights, const float* eu_bins, int64_t N, int S, float threshold,
+                       float* depth, int64_t* index, void* stream);
+/* One-pass compositing used by the model fast path (nerfacto_nusc_ms.py:503-544):
+ *   in : eu_bins [N,S+1], density [N,S], rgb [N,S,3] (nullable), sem [N,S,C] (nullable, C<=128)
+ *   out: weights [N,S], rgb_out [N,3], acc [N] (unclamped), depth_exp [N] = sum w t/(sum w+1e-10) (unclipped),
+ *        depth_thr [N], sem_out [N,C], tminmax [2] (global min/max of mid-points, caller-initialised +inf/-inf)
+ */
+int ps_composite_fwd(const float* eu_bins, const float* density, const float* rgb, const float* sem, int64_t N,
+                     int S, int C, float threshold, float* weights, float* rgb_out, float* acc, float* depth_exp,
+                     float* depth_thr, float* sem_out, float* tminmax, void* stream);
+/* grads: d_weights_in [N,S] (nullable; direct seeds on the weights), d_rgb_out [N,3], d_acc [N], d_depth_exp [N],
+ *        d_sem_out [N,C] (each nullable) -> d_density [N,S], d_rgb [N,S,3], d_sem [N,S,C] (nullable if input null) */
+int ps_composite_bwd(const float* eu_bins, const float* density, const float* rgb, const float* sem,
+                     const float* weights, const float* acc, const float* depth_exp, int64_t N, int S, int C,
+                     const float* d_weights_in, const float* d_rgb_out, const float* d_acc, const float* d_depth_exp,
+                     const float* d_sem_out, float* d_density, float* d_rgb, float* d_sem, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRESIGHT_B200_H */

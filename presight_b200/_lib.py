@@ -1,0 +1,120 @@
+"""ctypes binding of libpresight_b200.so — the only door from Python into the CUDA kernels.
+
+The library is built in-tree by `presight_b200.build` (nvcc, sm_100a).  There is no fallback:
+if the shared object is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpresight_b200.so")
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_i = C.c_int
+_f = C.c_float
+_fp = C.POINTER(C.c_float)
+_pp = C.POINTER(C.c_void_p)
+_ip = C.POINTER(C.c_int)
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/presight_b200.h
+SIGNATURES = {
+    "ps_hash_fwd": [_p, _i64, _p, _fp, _i, _i, _i, _p, _p],
+    "ps_hash_bwd": [_p, _i64, _p, _fp, _i, _i, _i, _p, _p, _p, _p],
+    "ps_hash_indices": [_p, _i64, _fp, _i, _i, _p, _p, _p],
+    "ps_normalize_positions": [_p, _i64, _fp, _i, _p, _p, _p],
+    "ps_sample_positions": [_p, _p, _p, _i64, _i, _p, _p],
+    "ps_sh4": [_p, _i64, _i, _p, _p],
+    "ps_nearest_centroid": [_p, _i64, _p, _i, _p, _p],
+    "ps_mlp_fwd": [_p, _i64, _pp, _pp, _ip, _i, _i, _i, _p, _p],
+    "ps_mlp_bwd": [_p, _p, _p, _i64, _pp, _pp, _ip, _i, _i, _i, _p, _pp, _pp, _p],
+    "ps_trunc_exp_fwd": [_p, _p, _i64, _i64, _p, _p],
+    "ps_trunc_exp_bwd": [_p, _p, _p, _i64, _i64, _p, _i64, _p],
+    "ps_spaced_bins": [_p, _p, _p, _p, _i64, _i, _f, _p, _p, _p],
+    "ps_pdf_resample": [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _f, _f, _f, _f, _p, _p, _p, _p, _p, _p],
+    "ps_searchsorted_right": [_p, _p, _i64, _i, _i, _p, _p],
+    "ps_weights_fwd": [_p, _p, _i64, _i, _p, _p],
+    "ps_weights_bwd": [_p, _p, _p, _i64, _i, _p, _p],
+    "ps_render_fwd": [_p, _p, _i64, _i, _i, _p, _p],
+    "ps_render_bwd": [_p, _p, _p, _i64, _i, _i, _p, _p, _p],
+    "ps_depth_threshold": [_p, _p, _i64, _i, _f, _p, _p, _p],
+    "ps_composite_fwd": [_p, _p, _p, _p, _i64, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p],
+    "ps_composite_bwd": [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+}
+_RESTYPES = {"ps_last_error": C.c_char_p, "ps_abi_version": C.c_int, "ps_launch_count": C.c_int64}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once) and declare every prototype."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m presight_b200.build` "
+            "(there is no CPU or PyTorch fallback for the presight_b200 kernels)")
+    lib = C.CDLL(LIB_PATH)
+    for name, restype in _RESTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = C.c_int
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(list(SIGNATURES) + list(_RESTYPES))
+
+
+def launch_count() -> int:
+    return int(load().ps_launch_count())
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().ps_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"presight_b200.{what} failed (status {status}): {msg}")
+
+
+def ptr(t: Optional[torch.Tensor]):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("presight_b200 kernels need CUDA tensors (no CPU fallback exists)")
+    if not t.is_contiguous():
+        raise RuntimeError("presight_b200 kernels need contiguous tensors")
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def host_floats(vals: Sequence[float]):
+    arr = (C.c_float * len(vals))(*[float(v) for v in vals])
+    return arr
+
+
+def host_ptrs(tensors: Sequence[Optional[torch.Tensor]]):
+    arr = (C.c_void_p * len(tensors))(*[None if t is None else ptr(t) for t in tensors])
+    return arr
+
+
+def host_ints(vals: Sequence[int]):
+    return (C.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def call(name: str, *args) -> None:
+    check(getattr(load(), name)(*args), name)

@@ -1,0 +1,415 @@
+// Kernel #2: stand-alone fused MLP forward / backward built from the warp-level blocks of mlp_mma.cuh.
+// One CTA = 8 warps = 128 points per tile, persistent over tiles; weights live in shared memory for the
+// whole kernel; hidden activations never leave the SM (backward recomputes the forward).
+#pragma once
+#include "mlp_mma.cuh"
+
+namespace ps {
+namespace mma {
+
+constexpr int kTile = 128;
+constexpr int kWarps = kTile / 16;
+constexpr int kThreads = kWarps * 32;
+
+struct MlpArgs {
+    const float* x;
+    float* y;
+    const float* dy;
+    float* dx;
+    int64_t P;
+    const float* W[PS_MAX_MLP_LAYERS];
+    const float* b[PS_MAX_MLP_LAYERS];
+    float* dW[PS_MAX_MLP_LAYERS];
+    float* db[PS_MAX_MLP_LAYERS];
+    int in_dim, out_dim;  // real (unpadded) sizes; hidden width is exact
+    int out_act;
+};
+
+// Network archetype: K0 -> H -> ... (NHID hidden layers) ... -> NOUT, all padded to multiples of 16.
+template <int K0_, int H_, int NHID_, int NOUT_>
+struct Shape {
+    static constexpr int K0 = K0_, H = H_, NHID = NHID_, NOUT = NOUT_;
+    static constexpr int NL = NHID + 1;
+    static constexpr int N0 = NHID == 0 ? NOUT : H;  // width after the first layer
+    static constexpr int NMID = NHID > 1 ? NHID - 1 : 0;
+    static_assert(K0 % 16 == 0 && H % 16 == 0 && NOUT % 16 == 0, "dims must be padded to multiples of 16");
+    static_assert(H <= 64, "ReLU masks are kept in one 32-bit word per layer");
+};
+
+template <int KB>
+__device__ __forceinline__ void load_rows(const float* __restrict__ x, int64_t P, int dim, int64_t row0, int lane,
+                                          float (&c)[KB][4]) {
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t r0 = row0 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int j = 0; j < KB; ++j) {
+        const int col = 8 * j + 2 * t;
+        c[j][0] = (r0 < P && col < dim) ? __ldg(x + r0 * dim + col) : 0.f;
+        c[j][1] = (r0 < P && col + 1 < dim) ? __ldg(x + r0 * dim + col + 1) : 0.f;
+        c[j][2] = (r1 < P && col < dim) ? __ldg(x + r1 * dim + col) : 0.f;
+        c[j][3] = (r1 < P && col + 1 < dim) ? __ldg(x + r1 * dim + col + 1) : 0.f;
+    }
+}
+
+template <int KB>
+__device__ __forceinline__ void store_rows(float* __restrict__ y, int64_t P, int dim, int64_t row0, int lane,
+                                           const float (&c)[KB][4]) {
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t r0 = row0 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int j = 0; j < KB; ++j) {
+        const int col = 8 * j + 2 * t;
+        if (r0 < P && col < dim) y[r0 * dim + col] = c[j][0];
+        if (r0 < P && col + 1 < dim) y[r0 * dim + col + 1] = c[j][1];
+        if (r1 < P && col < dim) y[r1 * dim + col] = c[j][2];
+        if (r1 < P && col + 1 < dim) y[r1 * dim + col + 1] = c[j][3];
+    }
+}
+
+template <int KB>
+__device__ __forceinline__ uint32_t relu_inplace(float (&c)[KB][4]) {
+    uint32_t mask = 0;
+#pragma unroll
+    for (int j = 0; j < KB; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (c[j][q] > 0.f)
+                mask |= 1u << (4 * j + q);
+            else
+                c[j][q] = 0.f;
+        }
+    return mask;
+}
+template <int KB>
+__device__ __forceinline__ void apply_mask(float (&c)[KB][4], uint32_t mask) {
+#pragma unroll
+    for (int j = 0; j < KB; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (!((mask >> (4 * j + q)) & 1u)) c[j][q] = 0.f;
+}
+
+// shared-memory carve-up shared by forward and backward
+template <class S, int PREC>
+struct Smem {
+    using E = typename Elem<PREC>::type;
+    static constexpr size_t w0 = (size_t)S::N0 * stride_of<PREC>(S::K0);
+    static constexpr size_t wmid = (size_t)S::H * stride_of<PREC>(S::H);
+    static constexpr size_t wlast = S::NHID > 0 ? (size_t)S::NOUT * stride_of<PREC>(S::H) : 0;
+    static constexpr size_t w_elems = w0 + S::NMID * wmid + wlast;
+    static constexpr size_t bias_floats = S::N0 + S::NMID * S::H + (S::NHID > 0 ? S::NOUT : 0);
+    static constexpr size_t fwd_bytes = ((w_elems * sizeof(E) + 15) / 16) * 16 + bias_floats * sizeof(float);
+    // backward adds the staged activations (inputs of every layer) and one dZ tile
+    static constexpr size_t act0 = (size_t)kTile * stride_of<PREC>(S::K0);
+    static constexpr size_t acth = (size_t)kTile * stride_of<PREC>(S::H);
+    static constexpr int maxN = S::NOUT > S::H ? S::NOUT : S::H;
+    static constexpr size_t dz = (size_t)kTile * stride_of<PREC>(maxN);
+    static constexpr size_t bwd_bytes = ((fwd_bytes + 15) / 16) * 16 + (act0 + S::NHID * acth + dz) * sizeof(E);
+};
+
+template <class S, int PREC>
+struct Weights {
+    using E = typename Elem<PREC>::type;
+    E* w0;
+    E* wmid;   // NMID consecutive [H][stride(H)] blocks
+    E* wlast;
+    float* b0;
+    float* bmid;
+    float* blast;
+    unsigned char* end;
+
+    __device__ __forceinline__ void carve(unsigned char* base) {
+        using SM = Smem<S, PREC>;
+        w0 = reinterpret_cast<E*>(base);
+        wmid = w0 + SM::w0;
+        wlast = wmid + S::NMID * SM::wmid;
+        float* bias = reinterpret_cast<float*>(base + ((SM::w_elems * sizeof(E) + 15) / 16) * 16);
+        b0 = bias;
+        bmid = b0 + S::N0;
+        blast = bmid + S::NMID * S::H;
+        end = base + ((SM::fwd_bytes + 15) / 16) * 16;
+    }
+    __device__ __forceinline__ void load(const MlpArgs& a, int tid) {
+        if constexpr (S::NHID == 0) {
+            load_weights<S::K0, S::NOUT, PREC>(a.W[0], a.b[0], a.out_dim, a.in_dim, w0, b0, tid, kThreads);
+        } else {
+            load_weights<S::K0, S::H, PREC>(a.W[0], a.b[0], S::H, a.in_dim, w0, b0, tid, kThreads);
+#pragma unroll
+            for (int m = 0; m < S::NMID; ++m)
+                load_weights<S::H, S::H, PREC>(a.W[1 + m], a.b[1 + m], S::H, S::H, wmid + m * Smem<S, PREC>::wmid,
+                                               bmid + m * S::H, tid, kThreads);
+            load_weights<S::H, S::NOUT, PREC>(a.W[S::NHID], a.b[S::NHID], a.out_dim, S::H, wlast, blast, tid, kThreads);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+template <class S, int PREC>
+__global__ void __launch_bounds__(kThreads) mlp_fwd_kernel(MlpArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Weights<S, PREC> w;
+    w.carve(smem_raw);
+    w.load(a, threadIdx.x);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ntiles = (a.P + kTile - 1) / kTile;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t row0 = tile * kTile + warp * 16;
+        if (row0 >= a.P) continue;
+        float in[S::K0 / 8][4];
+        load_rows<S::K0 / 8>(a.x, a.P, a.in_dim, row0, lane, in);
+        float out[S::NOUT / 8][4];
+        if constexpr (S::NHID == 0) {
+            layer_forward<S::K0, S::NOUT, PREC>(in, w.w0, w.b0, out, lane);
+        } else {
+            float h[S::H / 8][4];
+            layer_forward<S::K0, S::H, PREC>(in, w.w0, w.b0, h, lane);
+            relu_inplace<S::H / 8>(h);
+#pragma unroll
+            for (int m = 0; m < S::NMID; ++m) {
+                float h2[S::H / 8][4];
+                layer_forward<S::H, S::H, PREC>(h, w.wmid + m * Smem<S, PREC>::wmid, w.bmid + m * S::H, h2, lane);
+                relu_inplace<S::H / 8>(h2);
+#pragma unroll
+                for (int j = 0; j < S::H / 8; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) h[j][q] = h2[j][q];
+            }
+            layer_forward<S::H, S::NOUT, PREC>(h, w.wlast, w.blast, out, lane);
+        }
+        if (a.out_act == PS_ACT_SIGMOID) {
+#pragma unroll
+            for (int j = 0; j < S::NOUT / 8; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) out[j][q] = sigmoidf(out[j][q]);
+        } else if (a.out_act == PS_ACT_RELU) {
+            relu_inplace<S::NOUT / 8>(out);
+        }
+        store_rows<S::NOUT / 8>(a.y, a.P, a.out_dim, row0, lane, out);
+    }
+}
+
+// Accumulate one layer's weight/bias gradient from the staged tiles.
+//   dZs [kTile][stride(N)] (this layer's pre-activation gradient), Acts [kTile][stride(K)] (this layer's input)
+template <int K, int N, int PREC, int MAXB>
+__device__ __forceinline__ void accumulate_dw(const typename Elem<PREC>::type* dZs, const typename Elem<PREC>::type* Acts,
+                                              float (&acc)[MAXB][2][4], float& db, int warp, int lane, int tid) {
+    constexpr int KBLK = K / 16, NBLK = (N / 16) * KBLK;
+#pragma unroll
+    for (int i = 0; i < MAXB; ++i) {
+        const int b = warp + i * kWarps;
+        if (b < NBLK) {
+            const int n0 = (b / KBLK) * 16, f0 = (b % KBLK) * 16;
+            dw_block<kTile, PREC>(dZs, stride_of<PREC>(N), n0, Acts, stride_of<PREC>(K), f0, acc[i], lane);
+        }
+    }
+    if (tid < N) {
+        constexpr int SZ = stride_of<PREC>(N);
+        float s = 0.f;
+#pragma unroll 8
+        for (int p = 0; p < kTile; ++p) {
+            if constexpr (PREC == kBF16)
+                s += __bfloat162float(dZs[p * SZ + tid]);
+            else
+                s += dZs[p * SZ + tid];
+        }
+        db += s;
+    }
+}
+
+template <int K, int N, int MAXB>
+__device__ __forceinline__ void flush_dw(float* __restrict__ dW, float* __restrict__ dbg, int n_real, int k_real,
+                                         const float (&acc)[MAXB][2][4], float db, int warp, int lane, int tid) {
+    constexpr int KBLK = K / 16, NBLK = (N / 16) * KBLK;
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int i = 0; i < MAXB; ++i) {
+        const int b = warp + i * kWarps;
+        if (b < NBLK) {
+            const int n0 = (b / KBLK) * 16, f0 = (b % KBLK) * 16;
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int n = n0 + g + (q >> 1) * 8, k = f0 + 8 * nb + 2 * t + (q & 1);
+                    if (n < n_real && k < k_real && acc[i][nb][q] != 0.f) atomicAdd(dW + (size_t)n * k_real + k, acc[i][nb][q]);
+                }
+        }
+    }
+    if (dbg && tid < n_real) atomicAdd(dbg + tid, db);
+}
+
+template <int K, int N>
+constexpr int max_blocks() {
+    return ((N / 16) * (K / 16) + kWarps - 1) / kWarps;
+}
+
+template <class S, int PREC>
+__global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(MlpArgs a) {
+    using E = typename Elem<PREC>::type;
+    using SM = Smem<S, PREC>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Weights<S, PREC> w;
+    w.carve(smem_raw);
+    E* acts0 = reinterpret_cast<E*>(w.end);
+    E* actsh = acts0 + SM::act0;              // NHID tiles [kTile][stride(H)]
+    E* dZs = actsh + S::NHID * SM::acth;
+    w.load(a, threadIdx.x);
+    __syncthreads();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    constexpr int MB0 = max_blocks<S::K0, S::N0>();
+    constexpr int MBM = max_blocks<S::H, S::H>();
+    constexpr int MBL = S::NHID > 0 ? max_blocks<S::H, S::NOUT>() : 1;
+    float acc0[MB0][2][4] = {};
+    float accm[S::NMID > 0 ? S::NMID : 1][MBM][2][4] = {};
+    float accl[MBL][2][4] = {};
+    float db0 = 0.f, dbl = 0.f, dbm[S::NMID > 0 ? S::NMID : 1] = {};
+
+    const int64_t ntiles = (a.P + kTile - 1) / kTile;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t row0 = tile * kTile + warp * 16;
+        const int srow = warp * 16;
+        // ---- recompute the forward, staging every layer's input --------------------------------
+        float in[S::K0 / 8][4];
+        load_rows<S::K0 / 8>(a.x, a.P, a.in_dim, row0, lane, in);
+        stage_rows<S::K0, PREC>(in, acts0, srow, lane);
+        float dz[S::NOUT / 8][4];
+        uint32_t mask[S::NHID > 0 ? S::NHID : 1] = {};
+        {
+            float out[S::NOUT / 8][4];
+            if constexpr (S::NHID == 0) {
+                layer_forward<S::K0, S::NOUT, PREC>(in, w.w0, w.b0, out, lane);
+            } else {
+                float h[S::H / 8][4];
+                layer_forward<S::K0, S::H, PREC>(in, w.w0, w.b0, h, lane);
+                mask[0] = relu_inplace<S::H / 8>(h);
+                stage_rows<S::H, PREC>(h, actsh, srow, lane);
+#pragma unroll
+                for (int m = 0; m < S::NMID; ++m) {
+                    float h2[S::H / 8][4];
+                    layer_forward<S::H, S::H, PREC>(h, w.wmid + m * SM::wmid, w.bmid + m * S::H, h2, lane);
+                    mask[m + 1] = relu_inplace<S::H / 8>(h2);
+                    stage_rows<S::H, PREC>(h2, actsh + (m + 1) * SM::acth, srow, lane);
+#pragma unroll
+                    for (int j = 0; j < S::H / 8; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) h[j][q] = h2[j][q];
+                }
+                layer_forward<S::H, S::NOUT, PREC>(h, w.wlast, w.blast, out, lane);
+            }
+            // ---- gradient w.r.t. the last pre-activation ----------------------------------------
+            load_rows<S::NOUT / 8>(a.dy, a.P, a.out_dim, row0, lane, dz);
+            if (a.out_act == PS_ACT_SIGMOID) {
+#pragma unroll
+                for (int j = 0; j < S::NOUT / 8; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float y = sigmoidf(out[j][q]);
+                        dz[j][q] *= y * (1.f - y);
+                    }
+            } else if (a.out_act == PS_ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < S::NOUT / 8; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (!(out[j][q] > 0.f)) dz[j][q] = 0.f;
+            }
+        }
+        // ---- walk the layers backwards ----------------------------------------------------------
+        if constexpr (S::NHID == 0) {
+            stage_rows<S::NOUT, PREC>(dz, dZs, srow, lane);
+            __syncthreads();
+            accumulate_dw<S::K0, S::NOUT, PREC, MB0>(dZs, acts0, acc0, db0, warp, lane, tid);
+            if (a.dx) {
+                float da[S::K0 / 8][4];
+                layer_backward_input<S::K0, S::NOUT, PREC>(dz, w.w0, da, lane);
+                store_rows<S::K0 / 8>(a.dx, a.P, a.in_dim, row0, lane, da);
+            }
+            __syncthreads();
+        } else {
+            float dzh[S::H / 8][4];
+            stage_rows<S::NOUT, PREC>(dz, dZs, srow, lane);
+            __syncthreads();
+            accumulate_dw<S::H, S::NOUT, PREC, MBL>(dZs, actsh + (S::NHID - 1) * SM::acth, accl, dbl, warp, lane, tid);
+            layer_backward_input<S::H, S::NOUT, PREC>(dz, w.wlast, dzh, lane);
+            apply_mask<S::H / 8>(dzh, mask[S::NHID - 1]);
+            __syncthreads();
+#pragma unroll
+            for (int m = S::NMID - 1; m >= 0; --m) {
+                stage_rows<S::H, PREC>(dzh, dZs, srow, lane);
+                __syncthreads();
+                accumulate_dw<S::H, S::H, PREC, MBM>(dZs, actsh + m * SM::acth, accm[m], dbm[m], warp, lane, tid);
+                float da[S::H / 8][4];
+                layer_backward_input<S::H, S::H, PREC>(dzh, w.wmid + m * SM::wmid, da, lane);
+                apply_mask<S::H / 8>(da, mask[m]);
+#pragma unroll
+                for (int j = 0; j < S::H / 8; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dzh[j][q] = da[j][q];
+                __syncthreads();
+            }
+            stage_rows<S::H, PREC>(dzh, dZs, srow, lane);
+            __syncthreads();
+            accumulate_dw<S::K0, S::H, PREC, MB0>(dZs, acts0, acc0, db0, warp, lane, tid);
+            if (a.dx) {
+                float da[S::K0 / 8][4];
+                layer_backward_input<S::K0, S::H, PREC>(dzh, w.w0, da, lane);
+                store_rows<S::K0 / 8>(a.dx, a.P, a.in_dim, row0, lane, da);
+            }
+            __syncthreads();
+        }
+    }
+    // ---- flush the per-CTA partial weight gradients ------------------------------------------------
+    if constexpr (S::NHID == 0) {
+        flush_dw<S::K0, S::NOUT, MB0>(a.dW[0], a.db[0], a.out_dim, a.in_dim, acc0, db0, warp, lane, tid);
+    } else {
+        flush_dw<S::K0, S::H, MB0>(a.dW[0], a.db[0], S::H, a.in_dim, acc0, db0, warp, lane, tid);
+#pragma unroll
+        for (int m = 0; m < S::NMID; ++m)
+            flush_dw<S::H, S::H, MBM>(a.dW[1 + m], a.db[1 + m], S::H, S::H, accm[m], dbm[m], warp, lane, tid);
+        flush_dw<S::H, S::NOUT, MBL>(a.dW[S::NHID], a.db[S::NHID], a.out_dim, S::H, accl, dbl, warp, lane, tid);
+    }
+}
+
+// host-side launchers -------------------------------------------------------------------------------
+template <class S, int PREC>
+int launch_fwd(const MlpArgs& a, cudaStream_t stream) {
+    constexpr size_t smem = Smem<S, PREC>::fwd_bytes;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(mlp_fwd_kernel<S, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess) {
+            set_error("mlp_fwd: cannot reserve %zu bytes of shared memory", smem);
+            return 2;
+        }
+        configured = true;
+    }
+    const int64_t ntiles = (a.P + kTile - 1) / kTile;
+    const int ctas_per_sm = smem > 100 * 1024 ? 1 : 2;
+    const int grid = (int)(ntiles < (int64_t)kNumSMs * ctas_per_sm ? ntiles : (int64_t)kNumSMs * ctas_per_sm);
+    mlp_fwd_kernel<S, PREC><<<grid, kThreads, smem, stream>>>(a);
+    return check_launch("mlp_fwd");
+}
+
+template <class S, int PREC>
+int launch_bwd(const MlpArgs& a, cudaStream_t stream) {
+    constexpr size_t smem = Smem<S, PREC>::bwd_bytes;
+    static_assert(smem <= 227 * 1024, "backward tile does not fit in shared memory");
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(mlp_bwd_kernel<S, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess) {
+            set_error("mlp_bwd: cannot reserve %zu bytes of shared memory", smem);
+            return 2;
+        }
+        configured = true;
+    }
+    const int64_t ntiles = (a.P + kTile - 1) / kTile;
+    const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+    mlp_bwd_kernel<S, PREC><<<grid, kThreads, smem, stream>>>(a);
+    return check_launch("mlp_bwd");
+}
+
+}  // namespace mma
+}  // namespace ps

@@ -1,0 +1,127 @@
+"""Nearest-centroid routers over sub-fields (reference: fields/PreSight/ingp_field_ms.py,
+prop_density_field_ms.py, sky_field_ms.py).
+
+Routing runs in `ps_nearest_centroid`; points are then bucketed per sub-field with one device-side sort
+(no per-field `torch.any` host sync as in ingp_field_ms.py:103) and a single bincount read-back.
+State-dict layout (`centroids`, `fields.{i}.*`) matches the reference.
+"""
+from __future__ import annotations
+
+from copy import deepcopy
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from .. import ops
+from ..cameras.rays import RaySamples
+from .ingp_field import FieldHeadNames, iNGPField
+from .prop_density_field import PropNetDensityField
+from .sky_field import SkyField
+
+
+def _route(points: Tensor, centroids: Tensor, n_fields: int):
+    """-> (order [P] permutation grouping points by field, counts list[int])."""
+    assign = ops.nearest_centroid(points, centroids).long()
+    order = torch.argsort(assign, stable=True)
+    counts = torch.bincount(assign, minlength=n_fields).tolist()   # one host sync for all fields
+    return order, counts
+
+
+def _dispatch(points: Tensor, centroids: Tensor, n_fields: int, per_field: Callable, extras: Sequence[Optional[Tensor]] = ()):
+    """Run `per_field(i, pts_i, *extras_i) -> dict` on every non-empty bucket and scatter the results back."""
+    if n_fields == 1:
+        return per_field(0, points, *extras)
+    order, counts = _route(points, centroids, n_fields)
+    sorted_pts = points[order]
+    sorted_extras = [None if e is None else e[order] for e in extras]
+    pieces: Dict[str, List[Tensor]] = {}
+    start = 0
+    for i, c in enumerate(counts):
+        if c == 0:
+            continue
+        sub = per_field(i, sorted_pts[start:start + c], *[None if e is None else e[start:start + c] for e in sorted_extras])
+        for k, v in sub.items():
+            pieces.setdefault(k, []).append(v)
+        start += c
+    inv = torch.empty_like(order)
+    inv[order] = torch.arange(order.numel(), device=order.device)
+    return {k: torch.cat(v, dim=0)[inv] for k, v in pieces.items()}
+
+
+class iNGPFieldMS(nn.Module):
+    def __init__(self, fields: List[iNGPField], centroids: Tensor) -> None:
+        super().__init__()
+        self.register_buffer("centroids", deepcopy(centroids))
+        self.fields = nn.ModuleList(fields)
+
+    def forward(self, ray_samples: RaySamples, appearance_embedding: Optional[Tensor]) -> Dict[str, Tensor]:
+        """ingp_field_ms.py:80-126."""
+        positions = ray_samples.frustums.get_positions()
+        output_shape = positions.shape[:-1]
+        positions = positions.reshape(-1, 3)
+        directions = ray_samples.frustums.directions.expand(*output_shape, 3).reshape(-1, 3)
+        app = None if appearance_embedding is None else appearance_embedding.flatten(0, -2)
+
+        def run(i, p, d, a):
+            f: iNGPField = self.fields[i]
+            density, emb = f.density_fn(p)
+            out = f.get_outputs(d, density_embedding=emb, appearance_embedding=a)
+            out[FieldHeadNames.DENSITY] = density
+            return out
+        res = _dispatch(positions, self.centroids, len(self.fields), run, (directions, app))
+        return {k: v.reshape(*output_shape, -1) for k, v in res.items()}
+
+    def density_fn(self, positions: Tensor) -> Tuple[Tensor, Tensor]:
+        """ingp_field_ms.py:128-153."""
+        output_shape = positions.shape[:-1]
+        flat = positions.reshape(-1, 3)
+
+        def run(i, p):
+            density, emb = self.fields[i].density_fn(p)
+            return {"density": density, "embedding": emb}
+        res = _dispatch(flat, self.centroids, len(self.fields), run)
+        return res["density"].reshape(*output_shape, 1), res["embedding"].reshape(*output_shape, -1)
+
+    def get_density(self, ray_samples: RaySamples):
+        return self.density_fn(ray_samples.frustums.get_positions())
+
+    def semantic_fn(self, positions: Tensor) -> Tensor:
+        """ingp_field_ms.py:161-185."""
+        output_shape = positions.shape[:-1]
+        res = _dispatch(positions.reshape(-1, 3), self.centroids, len(self.fields),
+                        lambda i, p: {"semantics": self.fields[i].semantic_fn(p)})
+        return res["semantics"].reshape(*output_shape, -1)
+
+
+class PropNetDensityFieldMS(nn.Module):
+    def __init__(self, fields: List[PropNetDensityField], centroids: Tensor) -> None:
+        super().__init__()
+        self.register_buffer("centroids", deepcopy(centroids))
+        self.fields = nn.ModuleList(fields)
+
+    def get_density(self, ray_samples: RaySamples) -> Tuple[Tensor, None]:
+        return self.density_fn(ray_samples.frustums.get_positions()), None
+
+    def density_fn(self, positions: Tensor) -> Tensor:
+        """prop_density_field_ms.py:86-105."""
+        output_shape = positions.shape[:-1]
+        res = _dispatch(positions.reshape(-1, 3), self.centroids, len(self.fields),
+                        lambda i, p: {"density": self.fields[i].density_fn(p)})
+        return res["density"].reshape(*output_shape, 1)
+
+
+class SkyFieldMS(nn.Module):
+    def __init__(self, fields: List[SkyField], centroids: Tensor) -> None:
+        super().__init__()
+        self.register_buffer("centroids", deepcopy(centroids))
+        self.fields = nn.ModuleList(fields)
+
+    def forward(self, ray_samples: RaySamples, appearance_embedding: Optional[Tensor]) -> Dict[str, Tensor]:
+        """sky_field_ms.py:81-117 (routed by ray origin)."""
+        origins = ray_samples.frustums.origins[:, 0, :]
+        directions = ray_samples.frustums.directions[:, 0, :]
+        app = None if appearance_embedding is None else appearance_embedding[:, 0, :]
+        res = _dispatch(origins.contiguous(), self.centroids, len(self.fields),
+                        lambda i, o, d, a: self.fields[i].get_outputs(d, a), (directions, app))
+        return {k: v.contiguous() for k, v in res.items()}

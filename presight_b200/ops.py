@@ -1,0 +1,351 @@
+"""Autograd-aware Python wrappers over the C-ABI kernels (libpresight_b200.so).
+
+Every function here allocates outputs with torch, passes raw device pointers + the current CUDA stream
+through ctypes, and fails loudly when the library is missing or the tensors are not on a CUDA device.
+There is no CPU / PyTorch fallback.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import call, host_floats, host_ints, host_ptrs, ptr, stream
+
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+PREC_TF32X3, PREC_BF16 = 0, 1
+
+
+def _f32c(t: Tensor) -> Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# kernel #1: hash encoding
+# --------------------------------------------------------------------------------------------------
+class _HashEncode(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x01: Tensor, table: Tensor, scalings: Tuple[float, ...], log2_T: int):
+        x = _f32c(x01.detach()).view(-1, 3)
+        tab = table.detach()
+        assert tab.dtype == torch.float32 and tab.is_contiguous()
+        L, F = len(scalings), tab.shape[1]
+        P = x.shape[0]
+        out = torch.empty(P, L * F, device=x.device, dtype=torch.float32)
+        call("ps_hash_fwd", ptr(x), P, ptr(tab), host_floats(scalings), L, F, log2_T, ptr(out), stream())
+        ctx.save_for_backward(x, table)
+        ctx.meta = (scalings, log2_T, x01.shape, x01.requires_grad)
+        return out.view(*x01.shape[:-1], L * F)
+
+    @staticmethod
+    def backward(ctx, dout: Tensor):
+        x, table = ctx.saved_tensors
+        scalings, log2_T, xshape, need_dx = ctx.meta
+        L, F = len(scalings), table.shape[1]
+        P = x.shape[0]
+        dout = _f32c(dout).view(P, L * F)
+        dtable = torch.zeros_like(table) if ctx.needs_input_grad[1] else None
+        dx = torch.zeros_like(x) if (need_dx and ctx.needs_input_grad[0]) else None
+        if dtable is None and dx is None:
+            return None, None, None, None
+        if dtable is None:  # the kernel always scatters; give it a scratch target
+            dtable = torch.zeros_like(table)
+        call("ps_hash_bwd", ptr(x), P, ptr(table.detach()), host_floats(scalings), L, F, log2_T, ptr(dout),
+             ptr(dtable), ptr(dx), stream())
+        return (dx.view(xshape) if dx is not None else None), (dtable if ctx.needs_input_grad[1] else None), None, None
+
+
+def hash_encode(x01: Tensor, table: Tensor, scalings: Sequence[float], log2_T: int) -> Tensor:
+    """[..., 3] -> [..., L*F]; replaces HashEncoding.pytorch_fwd (encodings.py:343-384)."""
+    return _HashEncode.apply(x01, table, tuple(float(s) for s in scalings), int(log2_T))
+
+
+def hash_indices(x01: Tensor, scalings: Sequence[float], log2_T: int) -> Tuple[Tensor, Tensor]:
+    """Parity probe: ([P,L,8] int64 rows incl. level offset, [P,L,3] offsets)."""
+    x = _f32c(x01).view(-1, 3)
+    P, L = x.shape[0], len(scalings)
+    idx = torch.empty(P, L, 8, device=x.device, dtype=torch.int64)
+    off = torch.empty(P, L, 3, device=x.device, dtype=torch.float32)
+    call("ps_hash_indices", ptr(x), P, host_floats(scalings), L, int(log2_T), ptr(idx), ptr(off), stream())
+    return idx, off
+
+
+# --------------------------------------------------------------------------------------------------
+# position prologue
+# --------------------------------------------------------------------------------------------------
+def normalize_positions(pos: Tensor, aabb: Sequence[float], contract: bool = True) -> Tuple[Tensor, Tensor]:
+    """World positions [...,3] -> (unit-cube positions, uint8 selector [...]); no gradient
+    (ingp_field.py:169-177).  `aabb` = 6 host floats (min xyz, max xyz)."""
+    p = _f32c(pos.detach()).view(-1, 3)
+    P = p.shape[0]
+    x01 = torch.empty_like(p)
+    sel = torch.empty(P, device=p.device, dtype=torch.uint8)
+    call("ps_normalize_positions", ptr(p), P, host_floats(aabb), 1 if contract else 0, ptr(x01), ptr(sel), stream())
+    return x01.view(pos.shape), sel.view(pos.shape[:-1])
+
+
+def sample_positions(origins: Tensor, dirs: Tensor, eu_bins: Tensor) -> Tensor:
+    """Frustum mid-points [N,S,3] (cameras/rays.py:49-58)."""
+    N, S = eu_bins.shape[0], eu_bins.shape[1] - 1
+    pos = torch.empty(N, S, 3, device=eu_bins.device, dtype=torch.float32)
+    call("ps_sample_positions", ptr(_f32c(origins)), ptr(_f32c(dirs)), ptr(_f32c(eu_bins)), N, S, ptr(pos), stream())
+    return pos
+
+
+def sh4(dirs: Tensor, mapped: bool = False) -> Tensor:
+    """[...,3] -> 16 SH components (math.py:27-74); no gradient.  mapped=False: raw directions, the kernel
+    applies the (d+1)/2 mapping of base_field.py:136-142; mapped=True: input already mapped."""
+    d = _f32c(dirs.detach()).view(-1, 3)
+    out = torch.empty(d.shape[0], 16, device=d.device, dtype=torch.float32)
+    call("ps_sh4", ptr(d), d.shape[0], 1 if mapped else 0, ptr(out), stream())
+    return out.view(*dirs.shape[:-1], 16)
+
+
+def nearest_centroid(pos: Tensor, centroids: Tensor) -> Tensor:
+    """[P,3],[nf,3] -> int32 [P] (ingp_field_ms.py:97)."""
+    p = _f32c(pos.detach()).view(-1, 3)
+    c = _f32c(centroids)
+    out = torch.empty(p.shape[0], device=p.device, dtype=torch.int32)
+    call("ps_nearest_centroid", ptr(p), p.shape[0], ptr(c), c.shape[0], ptr(out), stream())
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# kernel #2: fused MLP, trunc_exp
+# --------------------------------------------------------------------------------------------------
+class _Mlp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, out_act: int, precision: int, n_layers: int, *params: Tensor):
+        ws, bs = params[:n_layers], params[n_layers:]
+        xs = _f32c(x.detach())
+        lead = xs.shape[:-1]
+        x2 = xs.view(-1, xs.shape[-1])
+        dims = [x2.shape[1]] + [w.shape[0] for w in ws]
+        for i, w in enumerate(ws):
+            assert w.shape[1] == dims[i], f"layer {i}: weight {tuple(w.shape)} does not match input width {dims[i]}"
+        y = torch.empty(x2.shape[0], dims[-1], device=x2.device, dtype=torch.float32)
+        wd = [w.detach().contiguous() for w in ws]
+        bd = [None if b is None else b.detach().contiguous() for b in bs]
+        call("ps_mlp_fwd", ptr(x2), x2.shape[0], host_ptrs(wd), host_ptrs(bd), host_ints(dims), n_layers, out_act,
+             precision, ptr(y), stream())
+        ctx.save_for_backward(x2, *wd, *[b for b in bd if b is not None])
+        ctx.meta = (out_act, precision, n_layers, dims, [b is not None for b in bd], x.shape)
+        return y.view(*lead, dims[-1])
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        out_act, precision, n_layers, dims, has_b, xshape = ctx.meta
+        saved = ctx.saved_tensors
+        x2, wd = saved[0], list(saved[1:1 + n_layers])
+        rest = list(saved[1 + n_layers:])
+        bd = [rest.pop(0) if hb else None for hb in has_b]
+        dy2 = _f32c(dy).view(-1, dims[-1])
+        dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+        dW = [torch.zeros_like(w) for w in wd]
+        db = [None if b is None else torch.zeros_like(b) for b in bd]
+        call("ps_mlp_bwd", ptr(x2), None, ptr(dy2), x2.shape[0], host_ptrs(wd), host_ptrs(bd), host_ints(dims),
+             n_layers, out_act, precision, ptr(dx), host_ptrs(dW), host_ptrs(db), stream())
+        return (None if dx is None else dx.view(xshape), None, None, None, *dW, *db)
+
+
+def mlp(x: Tensor, weights: Sequence[Tensor], biases: Sequence[Optional[Tensor]], out_act: int = ACT_NONE,
+        precision: int = PREC_BF16) -> Tensor:
+    """Linear+ReLU stack with optional output activation (mlp.py:157-174) in ONE kernel per direction."""
+    return _Mlp.apply(x, int(out_act), int(precision), len(weights), *weights, *biases)
+
+
+class _TruncExp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, sel: Optional[Tensor]):
+        xs = _f32c(x.detach())
+        y = torch.empty_like(xs)
+        s = None if sel is None else sel.contiguous()
+        call("ps_trunc_exp_fwd", ptr(xs), ptr(s), xs.numel(), 1, ptr(y), stream())
+        ctx.save_for_backward(xs)
+        ctx.sel = s
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        (xs,) = ctx.saved_tensors
+        dx = torch.empty_like(xs)
+        call("ps_trunc_exp_bwd", ptr(xs), ptr(ctx.sel), ptr(_f32c(dy)), xs.numel(), 1, ptr(dx), 1, stream())
+        return dx, None
+
+
+def trunc_exp(x: Tensor, selector: Optional[Tensor] = None) -> Tensor:
+    """exp(x) * selector with the clamped backward of activations.py:28-41 (selector: uint8, same numel)."""
+    return _TruncExp.apply(x, selector)
+
+
+# --------------------------------------------------------------------------------------------------
+# kernel #3: samplers
+# --------------------------------------------------------------------------------------------------
+def spaced_bins(nears: Tensor, fars: Tensor, num_samples: int, thr: float, t_rand: Optional[Tensor]):
+    """-> (spacing bins [N,S+1], euclidean bins [N,S+1]); ray_samplers.py:98-128 with PreSight's spacing."""
+    n = _f32c(nears).view(-1)
+    f = _f32c(fars).view(-1)
+    N = n.shape[0]
+    lin = torch.linspace(0.0, 1.0, num_samples + 1, device=n.device)
+    sp = torch.empty(N, num_samples + 1, device=n.device, dtype=torch.float32)
+    eu = torch.empty_like(sp)
+    tr = None if t_rand is None else _f32c(t_rand).view(-1)
+    call("ps_spaced_bins", ptr(n), ptr(f), ptr(lin), ptr(tr), N, num_samples, float(thr), ptr(sp), ptr(eu), stream())
+    return sp, eu
+
+
+def pdf_resample(weights: Tensor, sp_in: Tensor, num_samples: int, rand: Optional[Tensor], nears: Tensor, fars: Tensor,
+                 thr: float, padding: float = 0.01, eps: float = 1e-5, anneal: float = 1.0, probes: bool = False):
+    """Inverse-CDF resampling (ray_samplers.py:305-362).  weights [N,S_in], sp_in [N,S_in+1].
+    -> (sp_out, eu_out[, inds, cdf, u])."""
+    w = _f32c(weights.detach())
+    N, S_in = w.shape
+    nb = num_samples + 1
+    dev = w.device
+    u_base = torch.linspace(0.0, 1.0 - (1.0 / nb), steps=nb, device=dev)
+    sp_out = torch.empty(N, nb, device=dev, dtype=torch.float32)
+    eu_out = torch.empty_like(sp_out)
+    inds = torch.empty(N, nb, device=dev, dtype=torch.int64) if probes else None
+    cdf = torch.empty(N, S_in + 1, device=dev, dtype=torch.float32) if probes else None
+    u = torch.empty(N, nb, device=dev, dtype=torch.float32) if probes else None
+    r = None if rand is None else _f32c(rand).view(-1)
+    call("ps_pdf_resample", ptr(w), ptr(_f32c(sp_in.detach())), ptr(u_base), ptr(r), ptr(_f32c(nears).view(-1)),
+         ptr(_f32c(fars).view(-1)), N, S_in, num_samples, float(padding), float(eps), float(anneal), float(thr),
+         ptr(sp_out), ptr(eu_out), ptr(inds), ptr(cdf), ptr(u), stream())
+    return (sp_out, eu_out, inds, cdf, u) if probes else (sp_out, eu_out)
+
+
+def searchsorted_right(cdf: Tensor, u: Tensor) -> Tensor:
+    c, v = _f32c(cdf), _f32c(u)
+    out = torch.empty(v.shape, device=v.device, dtype=torch.int64)
+    call("ps_searchsorted_right", ptr(c), ptr(v), c.shape[0], c.shape[1], v.shape[1], ptr(out), stream())
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# kernel #4: compositing
+# --------------------------------------------------------------------------------------------------
+class _Weights(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, deltas: Tensor, density: Tensor):
+        d, s = _f32c(deltas.detach()), _f32c(density.detach())
+        N, S = d.shape[0], d.shape[1]
+        w = torch.empty_like(s)
+        call("ps_weights_fwd", ptr(d), ptr(s), N, S, ptr(w), stream())
+        ctx.save_for_backward(d, s)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw: Tensor):
+        d, s = ctx.saved_tensors
+        ds = torch.empty_like(s)
+        call("ps_weights_bwd", ptr(d), ptr(s), ptr(_f32c(dw)), d.shape[0], d.shape[1], ptr(ds), stream())
+        return None, ds
+
+
+def get_weights(deltas: Tensor, density: Tensor) -> Tensor:
+    """[N,S,1] x [N,S,1] -> [N,S,1] (cameras/rays.py:128-150)."""
+    return _Weights.apply(deltas, density)
+
+
+class _Render(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weights: Tensor, values: Optional[Tensor]):
+        w = _f32c(weights.detach())
+        N, S = w.shape[0], w.shape[1]
+        v = None if values is None else _f32c(values.detach())
+        C = 1 if v is None else v.shape[-1]
+        out = torch.empty(N, C, device=w.device, dtype=torch.float32)
+        call("ps_render_fwd", ptr(w), ptr(v), N, S, C, ptr(out), stream())
+        ctx.save_for_backward(w, *(() if v is None else (v,)))
+        ctx.has_v = v is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: Tensor):
+        w = ctx.saved_tensors[0]
+        v = ctx.saved_tensors[1] if ctx.has_v else None
+        N, S = w.shape[0], w.shape[1]
+        C = 1 if v is None else v.shape[-1]
+        dw = torch.zeros_like(w)
+        dv = torch.empty_like(v) if (v is not None and ctx.needs_input_grad[1]) else None
+        call("ps_render_bwd", ptr(w), ptr(v), ptr(_f32c(dout)), N, S, C, ptr(dw), ptr(dv), stream())
+        return dw, dv
+
+
+def render(weights: Tensor, values: Optional[Tensor]) -> Tensor:
+    """sum_s w[n,s] * v[n,s,:] -> [N,C]; values=None gives the accumulation (renderers.py:102-103,313)."""
+    return _Render.apply(weights, values)
+
+
+def depth_threshold(weights: Tensor, eu_bins: Tensor, threshold: float = 0.5) -> Tuple[Tensor, Tensor]:
+    """-> (depth [N,1], index [N,1] int64); renderers.py:352-362."""
+    w = _f32c(weights.detach())
+    N, S = w.shape[0], w.shape[1]
+    depth = torch.empty(N, 1, device=w.device, dtype=torch.float32)
+    index = torch.empty(N, 1, device=w.device, dtype=torch.int64)
+    call("ps_depth_threshold", ptr(w), ptr(_f32c(eu_bins)), N, S, float(threshold), ptr(depth), ptr(index), stream())
+    return depth, index
+
+
+class _Composite(torch.autograd.Function):
+    """One-pass compositing: weights, rgb, accumulation, expected depth (unclipped), threshold depth, semantics."""
+
+    @staticmethod
+    def forward(ctx, eu_bins: Tensor, density: Tensor, rgb: Optional[Tensor], sem: Optional[Tensor], threshold: float):
+        b, s = _f32c(eu_bins.detach()), _f32c(density.detach())
+        N, S = s.shape[0], s.shape[1]
+        dev = s.device
+        r = None if rgb is None else _f32c(rgb.detach())
+        m = None if sem is None else _f32c(sem.detach())
+        C = 0 if m is None else m.shape[-1]
+        w = torch.empty(N, S, device=dev, dtype=torch.float32)
+        rgb_out = torch.empty(N, 3, device=dev, dtype=torch.float32) if r is not None else None
+        acc = torch.empty(N, 1, device=dev, dtype=torch.float32)
+        dexp = torch.empty(N, 1, device=dev, dtype=torch.float32)
+        dthr = torch.empty(N, 1, device=dev, dtype=torch.float32)
+        sem_out = torch.empty(N, C, device=dev, dtype=torch.float32) if m is not None else None
+        tmm = torch.tensor([float("inf"), float("-inf")], device=dev, dtype=torch.float32)
+        call("ps_composite_fwd", ptr(b), ptr(s), ptr(r), ptr(m), N, S, C, float(threshold), ptr(w), ptr(rgb_out),
+             ptr(acc), ptr(dexp), ptr(dthr), ptr(sem_out), ptr(tmm), stream())
+        ctx.save_for_backward(b, s, acc, dexp, *(t for t in (r, m) if t is not None))
+        ctx.flags = (r is not None, m is not None, C)
+        ctx.mark_non_differentiable(dthr, tmm)
+        outs = (w, rgb_out if rgb_out is not None else torch.empty(0, device=dev), acc, dexp, dthr,
+                sem_out if sem_out is not None else torch.empty(0, device=dev), tmm)
+        return outs
+
+    @staticmethod
+    def backward(ctx, dw, drgb, dacc, ddexp, _dthr, dsem, _dtmm):
+        has_rgb, has_sem, C = ctx.flags
+        saved = list(ctx.saved_tensors)
+        b, s, acc, dexp = saved[:4]
+        rest = saved[4:]
+        r = rest.pop(0) if has_rgb else None
+        m = rest.pop(0) if has_sem else None
+        N, S = s.shape[0], s.shape[1]
+        d_density = torch.empty_like(s)
+        d_rgb = torch.empty_like(r) if (r is not None and ctx.needs_input_grad[2]) else None
+        d_sem = torch.empty_like(m) if (m is not None and ctx.needs_input_grad[3]) else None
+
+        def opt(t):
+            return None if t is None else _f32c(t)
+        call("ps_composite_bwd", ptr(b), ptr(s), ptr(r), ptr(m), None, ptr(acc), ptr(dexp), N, S, C,
+             ptr(opt(dw)), ptr(opt(drgb) if has_rgb else None), ptr(opt(dacc)), ptr(opt(ddexp)),
+             ptr(opt(dsem) if has_sem else None), ptr(d_density), ptr(d_rgb), ptr(d_sem), stream())
+        return None, d_density, d_rgb, d_sem, None
+
+
+def composite(eu_bins: Tensor, density: Tensor, rgb: Optional[Tensor], sem: Optional[Tensor], threshold: float = 0.5):
+    """eu_bins [N,S+1], density [N,S], rgb [N,S,3], sem [N,S,C] ->
+    (weights [N,S], rgb [N,3], acc [N,1], depth_expected_unclipped [N,1], depth_threshold [N,1], sem [N,C],
+     tminmax [2])."""
+    return _Composite.apply(eu_bins, density, rgb, sem, float(threshold))
+
+
+def launch_count() -> int:
+    return _lib.launch_count()

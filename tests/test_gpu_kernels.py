@@ -1,0 +1,348 @@
+"""GPU parity tests: every CUDA kernel (through the C-ABI) against the CPU oracle and the golden fixtures.
+
+Bars (BASELINE.json north_star): bit-exact hash-corner indices and PDF bin indices; <= 1e-3 scale-relative for
+fp32 results; <= 1e-2 for the bf16-MLP path.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from oracle import state as OS
+from helpers import FAR, NEAR, THR, Fixture, assert_close, field_meta, prop_meta, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL32 = 1e-3
+TOL16 = 1e-2
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from presight_b200 import ops as _ops
+    return _ops
+
+
+# ------------------------------------------------------------------------------------------ hash
+@pytest.fixture(scope="module")
+def fx_hash():
+    return Fixture("hash.npz")
+
+
+@pytest.mark.parametrize("name", ["kat4", "main16", "presight10", "prop8a", "prop8b", "prop5a", "prop5b",
+                                  "main16_c2", "f8"])
+def test_hash_indices_bit_exact_golden(ops, fx_hash, name):
+    L, lo, hi, log2T, F = (int(v) for v in fx_hash.np(f"{name}/cfg"))
+    s = O.hash_scalings(L, lo, hi)
+    idx, off = ops.hash_indices(fx_hash["x"].to(DEV), s.tolist(), log2T)
+    assert torch.equal(idx.cpu(), fx_hash[f"{name}/idx"])
+    assert torch.equal(off.cpu(), fx_hash[f"{name}/offset"])
+
+
+def test_hash_indices_bit_exact_random(ops):
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(20000, 3, generator=g) * 1.2 - 0.1        # includes out-of-cube values
+    x[:100] = torch.randint(0, 65, (100, 3), generator=g).float() / 64.0   # exact lattice points
+    for (L, lo, hi, log2T) in [(16, 16, 2048, 22), (10, 16, 16384, 20), (8, 16, 4096, 20), (5, 16, 128, 17)]:
+        s = O.hash_scalings(L, lo, hi)
+        want, woff = O.hash_corner_indices(x, s, log2T)
+        got, goff = ops.hash_indices(x.to(DEV), s.tolist(), log2T)
+        assert torch.equal(got.cpu(), want)
+        assert torch.equal(goff.cpu(), woff)
+
+
+@pytest.mark.parametrize("name", ["v_l4f2", "v_l8f1", "v_l10f4", "v_l16f2", "v_l3f8"])
+def test_hash_values_and_grads_golden(ops, fx_hash, name):
+    L, lo, hi, log2T, F = (int(v) for v in fx_hash.np(f"{name}/cfg"))
+    s = O.hash_scalings(L, lo, hi).tolist()
+    table = fx_hash[f"{name}/table"].to(DEV).requires_grad_(True)
+    x = fx_hash["x"].to(DEV).requires_grad_(True)
+    y = ops.hash_encode(x, table, s, log2T)
+    # forward follows the reference's evaluation order with un-fused fp32 ops: bit-exact
+    assert torch.equal(y.cpu(), fx_hash[f"{name}/out"])
+    y.backward(fx_hash[f"{name}/dout"].to(DEV))
+    assert_close(table.grad.cpu(), fx_hash[f"{name}/dtable"], TOL32, "dtable")
+    assert_close(x.grad.cpu(), fx_hash[f"{name}/dx"], TOL32, "dx")
+
+
+def test_hash_large_against_oracle(ops):
+    """Config-2 sized levels on a smaller table; empty input; repeated points (atomic contention)."""
+    g = torch.Generator().manual_seed(11)
+    L, lo, hi, log2T, F = 16, 16, 2048, 16, 2
+    s = O.hash_scalings(L, lo, hi)
+    table = (torch.rand((1 << log2T) * L, F, generator=g) * 2 - 1)
+    x = torch.rand(30000, 3, generator=g)
+    x[1000:3000] = x[0]                       # 2000 identical points hammer the same entries
+    x[3000:3500] = 0.0                        # masked points collapse to the origin
+    dout = torch.randn(x.shape[0], L * F, generator=g)
+    t_cpu = table.clone().requires_grad_(True)
+    y_cpu = O.hash_encode(x, O.HashGrid(t_cpu, s, log2T))
+    y_cpu.backward(dout)
+    t_gpu = table.to(DEV).requires_grad_(True)
+    y = ops.hash_encode(x.to(DEV), t_gpu, s.tolist(), log2T)
+    assert torch.equal(y.cpu(), y_cpu.detach())
+    y.backward(dout.to(DEV))
+    assert_close(t_gpu.grad.cpu(), t_cpu.grad, TOL32, "dtable")
+    # linearity of the scatter: grad(2*dout) == 2*grad(dout)
+    t2 = table.to(DEV).requires_grad_(True)
+    ops.hash_encode(x.to(DEV), t2, s.tolist(), log2T).backward(2 * dout.to(DEV))
+    assert_close(t2.grad, 2 * t_gpu.grad, 1e-5, "linearity")
+    empty = ops.hash_encode(torch.zeros(0, 3, device=DEV), t_gpu, s.tolist(), log2T)
+    assert empty.shape == (0, L * F)
+
+
+# ------------------------------------------------------------------------------------------ prologue
+def test_normalize_positions_and_sh(ops):
+    fx = Fixture("fields.npz")
+    pos = fx["pos"]
+    aabb = fx["field/aabb"]
+    want, wsel = O.normalize_to_unit_cube(pos, aabb, True)
+    got, gsel = ops.normalize_positions(pos.to(DEV), aabb.flatten().tolist(), True)
+    assert torch.equal(gsel.cpu().bool(), wsel)
+    assert_close(got.cpu(), want, 1e-6, "x01")
+    want2, wsel2 = O.normalize_to_unit_cube(pos, aabb, False)
+    got2, gsel2 = ops.normalize_positions(pos.to(DEV), aabb.flatten().tolist(), False)
+    assert torch.equal(gsel2.cpu().bool(), wsel2)
+    assert_close(got2.cpu(), want2, 1e-6, "x01 (no contraction)")
+    assert_close(ops.sh4(fx["dirs"].to(DEV)).cpu(), fx["sh_out"], 1e-6, "sh4")
+    assert_close(ops.sh4(((fx["dirs"] + 1) / 2).to(DEV), mapped=True).cpu(), fx["sh_out"], 1e-6, "sh4 mapped")
+    assert torch.equal(ops.nearest_centroid(pos.to(DEV), fx["ms/centroids"].to(DEV)).cpu().long(), fx["ms/assign"])
+
+
+# ------------------------------------------------------------------------------------------ MLP
+SHAPES = [  # (in, hidden, n_layers, out, out_act)
+    (8, 64, 2, 1, 0), (10, 16, 2, 1, 0), (5, 64, 2, 1, 0), (8, 0, 1, 1, 0),
+    (32, 64, 2, 80, 0), (32, 64, 2, 16, 0), (40, 64, 2, 80, 0), (12, 64, 2, 80, 0),
+    (64, 64, 3, 64, 0), (47, 64, 3, 3, 2), (63, 64, 3, 3, 2), (31, 64, 3, 3, 2),
+    (32, 32, 3, 3, 2), (16, 32, 3, 64, 0),
+]
+
+
+def _make_mlp(g, n_in, hidden, n_layers, n_out):
+    dims = [n_in] + [hidden] * (n_layers - 1) + [n_out]
+    ws = [torch.randn(dims[i + 1], dims[i], generator=g) / np.sqrt(dims[i]) for i in range(n_layers)]
+    bs = [torch.randn(dims[i + 1], generator=g) * 0.1 for i in range(n_layers)]
+    return ws, bs
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("prec,tol", [(0, TOL32), (1, TOL16)])
+def test_mlp_forward_backward(ops, shape, prec, tol):
+    n_in, hidden, n_layers, n_out, act = shape
+    g = torch.Generator().manual_seed(n_in * 131 + n_out)
+    ws, bs = _make_mlp(g, n_in, hidden, n_layers, n_out)
+    P = 1000  # not a multiple of the 128-point tile
+    x = torch.randn(P, n_in, generator=g)
+    dy = torch.randn(P, n_out, generator=g)
+    # oracle
+    wc = [w.clone().requires_grad_(True) for w in ws]
+    bc = [b.clone().requires_grad_(True) for b in bs]
+    xc = x.clone().requires_grad_(True)
+    yc = O.mlp_forward(xc, O.Mlp(wc, bc, "sigmoid" if act == 2 else None))
+    yc.backward(dy)
+    # kernel
+    wg = [w.to(DEV).requires_grad_(True) for w in ws]
+    bg = [b.to(DEV).requires_grad_(True) for b in bs]
+    xg = x.to(DEV).requires_grad_(True)
+    yg = ops.mlp(xg, wg, bg, act, prec)
+    assert_close(yg.cpu(), yc, tol, "y")
+    yg.backward(dy.to(DEV))
+    assert_close(xg.grad.cpu(), xc.grad, tol, "dx")
+    for i in range(n_layers):
+        assert_close(wg[i].grad.cpu(), wc[i].grad, tol, f"dW{i}")
+        assert_close(bg[i].grad.cpu(), bc[i].grad, tol, f"db{i}")
+
+
+def test_mlp_multi_tile_and_empty(ops):
+    g = torch.Generator().manual_seed(3)
+    ws, bs = _make_mlp(g, 32, 64, 2, 80)
+    P = 128 * 300 + 17        # more tiles than the persistent grid has CTAs
+    x = torch.randn(P, 32, generator=g)
+    dy = torch.randn(P, 80, generator=g)
+    wc = [w.clone().requires_grad_(True) for w in ws]
+    bc = [b.clone().requires_grad_(True) for b in bs]
+    yc = O.mlp_forward(x, O.Mlp(wc, bc))
+    yc.backward(dy)
+    wg = [w.to(DEV).requires_grad_(True) for w in ws]
+    bg = [b.to(DEV).requires_grad_(True) for b in bs]
+    yg = ops.mlp(x.to(DEV), wg, bg, 0, 0)
+    assert_close(yg.cpu(), yc, TOL32, "y")
+    yg.backward(dy.to(DEV))
+    for i in range(2):
+        assert_close(wg[i].grad.cpu(), wc[i].grad, TOL32, f"dW{i}")
+        assert_close(bg[i].grad.cpu(), bc[i].grad, TOL32, f"db{i}")
+    assert ops.mlp(torch.zeros(0, 32, device=DEV), wg, bg, 0, 1).shape == (0, 80)
+
+
+def test_mlp_unsupported_shape_fails_loudly(ops):
+    g = torch.Generator().manual_seed(3)
+    ws, bs = _make_mlp(g, 200, 64, 2, 1)
+    with pytest.raises(RuntimeError, match="no kernel instantiated"):
+        ops.mlp(torch.zeros(4, 200, device=DEV), [w.to(DEV) for w in ws], [b.to(DEV) for b in bs], 0, 1)
+
+
+def test_trunc_exp(ops):
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(5000, 1, generator=g) * 8
+    x[0] = 20.0
+    x[1] = -30.0
+    sel = (torch.rand(5000, generator=g) > 0.2)
+    xc = x.clone().requires_grad_(True)
+    yc = O.trunc_exp(xc) * sel[:, None]
+    gy = torch.randn(5000, 1, generator=g)
+    yc.backward(gy)
+    xg = x.to(DEV).requires_grad_(True)
+    yg = ops.trunc_exp(xg, sel.to(DEV).to(torch.uint8))
+    assert_close(yg.cpu(), yc, 1e-5, "trunc_exp")
+    yg.backward(gy.to(DEV))
+    assert_close(xg.grad.cpu(), xc.grad, 1e-5, "trunc_exp grad")
+
+
+# ------------------------------------------------------------------------------------------ samplers
+@pytest.fixture(scope="module")
+def fx_sr():
+    return Fixture("sampler_render.npz")
+
+
+@pytest.mark.parametrize("S", [128, 256, 48])
+def test_spaced_bins_golden(ops, fx_sr, S):
+    fx = fx_sr
+    sp, eu = ops.spaced_bins(fx["nears"].to(DEV), fx["fars"].to(DEV), S, THR, fx[f"spaced{S}/t_rand"].to(DEV))
+    assert torch.equal(sp.cpu()[:, :-1], fx[f"spaced{S}/sp_starts"])
+    assert_close(eu.cpu()[:, :-1], fx[f"spaced{S}/starts"], 1e-6, "euclidean starts")
+    assert_close(eu.cpu()[:, 1:], fx[f"spaced{S}/ends"], 1e-6, "euclidean ends")
+    pos = ops.sample_positions(fx["origins"].to(DEV), fx["dirs"].to(DEV), eu)
+    assert_close(pos.cpu(), fx[f"spaced{S}/positions"], 1e-6, "positions")
+    _, eu_e = ops.spaced_bins(fx["nears"].to(DEV), fx["fars"].to(DEV), S, THR, None)
+    assert_close(eu_e.cpu()[:, :-1], fx[f"spaced{S}/eval_starts"], 1e-6, "eval starts")
+
+
+@pytest.mark.parametrize("S_in,S_out", [(128, 64), (64, 64), (256, 96), (96, 48)])
+def test_pdf_resample_golden(ops, fx_sr, S_in, S_out):
+    fx = fx_sr
+    k = f"pdf{S_in}_{S_out}"
+    eps = float(torch.finfo(torch.float32).eps)
+    args = (fx[f"{k}/weights"].to(DEV), fx[f"{k}/existing_sp"].to(DEV), S_out)
+    nf = (fx["nears"].to(DEV), fx["fars"].to(DEV), THR)
+    sp, eu, inds, cdf, u = ops.pdf_resample(*args, fx[f"{k}/rand"].to(DEV), *nf, padding=0.01, eps=eps, probes=True)
+    assert torch.equal(u.cpu(), fx[f"{k}/u"])
+    assert_close(cdf.cpu(), fx[f"{k}/cdf"], 1e-6, "cdf")
+    # (i) the bin search itself is bit-exact on identical inputs ...
+    assert torch.equal(ops.searchsorted_right(fx[f"{k}/cdf"].to(DEV), fx[f"{k}/u"].to(DEV)).cpu(), fx[f"{k}/inds"])
+    assert torch.equal(inds.cpu(), torch.searchsorted(cdf.cpu(), u.cpu(), side="right"))
+    # (ii) ... and end to end the indices agree except where u sits within 2 ulp of a cdf entry
+    ref_inds = fx[f"{k}/inds"]
+    mism = inds.cpu() != ref_inds
+    if mism.any():
+        rc, ru = fx[f"{k}/cdf"], fx[f"{k}/u"]
+        near = torch.gather(rc, 1, ref_inds.clamp(0, S_in)) - ru
+        near2 = torch.gather(rc, 1, (ref_inds - 1).clamp(0, S_in)) - ru
+        gap = torch.minimum(near.abs(), near2.abs())
+        assert (gap[mism] <= 4 * np.finfo(np.float32).eps).all(), "bin index differs away from a cdf edge"
+        assert mism.float().mean() < 0.01
+    assert_close(sp.cpu()[:, :-1], fx[f"{k}/train/sp_starts"], 1e-5, "spacing bins")
+    assert_close(eu.cpu()[:, 1:], fx[f"{k}/train/ends"], 1e-5, "euclidean bins")
+    sp_e, eu_e = ops.pdf_resample(*args, None, *nf, padding=0.01, eps=eps)
+    assert_close(sp_e.cpu()[:, :-1], fx[f"{k}/eval/sp_starts"], 1e-5, "eval spacing bins")
+    assert_close(eu_e.cpu()[:, :-1], fx[f"{k}/eval/starts"], 1e-5, "eval euclidean bins")
+
+
+def test_pdf_resample_anneal_and_sortedness(ops):
+    g = torch.Generator().manual_seed(21)
+    N, S_in, S_out = 4096, 128, 64
+    w = torch.rand(N, S_in, generator=g) ** 4
+    nears, fars = torch.full((N, 1), NEAR), torch.full((N, 1), FAR)
+    sp0, _ = O.spaced_bins(nears, fars, S_in, THR, torch.rand(N, 1, generator=g))
+    rand = torch.rand(N, 1, generator=g)
+    want, winds, _, _ = O.pdf_resample(torch.pow(w, 0.37), sp0, S_out, rand, 0.01, 1e-5)
+    sp, eu, inds, _, _ = ops.pdf_resample(w.to(DEV), sp0.to(DEV), S_out, rand.to(DEV), nears.to(DEV), fars.to(DEV), THR,
+                                          padding=0.01, eps=1e-5, anneal=0.37, probes=True)
+    assert_close(sp.cpu(), want, 1e-4, "annealed bins")
+    assert (inds.cpu() != winds).float().mean() < 0.01
+    assert (sp[:, 1:] >= sp[:, :-1]).all() and (eu[:, 1:] >= eu[:, :-1]).all()      # sorted without a sort
+    assert (sp >= 0).all() and (sp <= 1).all()
+
+
+# ------------------------------------------------------------------------------------------ compositing
+def test_weights_and_renderers_golden(ops, fx_sr):
+    fx = fx_sr
+    deltas = fx["render/deltas"].to(DEV)
+    dens = fx["render/density"][..., 0].to(DEV).requires_grad_(True)
+    rgb = fx["render/rgb"].to(DEV).requires_grad_(True)
+    sem = fx["render/sem"].to(DEV).requires_grad_(True)
+    eu = torch.cat([fx["render/starts"], fx["render/ends"][:, -1:]], dim=-1).to(DEV)
+    w = ops.get_weights(deltas, dens)
+    assert_close(w.cpu(), fx["render/weights"][..., 0], 1e-5, "weights")
+    img = ops.render(w, rgb)
+    acc = ops.render(w, None)
+    steps = ((fx["render/starts"] + fx["render/ends"]) / 2).to(DEV)
+    dexp = torch.clip(ops.render(w, steps[..., None]) / (acc + 1e-10), steps.min(), steps.max())
+    semo = ops.render(w, sem)
+    dthr, didx = ops.depth_threshold(w, eu, 0.5)
+    assert_close(img.cpu(), fx["render/img"], 1e-5, "rgb")
+    assert_close(acc.cpu(), fx["render/acc"], 1e-5, "acc")
+    assert_close(dexp.cpu(), fx["render/depth_expected"], 1e-5, "expected depth")
+    assert_close(semo.cpu(), fx["render/sem_out"], 1e-5, "semantics")
+    assert torch.equal(didx.cpu(), fx["render/depth_index"])
+    assert_close(dthr.cpu(), fx["render/depth_threshold"], 1e-6, "threshold depth")
+    loss = (img * fx["render/g_img"].to(DEV)).sum() + (acc * fx["render/g_acc"].to(DEV)).sum() \
+        + (dexp * fx["render/g_dexp"].to(DEV)).sum() + (semo * fx["render/g_sem"].to(DEV)).sum() \
+        + (w * fx["render/g_w"][..., 0].to(DEV)).sum()
+    loss.backward()
+    assert_close(dens.grad.cpu(), fx["render/d_density"][..., 0], TOL32, "d_density")
+    assert_close(rgb.grad.cpu(), fx["render/d_rgb"], 1e-5, "d_rgb")
+    assert_close(sem.grad.cpu(), fx["render/d_sem"], 1e-5, "d_sem")
+
+
+def test_fused_composite_golden(ops, fx_sr):
+    fx = fx_sr
+    dens = fx["render/density"][..., 0].to(DEV).requires_grad_(True)
+    rgb = fx["render/rgb"].to(DEV).requires_grad_(True)
+    sem = fx["render/sem"].to(DEV).requires_grad_(True)
+    eu = torch.cat([fx["render/starts"], fx["render/ends"][:, -1:]], dim=-1).to(DEV)
+    w, img, acc, dexp_raw, dthr, semo, tmm = ops.composite(eu, dens, rgb, sem, 0.5)
+    dexp = torch.clip(dexp_raw, tmm[0], tmm[1])
+    assert_close(w.cpu(), fx["render/weights"][..., 0], 1e-5, "weights")
+    assert_close(img.cpu(), fx["render/img"], 1e-5, "rgb")
+    assert_close(acc.cpu(), fx["render/acc"], 1e-5, "acc")
+    assert_close(dexp.cpu(), fx["render/depth_expected"], 1e-5, "expected depth")
+    assert_close(dthr.cpu(), fx["render/depth_threshold"], 1e-6, "threshold depth")
+    assert_close(semo.cpu(), fx["render/sem_out"], 1e-5, "semantics")
+    steps = (fx["render/starts"] + fx["render/ends"]) / 2
+    assert float(tmm[0]) == float(steps.min()) and float(tmm[1]) == float(steps.max())
+    loss = (img * fx["render/g_img"].to(DEV)).sum() + (acc * fx["render/g_acc"].to(DEV)).sum() \
+        + (dexp * fx["render/g_dexp"].to(DEV)).sum() + (semo * fx["render/g_sem"].to(DEV)).sum() \
+        + (w * fx["render/g_w"][..., 0].to(DEV)).sum()
+    loss.backward()
+    assert_close(dens.grad.cpu(), fx["render/d_density"][..., 0], TOL32, "d_density")
+    assert_close(rgb.grad.cpu(), fx["render/d_rgb"], 1e-5, "d_rgb")
+    assert_close(sem.grad.cpu(), fx["render/d_sem"], 1e-5, "d_sem")
+
+
+def test_composite_long_rays_against_oracle(ops):
+    """S = 256 (8 chunks per warp) and S = 48 (ragged last chunk), random densities incl. opaque and empty rays."""
+    g = torch.Generator().manual_seed(33)
+    for S in (256, 48, 1):
+        N = 777
+        nears, fars = torch.full((N, 1), NEAR), torch.full((N, 1), FAR)
+        _, eu = O.spaced_bins(nears, fars, S, THR, torch.rand(N, 1, generator=g))
+        dens = torch.exp(torch.randn(N, S, generator=g) * 2)
+        dens[0] = 0
+        dens[1] = 1e7
+        rgb = torch.rand(N, S, 3, generator=g)
+        dc = dens.clone().requires_grad_(True)
+        starts, ends = eu[:, :-1, None], eu[:, 1:, None]
+        wc = O.get_weights(ends - starts, dc[..., None])
+        imgc = O.render_rgb(rgb, wc)
+        gw = torch.randn(N, S, generator=g)
+        gi = torch.randn(N, 3, generator=g)
+        ((wc[..., 0] * gw).sum() + (imgc * gi).sum()).backward()
+        dg = dens.to(DEV).requires_grad_(True)
+        w, img, acc, dexp, dthr, _, tmm = ops.composite(eu.to(DEV), dg, rgb.to(DEV), None, 0.5)
+        assert_close(w.cpu(), wc[..., 0], 1e-5, f"weights S={S}")
+        assert_close(img.cpu(), imgc, 1e-5, f"rgb S={S}")
+        ((w * gw.to(DEV)).sum() + (img * gi.to(DEV)).sum()).backward()
+        assert_close(dg.grad.cpu(), dc.grad, TOL32, f"d_density S={S}")
+        dth_c, idx_c = O.render_depth_threshold(wc.detach(), starts, ends)
+        assert_close(dthr.cpu(), dth_c, 1e-6, f"threshold depth S={S}")
+        assert float(acc.max()) <= 1.0 + 1e-5       # sum of weights never exceeds 1
