@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Headline benchmark: train rays/s of the PreSight city-NeRF inner loop (BASELINE.json config 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2|c1] [--fp32] [--strong]
+
+One step = encode + MLP + sample + composite, forward and backward (update step: proposal nets get gradients),
+plus the gradient all-reduce for N > 1; the optimizer is excluded.  Prints ONE JSON line.
+  value     device-resident inputs, CUDA-event timed, max over ranks
+  e2e       the same step through the public model API with HOST (pinned) ray batches copied in every step and the
+            loss read back every step
+  roofline  dominant kernel (main-grid hash scatter-add), algorithmic bytes / CUDA-event duration vs measured HBM peak
+  cpu_baseline  the oracle port of the reference's torch path, timed on this box's host cores on a bounded sample
+`--impl reference` times that CPU path alone (the reference arm of the harness).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "train_rays_per_s"
+UNIT = "rays/s"
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int) -> None:
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self) -> None:
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) == 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def build_config(name: str, impl: str):
+    from presight_b200 import synthetic
+    return {"c1": synthetic.config_c1, "c2": synthetic.config_c2}[name](impl)
+
+
+def workload_name(name: str) -> str:
+    return {"c2": "PreSight city NeRF train step: 16-level 2^22-entry hash grid F2 + props L8 F1 2^20 (128/64/64 "
+                  "samples), 6-cam nuScenes-shaped rays",
+            "c1": "nerfacto-style hash-grid field: main L16 F2 2^19 + props L5 F2 2^17 (256/96/48 samples)"}[name]
+
+
+# ------------------------------------------------------------------------------------------------ loss
+def step_loss(model, out, batch):
+    """rgb MSE + sky BCE + semantic MSE + interlevel (nerfacto_nusc_ms.py:558-645, multipliers :167,:192,:145)."""
+    from presight_b200 import losses
+    loss = torch.nn.functional.mse_loss(out["rgb"], batch["rgb"])
+    if model.config.use_sky_model:
+        loss = loss + 0.001 * losses.sky_loss(out["accumulation"].view(-1, 1), batch["sky"])
+    if model.config.use_semantics:
+        loss = loss + 0.5 * losses.semantic_loss(out["semantics"], batch["features"])
+    sp = [rs.sp_bins for rs in out["ray_samples_list"]]
+    loss = loss + 1.0 * losses.interlevel_loss(out["weights_list"], sp)
+    return loss
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def oracle_model_from(model, cfg):
+    """Build the oracle's parameter containers from the product model's state dict (CPU copies)."""
+    import oracle as O
+    from oracle import state as OS
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    fmeta = dict(num_levels=cfg.num_levels, base_res=cfg.base_res, max_res=cfg.max_res,
+                 log2_hashmap_size=cfg.log2_hashmap_size, use_semantics=cfg.use_semantics,
+                 semantic_dim=cfg.semantic_dim)
+    nf = len(model.field.fields)
+    fields = [OS.ngp_from_state(sd, f"field.fields.{i}.", fmeta, True) for i in range(nf)]
+    props = []
+    for lvl, net in enumerate(model.proposal_networks):
+        a = cfg.proposal_net_args_list[min(lvl, len(cfg.proposal_net_args_list) - 1)]
+        pm = dict(num_levels=a["num_levels"], base_res=a.get("base_res", 16), max_res=a["max_res"],
+                  log2_hashmap_size=a["log2_hashmap_size"], use_linear=a.get("use_linear", False))
+        props.append([OS.prop_from_state(sd, f"proposal_networks.{lvl}.fields.{i}.", pm, True) for i in range(nf)])
+    sky = None
+    if cfg.use_sky_model:
+        sky = [OS.sky_from_state(sd, f"sky_model.fields.{i}.", cfg.use_semantics, True) for i in range(nf)]
+    ocfg = O.ModelCfg(num_proposal_samples=tuple(cfg.num_proposal_samples_per_ray),
+                      num_nerf_samples=cfg.num_nerf_samples_per_ray, near=cfg.near_plane, far=cfg.far_plane,
+                      piecewise_thr=cfg.piecewise_sampler_threshold)
+    emb = {k: sd[k] for k in sd if "embedding.embedding.weight" in k}
+    return O.Model(ocfg, model.centroids.cpu(), fields, props, sky), emb
+
+
+def cpu_reference_step(omodel, emb, cfg, batch, n):
+    """One fwd+bwd of the oracle port on `n` rays (torch CPU, all host threads)."""
+    import oracle as O
+    from presight_b200 import losses
+    o, d = batch["origins"][:n], batch["directions"][:n]
+    parts = []
+    if cfg.appearance_embed_dim > 0:
+        parts.append(emb["appearance_embedding.embedding.weight"][batch["camera_indices"][:n, 0]])
+    if cfg.video_embed_dim > 0:
+        parts.append(emb["video_embedding.embedding.weight"][batch["video_ids"][:n, 0]])
+    app = torch.cat(parts, dim=-1) if parts else None
+    jit = [torch.rand(n, 1) for _ in range(len(cfg.num_proposal_samples_per_ray) + 1)]
+    out = O.model_outputs(omodel, o, d, app, jit)
+    loss = torch.nn.functional.mse_loss(out["rgb"], batch["rgb"][:n])
+    if cfg.use_sky_model:
+        loss = loss + 0.001 * losses.sky_loss(out["accumulation"].view(-1, 1), batch["sky"][:n])
+    if cfg.use_semantics:
+        loss = loss + 0.5 * losses.semantic_loss(out["semantics"], batch["features"][:n])
+    loss = loss + losses.interlevel_loss(out["weights_list"], [b[0] for b in out["bins_list"]])
+    params = [f.grid.table for f in omodel.fields] + [p.grid.table for lvl in omodel.props for p in lvl]
+    for p in params:
+        p.grad = None
+    loss.backward()
+    return float(loss.detach())
+
+
+def time_cpu_reference(model, cfg, batch, sample_rays, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    omodel, emb = oracle_model_from(model, cfg)
+    for _ in range(warmup):
+        cpu_reference_step(omodel, emb, cfg, batch, sample_rays)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_reference_step(omodel, emb, cfg, batch, sample_rays)
+        ts.append(time.perf_counter() - t0)
+    return sample_rays / statistics.median(ts), statistics.median(ts)
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=["c1", "c2"])
+    ap.add_argument("--rays", type=int, default=65536, help="rays per GPU (weak scaling) or global (--strong)")
+    ap.add_argument("--fp32", action="store_true", help="3xTF32 MLPs (1e-3 parity class) instead of bf16")
+    ap.add_argument("--strong", action="store_true", help="fixed global batch split across ranks (reference semantics)")
+    ap.add_argument("--cpu-sample-rays", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    impl = "b200+fp32" if args.fp32 else "b200"
+    from presight_b200 import synthetic
+    cfg = build_config(args.config, impl)
+
+    # ---------------------------------------------------------------- reference arm: CPU only, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from presight_b200.model import NerfactoNuscMSModel
+        torch.manual_seed(42)
+        batch = synthetic.make_rays(max(args.cpu_sample_rays, 1), seed=42)
+        model = NerfactoNuscMSModel(cfg, torch.zeros(1, 3), synthetic.tile_aabb(), batch["n_cameras"], batch["n_videos"])
+        t_start = time.perf_counter()
+        rps, med = time_cpu_reference(model, cfg, batch, args.cpu_sample_rays, max(1, args.steps), max(1, args.warmup))
+        cores = os.cpu_count() or 1
+        sample = f"{args.cpu_sample_rays} rays/step of the same workload, torch CPU fp32, {cores} threads"
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": rps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.config), "rays_per_step": args.cpu_sample_rays},
+            "cpu_baseline": {"value": rps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t_start}))
+        return
+
+    # ---------------------------------------------------------------- b200 arm
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the b200 path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from presight_b200 import ops
+    from presight_b200.cameras.rays import RayBundle
+    from presight_b200.model import VIDEO_ID, NerfactoNuscMSModel
+    from presight_b200.parallel import GradSynchronizer
+
+    rays_per_rank = args.rays // world if args.strong else args.rays
+    torch.manual_seed(42)                                        # identical weights on every rank
+    host = synthetic.make_rays(rays_per_rank, seed=42 + rank)    # reference seeds data with seed + rank (train.py:99)
+    model = NerfactoNuscMSModel(cfg, torch.zeros(1, 3), synthetic.tile_aabb(), host["n_cameras"], host["n_videos"]).to(dev)
+    model.train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    sync = GradSynchronizer(params, overlap=True) if world > 1 else None
+
+    tensor_keys = ("origins", "directions", "camera_indices", "video_ids", "rgb", "features", "sky")
+    pinned = {k: host[k].pin_memory() for k in tensor_keys}
+    resident = {k: pinned[k].to(dev, non_blocking=True) for k in tensor_keys}
+    h2d_bytes = sum(pinned[k].numel() * pinned[k].element_size() for k in tensor_keys)
+
+    def run_step(batch):
+        for p in params:
+            p.grad = None
+        rb = RayBundle(origins=batch["origins"], directions=batch["directions"],
+                       camera_indices=batch["camera_indices"], metadata={VIDEO_ID: batch["video_ids"]})
+        model.proposal_sampler._step = 0                 # update step: proposal nets receive gradients
+        out = model(rb)
+        loss = step_loss(model, out, batch)
+        loss.backward()
+        if sync is not None:
+            sync.finish()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, 3)):
+        run_step(resident)
+    barrier()
+
+    # ---- timed: device-resident inputs
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ops.PROBE = ops.KernelProbe()
+    launches0 = ops.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        run_step(resident)
+    ev1.record()
+    barrier()
+    launches = ops.launch_count() - launches0
+    probe = ops.PROBE.summary()
+    ops.PROBE = None
+    t_dev = ev0.elapsed_time(ev1) / 1e3
+
+    # ---- timed: end to end (pinned host batch -> device every step, loss read back every step)
+    for _ in range(2):
+        float(run_step({k: pinned[k].to(dev, non_blocking=True) for k in tensor_keys}))
+    barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record()
+    last = 0.0
+    for _ in range(args.steps):
+        batch = {k: pinned[k].to(dev, non_blocking=True) for k in tensor_keys}
+        last = float(run_step(batch))        # .item(): device->host read of the step's result
+    ev3.record()
+    barrier()
+    t_e2e = ev2.elapsed_time(ev3) / 1e3
+    clock_info = clocks.stop()
+
+    if world > 1:
+        t = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(t[0]), float(t[1])
+    total_rays = rays_per_rank * world
+    value = total_rays * args.steps / t_dev
+    e2e = total_rays * args.steps / t_e2e
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        L, F = cfg.num_levels, cfg.features_per_level
+        points = rays_per_rank * cfg.num_nerf_samples_per_ray
+        kname = f"hash_bwd_L{L}F{F}T{cfg.log2_hashmap_size}"
+        n_launch, k_ms = probe.get(kname, (0, float("nan")))
+        algo_bytes = synthetic.hash_bytes_bwd(L, F) * points
+        achieved = algo_bytes / (k_ms * 1e-3) / 1e9 if n_launch else None
+        step_bytes = synthetic.step_bytes_per_ray(cfg, True)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+            "dtype": "f32 (hash/compositing) + " + ("tf32x3 MLP" if args.fp32 else "bf16 MLP, fp32 accumulate"),
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.config), "rays_per_gpu": rays_per_rank, "global_rays": total_rays,
+                       "parallelism": f"dp{world}", "step": "update step (proposal nets trained), optimizer excluded",
+                       "l2": "inputs larger than L2 (576 MiB of hash tables + grads re-zeroed every step)"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": t_e2e / args.steps * 1e3},
+            "gpu_launches": int(launches),
+            "clocks": clock_info,
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": k_ms, "algorithmic_bytes_per_launch": algo_bytes,
+                         "step_frac_of_hbm_roofline": (step_bytes * total_rays / world) / (t_dev / args.steps) / 1e9 / peak},
+            "kernels_ms": {k: round(v[1], 4) for k, v in sorted(probe.items())},
+            "loss": last,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n = args.cpu_sample_rays
+            rps, med = time_cpu_reference(model, cfg, host, n, 3, 1)
+            line["cpu_baseline"] = {"value": rps, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{n} rays/step of the same workload and weights, torch CPU fp32, "
+                                              f"{cores} threads, median of 3 steps ({med:.2f} s/step)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -32,7 +32,7 @@ __all__ = [
     "prop_density", "nearest_centroid", "ms_dispatch", "spaced_bins", "spacing_fns", "pdf_cdf",
     "pdf_resample", "sample_positions", "get_weights", "render_rgb", "render_accumulation",
     "render_depth_expected", "render_depth_threshold", "proposal_sample", "model_outputs",
-    "model_depth", "prior_query", "sky_outputs", "PRIME_Y", "PRIME_Z",
+    "model_depth", "prior_query", "sky_outputs", "PRIME_Y", "PRIME_Z", "mlp_forward_bf16_emulated",
 ]
 
 PRIME_Y = 2654435761  # ENC:336
@@ -634,3 +634,39 @@ def prior_query(model: Model, points_scaled: Tensor) -> Tuple[Tensor, Tensor]:
                           lambda i, p: {"semantics": ngp_semantics(model.fields[i], p)}, len(model.fields))
         feats = sem["semantics"].clip(0.0, 1.0).to(torch.float16)
     return mean, feats
+
+
+# --------------------------------------------------------------------------------------
+# bf16-operand emulation of the MLP (checker for the tensor-core path; not a reference restatement)
+# --------------------------------------------------------------------------------------
+def _bf(t: Tensor) -> Tensor:
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+class _Bf16Linear(torch.autograd.Function):
+    """y = bf16(x) @ bf16(W)^T + b with fp32 accumulation; the backward rounds the incoming gradient and the
+    saved operands to bf16 as well — the arithmetic of the bf16 MMA kernels (mlp_mma.cuh)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        xq, wq = _bf(x), _bf(w)
+        ctx.save_for_backward(xq, wq)
+        return xq @ wq.T + b
+
+    @staticmethod
+    def backward(ctx, g):
+        xq, wq = ctx.saved_tensors
+        gq = _bf(g)
+        return gq @ wq, gq.T @ xq, gq.sum(dim=0)
+
+
+def mlp_forward_bf16_emulated(x: Tensor, net: Mlp) -> Tensor:
+    """Same network as mlp_forward (MLPF:157-174) with every matrix operand rounded to bf16."""
+    n = len(net.weights)
+    for i, (w, b) in enumerate(zip(net.weights, net.biases)):
+        x = _Bf16Linear.apply(x, w, b)
+        if i < n - 1:
+            x = torch.relu(x)
+    if net.out_act == "sigmoid":
+        x = torch.sigmoid(x)
+    return x

@@ -36,7 +36,7 @@ def _headers():
 def _digest(paths):
     h = hashlib.sha256()
     for p in paths:
-        h.update(p.encode())
+        h.update(os.path.basename(p).encode())
         with open(p, "rb") as f:
             h.update(f.read())
     h.update(" ".join(ARCH + CFLAGS).encode())

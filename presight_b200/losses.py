@@ -1,0 +1,54 @@
+"""Loss terms that seed the backward pass of the hot path (reference: model_components/losses.py and
+model_components/PreSight/losses.py).  They consume `weights_list` / rendered outputs and stay in torch, as
+SURVEY §8(f)-1 scopes them ("next" row); only the terms needed to drive every gradient path are restated."""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+
+EPS = 1.0e-7
+
+
+def outer(t0_starts: Tensor, t0_ends: Tensor, t1_starts: Tensor, t1_ends: Tensor, y1: Tensor) -> Tensor:
+    """Upper envelope of a step function on coarser intervals (losses.py:48-77)."""
+    cy1 = torch.cat([torch.zeros_like(y1[..., :1]), torch.cumsum(y1, dim=-1)], dim=-1)
+    idx_lo = torch.searchsorted(t1_starts.contiguous(), t0_starts.contiguous(), side="right") - 1
+    idx_lo = torch.clamp(idx_lo, min=0, max=y1.shape[-1] - 1)
+    idx_hi = torch.searchsorted(t1_ends.contiguous(), t0_ends.contiguous(), side="right")
+    idx_hi = torch.clamp(idx_hi, min=0, max=y1.shape[-1] - 1)
+    cy1_lo = torch.take_along_dim(cy1[..., :-1], idx_lo, dim=-1)
+    cy1_hi = torch.take_along_dim(cy1[..., 1:], idx_hi, dim=-1)
+    return cy1_hi - cy1_lo
+
+
+def lossfun_outer(t: Tensor, w: Tensor, t_env: Tensor, w_env: Tensor) -> Tensor:
+    """losses.py:80-97."""
+    w_outer = outer(t[..., :-1], t[..., 1:], t_env[..., :-1], t_env[..., 1:], w_env)
+    return torch.clip(w - w_outer, min=0) ** 2 / (w + EPS)
+
+
+def interlevel_loss(weights_list: List[Tensor], sp_bins_list: List[Tensor]) -> Tensor:
+    """Proposal loss of mip-NeRF 360 (losses.py:108-126); sp_bins_list holds the spacing-domain bin edges."""
+    c = sp_bins_list[-1].detach()
+    w = weights_list[-1][..., 0].detach()
+    loss = 0.0
+    for sdist, weights in zip(sp_bins_list[:-1], weights_list[:-1]):
+        loss = loss + torch.mean(lossfun_outer(c, w, sdist, weights[..., 0]))
+    return loss
+
+
+def sky_loss(accumulation: Tensor, sky_mask: Tensor, eps: float = 1e-7) -> Tensor:
+    """PreSight/losses.py:104-114."""
+    target = 1.0 - sky_mask
+    accumulation = torch.clip(accumulation, min=eps, max=1 - eps)
+    return F.binary_cross_entropy(accumulation, target, reduction="none").mean()
+
+
+def semantic_loss(pred: Tensor, target: Tensor, clip: bool = True) -> Tensor:
+    """PreSight/losses.py:116-124."""
+    if clip:
+        target = torch.clip(target, min=0.0, max=1.0)
+    return F.mse_loss(pred, target, reduction="none").mean()

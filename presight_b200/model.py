@@ -1,0 +1,285 @@
+"""City-NeRF model driver (reference: nerfstudio/models/PreSight/nerfacto_nusc_ms.py).
+
+`NerfactoNuscMSModel` wires the b200 fields, the proposal sampler and the compositing kernels exactly like the
+reference's `populate_modules` (:203-383), `get_outputs` (:452-546), `get_depth` (:688-708) and the prior query of
+scripts/extract_priors.py:130-138.  Module names (`field`, `proposal_networks`, `sky_model`,
+`appearance_embedding`, `video_embedding`) match the reference so state dicts are interchangeable.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Literal, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+
+from . import ops
+from .cameras.rays import RayBundle, RaySamples
+from .field_components.spatial_distortions import SceneContraction
+from .fields.ingp_field import FieldHeadNames, iNGPField
+from .fields.multi_field import PropNetDensityFieldMS, SkyFieldMS, iNGPFieldMS
+from .fields.prop_density_field import PropNetDensityField
+from .fields.sky_field import SkyField
+from .model_components.ray_samplers import ProposalNetworkSampler, SpacedSampler
+from .model_components.renderers import AccumulationRenderer, DepthRenderer, RGBRenderer
+
+VIDEO_ID = "video_id"
+
+
+@dataclass
+class NerfactoNuscMSModelConfig:
+    """Hot-path subset of the reference's config (nerfacto_nusc_ms.py:76-200), same names and defaults."""
+    near_plane: float = 0.1
+    far_plane: float = 1000.0
+    background_color: Literal["random", "last_sample", "black", "white"] = "black"
+    hidden_dim: int = 64
+    hidden_dim_color: int = 64
+    num_levels: int = 10
+    base_res: int = 16
+    max_res: int = 16384
+    log2_hashmap_size: int = 20
+    features_per_level: int = 4
+    num_proposal_samples_per_ray: Tuple[int, ...] = (128, 64)
+    num_nerf_samples_per_ray: int = 64
+    proposal_update_every: int = 5
+    proposal_warmup: int = 1000
+    num_proposal_iterations: int = 2
+    use_same_proposal_network: bool = False
+    proposal_net_args_list: List[Dict] = field(
+        default_factory=lambda: [
+            {"features_per_level": 1, "log2_hashmap_size": 20, "num_levels": 8, "base_res": 16, "max_res": 1024,
+             "use_linear": False},
+            {"features_per_level": 1, "log2_hashmap_size": 20, "num_levels": 8, "base_res": 16, "max_res": 4096,
+             "use_linear": False},
+        ])
+    piecewise_sampler_threshold: float = 1.0
+    use_single_jitter: bool = True
+    disable_scene_contraction: bool = False
+    implementation: Literal["b200", "b200+fp32"] = "b200"
+    appearance_embed_dim: int = 4
+    video_embed_dim: int = 12
+    use_sky_model: bool = True
+    num_sky_mlp_layers: int = 3
+    sky_mlp_dims: int = 32
+    use_semantics: bool = True
+    semantic_dim: int = 64
+    use_average_appearance_embedding: bool = True
+    eval_num_rays_per_chunk: int = 1 << 15
+
+
+class Embedding(nn.Module):
+    """nerfstudio/field_components/embedding.py:24-55."""
+
+    def __init__(self, in_dim: int, out_dim: int) -> None:
+        super().__init__()
+        self.in_dim, self.out_dim = in_dim, out_dim
+        self.embedding = nn.Embedding(in_dim, out_dim)
+
+    def mean(self, dim=0):
+        return self.embedding.weight.mean(dim)
+
+    def forward(self, in_tensor: Tensor) -> Tensor:
+        return self.embedding(in_tensor)
+
+
+class NearFarCollider:
+    """nerfstudio/model_components/scene_colliders.py:169-187."""
+
+    def __init__(self, near_plane: float, far_plane: float) -> None:
+        self.near_plane, self.far_plane = near_plane, far_plane
+        self.training = True
+
+    def __call__(self, ray_bundle: RayBundle) -> RayBundle:
+        ones = torch.ones_like(ray_bundle.origins[..., 0:1])
+        near_plane = self.near_plane if self.training else 0
+        ray_bundle.nears = ones * near_plane
+        ray_bundle.fars = ones * self.far_plane
+        return ray_bundle
+
+
+class NerfactoNuscMSModel(nn.Module):
+    def __init__(self, config: NerfactoNuscMSModelConfig, centroids: Tensor, aabbs: Tensor, num_train_cameras: int = 1,
+                 num_train_videos: int = 1) -> None:
+        super().__init__()
+        self.config = config
+        self.centroids = centroids
+        self.aabbs = aabbs
+        c = config
+        contraction = None if c.disable_scene_contraction else SceneContraction(order=float("inf"))
+        app_dim = c.appearance_embed_dim + c.video_embed_dim
+        fields = [iNGPField(aabb, hidden_dim=c.hidden_dim, num_levels=c.num_levels, max_res=c.max_res,
+                            base_res=c.base_res, features_per_level=c.features_per_level,
+                            log2_hashmap_size=c.log2_hashmap_size, hidden_dim_color=c.hidden_dim_color,
+                            spatial_distortion=contraction, use_semantics=c.use_semantics, semantic_dim=c.semantic_dim,
+                            appearance_embedding_dim=app_dim, implementation=c.implementation) for aabb in aabbs]
+        self.field = iNGPFieldMS(fields, centroids)
+        if c.appearance_embed_dim > 0:
+            self.appearance_embedding = Embedding(num_train_cameras, c.appearance_embed_dim)
+        if c.video_embed_dim > 0:
+            self.video_embedding = Embedding(num_train_videos, c.video_embed_dim)
+        self.density_fns = []
+        self.proposal_networks = nn.ModuleList()
+        n_props = c.num_proposal_iterations
+        if c.use_same_proposal_network:
+            assert len(c.proposal_net_args_list) == 1, "Only one proposal network is allowed."
+            net = PropNetDensityFieldMS([PropNetDensityField(aabb, spatial_distortion=contraction,
+                                                             **c.proposal_net_args_list[0],
+                                                             implementation=c.implementation) for aabb in aabbs],
+                                        centroids)
+            self.proposal_networks.append(net)
+            self.density_fns.extend([net.density_fn for _ in range(n_props)])
+        else:
+            for i in range(n_props):
+                args = c.proposal_net_args_list[min(i, len(c.proposal_net_args_list) - 1)]
+                net = PropNetDensityFieldMS([PropNetDensityField(aabb, spatial_distortion=contraction, **args,
+                                                                 implementation=c.implementation) for aabb in aabbs],
+                                            centroids)
+                self.proposal_networks.append(net)
+            self.density_fns.extend([net.density_fn for net in self.proposal_networks])
+
+        def update_schedule(step):
+            return np.clip(np.interp(step, [0, c.proposal_warmup], [0, c.proposal_update_every]), 1,
+                           c.proposal_update_every)
+        initial_sampler = SpacedSampler(piecewise_threshold=c.piecewise_sampler_threshold,
+                                        single_jitter=c.use_single_jitter)
+        self.proposal_sampler = ProposalNetworkSampler(
+            num_nerf_samples_per_ray=c.num_nerf_samples_per_ray,
+            num_proposal_samples_per_ray=c.num_proposal_samples_per_ray,
+            num_proposal_network_iterations=c.num_proposal_iterations, single_jitter=c.use_single_jitter,
+            update_sched=update_schedule, initial_sampler=initial_sampler)
+        self.collider = NearFarCollider(near_plane=c.near_plane, far_plane=c.far_plane)
+        self.renderer_rgb = RGBRenderer(background_color=c.background_color)
+        self.renderer_accumulation = AccumulationRenderer()
+        self.renderer_depth = DepthRenderer(method="threshold")
+        self.renderer_expected_depth = DepthRenderer(method="expected")
+        if c.use_sky_model:
+            self.sky_model = SkyFieldMS([SkyField(mlp_num_layers=c.num_sky_mlp_layers, mlp_layer_width=c.sky_mlp_dims,
+                                                  appearance_embedding_dim=app_dim, use_semantics=c.use_semantics,
+                                                  semantic_dim=c.semantic_dim, implementation=c.implementation)
+                                         for _ in aabbs], centroids)
+
+    def train(self, mode: bool = True):
+        super().train(mode)
+        self.collider.training = mode
+        return self
+
+    def get_param_groups(self) -> Dict[str, List[nn.Parameter]]:
+        """nerfacto_nusc_ms.py:385-398."""
+        groups = {"proposal_networks": list(self.proposal_networks.parameters()), "fields": list(self.field.parameters())}
+        for name in ("appearance_embedding", "video_embedding", "sky_model"):
+            if hasattr(self, name):
+                groups["fields"] += list(getattr(self, name).parameters())
+        return groups
+
+    # ------------------------------------------------------------------------------------------
+    def _appearance(self, ray_samples: RaySamples) -> Optional[Tensor]:
+        """nerfacto_nusc_ms.py:456-490 -> [N,S,A] (expanded view) or None."""
+        c = self.config
+        cam = ray_samples.camera_indices.squeeze(dim=-1)          # [N,1]
+        N, S = ray_samples.shape
+        if self.training:
+            parts = []
+            if c.appearance_embed_dim > 0:
+                parts.append(self.appearance_embedding(cam))
+            if c.video_embed_dim > 0:
+                parts.append(self.video_embedding(ray_samples.metadata[VIDEO_ID].squeeze(dim=-1)))
+            emb = torch.cat(parts, dim=-1) if parts else None
+        else:
+            dim = c.appearance_embed_dim + c.video_embed_dim
+            if dim == 0:
+                emb = None
+            elif c.use_average_appearance_embedding:
+                parts = []
+                if c.appearance_embed_dim > 0:
+                    parts.append(self.appearance_embedding.mean(dim=0))
+                if c.video_embed_dim > 0:
+                    parts.append(self.video_embedding.mean(dim=0))
+                emb = torch.cat(parts, dim=-1)[None, None, :].expand(N, 1, dim)
+            else:
+                emb = torch.zeros((N, 1, dim), device=cam.device)
+        if emb is None:
+            return None
+        return emb.expand(N, S, emb.shape[-1])
+
+    def forward(self, ray_bundle: RayBundle, jitters: Optional[List[Tensor]] = None,
+                appearance: Optional[Tensor] = None) -> Dict[str, object]:
+        """Model.forward (models/base_model.py:131-142): collider, then get_outputs."""
+        return self.get_outputs(self.collider(ray_bundle), jitters, appearance)
+
+    def get_outputs(self, ray_bundle: RayBundle, jitters: Optional[List[Tensor]] = None,
+                    appearance: Optional[Tensor] = None) -> Dict[str, object]:
+        """nerfacto_nusc_ms.py:452-546.  `jitters` (per-level [N,1] uniforms) and `appearance` ([N,A], already
+        looked-up embeddings) are optional injection points so parity runs can share randomness and inputs."""
+        ray_samples, weights_list, ray_samples_list = self.proposal_sampler(ray_bundle, density_fns=self.density_fns,
+                                                                            jitters=jitters)
+        N, S = ray_samples.shape
+        app = self._appearance(ray_samples) if appearance is None else appearance[:, None, :].expand(N, S, -1)
+        fo = self.field.forward(ray_samples, appearance_embedding=app)
+        eu = ray_samples.frustums.eu_bins
+        sem = fo.get(FieldHeadNames.SEMANTICS)
+        # one-pass compositing kernel: weights + rgb + accumulation + both depths + semantics (:503-511, :530)
+        w, rgb, acc_raw, dexp_raw, depth, sem_out, tmm = ops.composite(
+            eu, fo[FieldHeadNames.DENSITY].reshape(N, S), fo[FieldHeadNames.RGB], sem, 0.5)
+        weights = w.view(N, S, 1)
+        weights_list.append(weights)
+        ray_samples_list.append(ray_samples)
+        expected_depth = torch.clip(dexp_raw, tmm[0], tmm[1])            # renderers.py:379 (batch-global clip)
+        accumulation = torch.clamp(acc_raw, min=0.0, max=1.0)
+        if not self.training:
+            rgb = torch.clamp(rgb, min=0.0, max=1.0)
+        sky_outputs = {}
+        if self.config.use_sky_model:
+            sky_outputs = self.sky_model(ray_samples, appearance_embedding=app)
+            rgb = rgb + (1.0 - accumulation) * sky_outputs[FieldHeadNames.RGB]
+        outputs: Dict[str, object] = {"rgb": rgb, "accumulation": accumulation, "depth": depth,
+                                      "expected_depth": expected_depth}
+        if self.config.use_semantics:
+            semantics = sem_out
+            if FieldHeadNames.SEMANTICS in sky_outputs:
+                semantics = semantics + (1.0 - accumulation) * sky_outputs[FieldHeadNames.SEMANTICS]
+            outputs["semantics"] = semantics
+        if self.training:
+            outputs["weights_list"] = weights_list
+            outputs["ray_samples_list"] = ray_samples_list
+        for i in range(self.config.num_proposal_iterations):
+            outputs[f"prop_depth_{i}"] = self.renderer_depth(weights=weights_list[i], ray_samples=ray_samples_list[i])
+        return outputs
+
+    def get_depth(self, ray_bundle: RayBundle, threshold: float = 0.5) -> Dict[str, object]:
+        """nerfacto_nusc_ms.py:688-708."""
+        ray_bundle = self.collider(ray_bundle)
+        ray_samples, weights_list, ray_samples_list = self.proposal_sampler(ray_bundle, density_fns=self.density_fns)
+        density, _ = self.field.get_density(ray_samples)
+        N, S = ray_samples.shape
+        w, _, _, dexp_raw, depth, _, tmm = ops.composite(ray_samples.frustums.eu_bins, density.reshape(N, S), None, None,
+                                                         threshold)
+        outputs: Dict[str, object] = {"depth": depth, "expected_depth": torch.clip(dexp_raw, tmm[0], tmm[1])}
+        if self.training:
+            outputs["weights_list"] = weights_list
+            outputs["ray_samples_list"] = ray_samples_list
+        return outputs
+
+    @torch.no_grad()
+    def get_depth_for_camera_ray_bundle(self, camera_ray_bundle: RayBundle, threshold: float = 0.5) -> Dict[str, Tensor]:
+        """nerfacto_nusc_ms.py:710-734: chunked evaluation."""
+        chunk = self.config.eval_num_rays_per_chunk
+        n = len(camera_ray_bundle)
+        lists: Dict[str, List[Tensor]] = {}
+        for i in range(0, n, chunk):
+            rb = RayBundle(origins=camera_ray_bundle.origins[i:i + chunk], directions=camera_ray_bundle.directions[i:i + chunk],
+                           camera_indices=None if camera_ray_bundle.camera_indices is None
+                           else camera_ray_bundle.camera_indices[i:i + chunk])
+            for k, v in self.get_depth(rb, threshold).items():
+                if torch.is_tensor(v):
+                    lists.setdefault(k, []).append(v)
+        return {k: torch.cat(v) for k, v in lists.items()}
+
+    @torch.no_grad()
+    def query_priors(self, points_scaled: Tensor) -> Tuple[Tensor, Tensor]:
+        """scripts/extract_priors.py:130-138: mean density over proposal nets + field, clipped fp16 semantics."""
+        dens = [p.density_fn(points_scaled).squeeze(-1) for p in self.proposal_networks]
+        dens.append(self.field.density_fn(points_scaled)[0].squeeze(-1))
+        densities_mean = torch.stack(dens, dim=0).mean(dim=0)
+        feats = self.field.semantic_fn(points_scaled).clip(0.0, 1.0).to(torch.float16)
+        return densities_mean, feats

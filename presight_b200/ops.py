@@ -18,6 +18,45 @@ ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 PREC_TF32X3, PREC_BF16 = 0, 1
 
 
+class KernelProbe:
+    """Optional per-kernel timing with CUDA events on the launching stream (used by bench.py for the roofline
+    line).  `with probe("name"):` brackets one launch; `summary()` returns {name: (launches, mean ms)}."""
+
+    def __init__(self) -> None:
+        self.events = {}
+
+    def __call__(self, name: str):
+        return _ProbeCtx(self, name)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v) / len(v)) for k, v in self.events.items()}
+
+
+class _ProbeCtx:
+    def __init__(self, probe, name):
+        self.probe, self.name = probe, name
+
+    def __enter__(self):
+        if self.probe is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+
+    def __exit__(self, *exc):
+        if self.probe is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            self.probe.events.setdefault(self.name, []).append((self.start, end))
+        return False
+
+
+PROBE: Optional[KernelProbe] = None
+
+
+def _probe(name: str):
+    return _ProbeCtx(PROBE, name)
+
+
 def _f32c(t: Tensor) -> Tensor:
     if t.dtype != torch.float32:
         t = t.float()
@@ -36,7 +75,8 @@ class _HashEncode(torch.autograd.Function):
         L, F = len(scalings), tab.shape[1]
         P = x.shape[0]
         out = torch.empty(P, L * F, device=x.device, dtype=torch.float32)
-        call("ps_hash_fwd", ptr(x), P, ptr(tab), host_floats(scalings), L, F, log2_T, ptr(out), stream())
+        with _probe(f"hash_fwd_L{L}F{F}T{log2_T}"):
+            call("ps_hash_fwd", ptr(x), P, ptr(tab), host_floats(scalings), L, F, log2_T, ptr(out), stream())
         ctx.save_for_backward(x, table)
         ctx.meta = (scalings, log2_T, x01.shape, x01.requires_grad)
         return out.view(*x01.shape[:-1], L * F)
@@ -54,8 +94,9 @@ class _HashEncode(torch.autograd.Function):
             return None, None, None, None
         if dtable is None:  # the kernel always scatters; give it a scratch target
             dtable = torch.zeros_like(table)
-        call("ps_hash_bwd", ptr(x), P, ptr(table.detach()), host_floats(scalings), L, F, log2_T, ptr(dout),
-             ptr(dtable), ptr(dx), stream())
+        with _probe(f"hash_bwd_L{L}F{F}T{log2_T}"):
+            call("ps_hash_bwd", ptr(x), P, ptr(table.detach()), host_floats(scalings), L, F, log2_T, ptr(dout),
+                 ptr(dtable), ptr(dx), stream())
         return (dx.view(xshape) if dx is not None else None), (dtable if ctx.needs_input_grad[1] else None), None, None
 
 
@@ -130,8 +171,9 @@ class _Mlp(torch.autograd.Function):
         y = torch.empty(x2.shape[0], dims[-1], device=x2.device, dtype=torch.float32)
         wd = [w.detach().contiguous() for w in ws]
         bd = [None if b is None else b.detach().contiguous() for b in bs]
-        call("ps_mlp_fwd", ptr(x2), x2.shape[0], host_ptrs(wd), host_ptrs(bd), host_ints(dims), n_layers, out_act,
-             precision, ptr(y), stream())
+        with _probe("mlp_fwd_" + "x".join(map(str, dims))):
+            call("ps_mlp_fwd", ptr(x2), x2.shape[0], host_ptrs(wd), host_ptrs(bd), host_ints(dims), n_layers, out_act,
+                 precision, ptr(y), stream())
         ctx.save_for_backward(x2, *wd, *[b for b in bd if b is not None])
         ctx.meta = (out_act, precision, n_layers, dims, [b is not None for b in bd], x.shape)
         return y.view(*lead, dims[-1])
@@ -147,8 +189,9 @@ class _Mlp(torch.autograd.Function):
         dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
         dW = [torch.zeros_like(w) for w in wd]
         db = [None if b is None else torch.zeros_like(b) for b in bd]
-        call("ps_mlp_bwd", ptr(x2), None, ptr(dy2), x2.shape[0], host_ptrs(wd), host_ptrs(bd), host_ints(dims),
-             n_layers, out_act, precision, ptr(dx), host_ptrs(dW), host_ptrs(db), stream())
+        with _probe("mlp_bwd_" + "x".join(map(str, dims))):
+            call("ps_mlp_bwd", ptr(x2), None, ptr(dy2), x2.shape[0], host_ptrs(wd), host_ptrs(bd), host_ints(dims),
+                 n_layers, out_act, precision, ptr(dx), host_ptrs(dW), host_ptrs(db), stream())
         return (None if dx is None else dx.view(xshape), None, None, None, *dW, *db)
 
 

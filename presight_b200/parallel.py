@@ -1,0 +1,95 @@
+"""Data-parallel gradient exchange (reference: DDP wrap at pipelines/PreSight/my_pipeline.py:121-124).
+
+Rays are sharded across ranks (data/PreSight/my_datamanager.py:206-212); the only exchange step is the
+all-reduce of the dense fp32 gradients (hash tables + MLPs).  Instead of DDP's 25 MB buckets, every large
+parameter's all-reduce is launched from a post-accumulate-grad hook the moment autograd has finished that
+parameter, so the 512 MiB main-table reduction (finished first in backward) travels over NVLink while the proposal
+networks' backward is still running.
+
+Two modes:
+  overlap=True   hooks + async all-reduce.  Requires that every rank produces gradients for the same set of
+                 parameters in the same order (single sub-field models; update / non-update steps are decided by
+                 the step counter, identically on all ranks).
+  overlap=False  one fixed-order pass in `finish()`; parameters without a gradient on this rank contribute zeros —
+                 the behaviour DDP's `find_unused_parameters=True` gives the reference when a rank's rays miss a
+                 sub-field (fields/PreSight/ingp_field_ms.py:103).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+
+class GradSynchronizer:
+    """Average gradients across ranks.   sync = GradSynchronizer(params); loss.backward(); sync.finish()"""
+
+    def __init__(self, params: Iterable[nn.Parameter], group: Optional[dist.ProcessGroup] = None,
+                 overlap: bool = True, min_async_numel: int = 1 << 16) -> None:
+        self.params: List[nn.Parameter] = [p for p in params if p.requires_grad]
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.overlap = overlap
+        self.min_async_numel = min_async_numel
+        # gloo has no AVG: sum, then scale
+        self._avg = dist.is_initialized() and dist.get_backend(group) == "nccl"
+        self._op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        self._pending = []       # (work, grad)
+        self._done = set()
+        self._handles = []
+        if self.world > 1 and overlap:
+            for p in self.params:
+                if p.numel() >= min_async_numel:
+                    self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad_ready))
+
+    def _on_grad_ready(self, p: nn.Parameter) -> None:
+        if p.grad is None:
+            return
+        self._pending.append((dist.all_reduce(p.grad, op=self._op, group=self.group, async_op=True), p.grad))
+        self._done.add(id(p))
+
+    def finish(self) -> None:
+        """Reduce everything not already in flight (as one flat buffer per dtype) and wait."""
+        if self.world <= 1:
+            return
+        rest = [p for p in self.params if id(p) not in self._done]
+        if self.overlap:
+            rest = [p for p in rest if p.grad is not None]        # same set on every rank by contract
+        big = [p for p in rest if p.numel() >= self.min_async_numel]
+        small = [p for p in rest if p.numel() < self.min_async_numel]
+        for p in big:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            self._pending.append((dist.all_reduce(p.grad, op=self._op, group=self.group, async_op=True), p.grad))
+        if small:
+            flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in small])
+            dist.all_reduce(flat, op=self._op, group=self.group)
+            if not self._avg:
+                flat.div_(self.world)
+            off = 0
+            for p in small:
+                n = p.numel()
+                if p.grad is None:
+                    p.grad = torch.empty_like(p)
+                p.grad.copy_(flat[off:off + n].view_as(p))
+                off += n
+        for work, grad in self._pending:
+            work.wait()
+            if not self._avg:
+                grad.div_(self.world)
+        self._pending.clear()
+        self._done.clear()
+
+    def remove(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles.clear()
+
+
+def shard_range(n_units: int, rank: int, world: int):
+    """Contiguous shard [lo, hi) of `n_units` independent units (rays, tiles) for `rank` — no communication."""
+    per = (n_units + world - 1) // world
+    lo = min(rank * per, n_units)
+    return lo, min(lo + per, n_units)

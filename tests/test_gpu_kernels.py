@@ -125,32 +125,55 @@ def _make_mlp(g, n_in, hidden, n_layers, n_out):
     return ws, bs
 
 
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
 @pytest.mark.parametrize("shape", SHAPES)
-@pytest.mark.parametrize("prec,tol", [(0, TOL32), (1, TOL16)])
-def test_mlp_forward_backward(ops, shape, prec, tol):
+@pytest.mark.parametrize("prec", [0, 1])
+def test_mlp_forward_backward(ops, shape, prec):
+    """prec 0 (3xTF32): everything within 1e-3 of the fp32 oracle.
+    prec 1 (bf16): outputs within 1e-2 of the fp32 oracle; gradients are checked tightly against the oracle's
+    bf16-operand emulation (ReLU-mask flips make a max-norm comparison with fp32 gradients meaningless) and in
+    relative L2 against the fp32 oracle."""
     n_in, hidden, n_layers, n_out, act = shape
     g = torch.Generator().manual_seed(n_in * 131 + n_out)
     ws, bs = _make_mlp(g, n_in, hidden, n_layers, n_out)
     P = 1000  # not a multiple of the 128-point tile
     x = torch.randn(P, n_in, generator=g)
     dy = torch.randn(P, n_out, generator=g)
-    # oracle
-    wc = [w.clone().requires_grad_(True) for w in ws]
-    bc = [b.clone().requires_grad_(True) for b in bs]
-    xc = x.clone().requires_grad_(True)
-    yc = O.mlp_forward(xc, O.Mlp(wc, bc, "sigmoid" if act == 2 else None))
-    yc.backward(dy)
-    # kernel
+
+    def run_oracle(fn):
+        wc = [w.clone().requires_grad_(True) for w in ws]
+        bc = [b.clone().requires_grad_(True) for b in bs]
+        xc = x.clone().requires_grad_(True)
+        yc = fn(xc, O.Mlp(wc, bc, "sigmoid" if act == 2 else None))
+        yc.backward(dy)
+        return yc.detach(), xc.grad, [w.grad for w in wc], [b.grad for b in bc]
+
+    y32, dx32, dW32, db32 = run_oracle(O.mlp_forward)
     wg = [w.to(DEV).requires_grad_(True) for w in ws]
     bg = [b.to(DEV).requires_grad_(True) for b in bs]
     xg = x.to(DEV).requires_grad_(True)
     yg = ops.mlp(xg, wg, bg, act, prec)
-    assert_close(yg.cpu(), yc, tol, "y")
     yg.backward(dy.to(DEV))
-    assert_close(xg.grad.cpu(), xc.grad, tol, "dx")
-    for i in range(n_layers):
-        assert_close(wg[i].grad.cpu(), wc[i].grad, tol, f"dW{i}")
-        assert_close(bg[i].grad.cpu(), bc[i].grad, tol, f"db{i}")
+    if prec == 0:
+        assert_close(yg.cpu(), y32, TOL32, "y")
+        assert_close(xg.grad.cpu(), dx32, TOL32, "dx")
+        for i in range(n_layers):
+            assert_close(wg[i].grad.cpu(), dW32[i], TOL32, f"dW{i}")
+            assert_close(bg[i].grad.cpu(), db32[i], TOL32, f"db{i}")
+    else:
+        assert_close(yg.cpu(), y32, TOL16, "y vs fp32 oracle")
+        y16, dx16, dW16, db16 = run_oracle(O.mlp_forward_bf16_emulated)
+        assert_close(yg.cpu(), y16, 1e-4, "y vs bf16 emulation")
+        assert rel_l2(xg.grad.cpu(), dx16) < 5e-3, "dx vs bf16 emulation"
+        assert rel_l2(xg.grad.cpu(), dx32) < 8e-2, "dx vs fp32 oracle"
+        for i in range(n_layers):
+            assert rel_l2(wg[i].grad.cpu(), dW16[i]) < 5e-3, f"dW{i} vs bf16 emulation"
+            assert rel_l2(bg[i].grad.cpu(), db16[i]) < 5e-3, f"db{i} vs bf16 emulation"
+            assert rel_l2(wg[i].grad.cpu(), dW32[i]) < 8e-2, f"dW{i} vs fp32 oracle"
 
 
 def test_mlp_multi_tile_and_empty(ops):

@@ -1,0 +1,76 @@
+"""Host-side data-parallel logic on CPU: world_size-2 gloo processes (no GPU)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, overlap, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from presight_b200.parallel import GradSynchronizer, shard_range
+    torch.manual_seed(0)
+    big = torch.nn.Parameter(torch.zeros(1 << 17))          # "hash table": async path
+    small = [torch.nn.Parameter(torch.zeros(64, 8)), torch.nn.Parameter(torch.zeros(64))]
+    unused = torch.nn.Parameter(torch.zeros(1 << 17))       # a sub-field no ray of this rank visited
+    params = [big, *small, unused]
+    sync = GradSynchronizer(params, overlap=overlap, min_async_numel=1 << 16)
+    # every rank gets its own shard of "rays"
+    lo, hi = shard_range(1000, rank, world)
+    x = torch.arange(lo, hi, dtype=torch.float32)
+    loss = (big[: x.numel()] * x).sum() + (small[0].sum() + small[1].sum()) * (rank + 1)
+    if not overlap and rank == 1:
+        loss = loss + unused.sum() * 3.0                    # only rank 1 touches the "unused" parameter
+    loss.backward()
+    sync.finish()
+    out = {"big": big.grad.clone(), "s0": small[0].grad.clone(), "s1": small[1].grad.clone(),
+           "unused": None if unused.grad is None else unused.grad.clone(), "range": (lo, hi)}
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("overlap", [True, False])
+def test_grad_synchronizer_gloo_world2(overlap):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, overlap, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0]["range"] == (0, 500) and res[1]["range"] == (500, 1000)
+    # mean over ranks of the per-rank gradients
+    want_big = torch.zeros(1 << 17)
+    want_big[:500] = (torch.arange(0, 500) + torch.arange(500, 1000)).float() / 2
+    for r in range(2):
+        assert torch.allclose(res[r]["big"], want_big)
+        assert torch.allclose(res[r]["s0"], torch.full((64, 8), 1.5))
+        assert torch.allclose(res[r]["s1"], torch.full((64,), 1.5))
+        if not overlap:
+            assert torch.allclose(res[r]["unused"], torch.full((1 << 17,), 1.5))   # zeros on rank 0, 3 on rank 1
+
+
+def test_shard_range_covers_everything():
+    from presight_b200.parallel import shard_range
+    for n in (0, 1, 7, 8, 1000, 65536):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
