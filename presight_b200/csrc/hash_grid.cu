@@ -1,101 +1,152 @@
 // Kernel #1: stand-alone multiresolution hash encoding, forward / backward / index probe.
-// Thread mapping: one thread per (point, level), level fastest — the [P, L*F] output row of a
-// point is written by L consecutive lanes, so stores (fwd) and dout loads (bwd) are fully
-// coalesced for any L, while each lane keeps 8 independent vector gathers in flight.
+//
+// Launch shape: grid = (point blocks, level groups), level group = blockIdx.y.  CTAs are dispatched x-fastest,
+// so the machine works through the table level group by level group: the live working set is LPT levels
+// (chosen <= ~40 MiB) instead of the whole table, which keeps the random gathers / scatter-adds resident in the
+// 126 MB L2 — DRAM sees each level's table roughly once per pass instead of one sector per corner.
+// Within a CTA consecutive threads are consecutive points (= consecutive samples along a ray).
+//
+// x-neighbour merge: the hash multiplies x by 1, so for an even floor coordinate the two x-corners of a (y,z)
+// pair are rows r and r^1 — one aligned 2F-float slot.  Backward then issues ONE vector reduction
+// (red.global.add.v4.f32 for F=2, .v2 for F=1) for both corners.
 #include "hash_grid.cuh"
 
 namespace ps {
 
-template <int F>
+template <int F, int LPT>
 __global__ void __launch_bounds__(256) hash_fwd_kernel(const float* __restrict__ x, int64_t P,
                                                        const float* __restrict__ table, HashParams hp,
                                                        float* __restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P * hp.L) return;
-    const int64_t p = i / hp.L;
-    const int l = (int)(i - p * hp.L);
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int l0 = blockIdx.y * LPT;
     const float px = __ldg(x + 3 * p), py = __ldg(x + 3 * p + 1), pz = __ldg(x + 3 * p + 2);
     const uint32_t mask = (1u << hp.log2_T) - 1u;
-    const Corner8 c = hash_corners(px, py, pz, hp.scale[l], mask);
-    const float* lt = table + ((size_t)l << hp.log2_T) * F;
-    float v[8][F];
+    float o[LPT][F];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) gather_row<F>(lt, c.row[k], v[k]);
-    float o[F];
-#pragma unroll
-    for (int f = 0; f < F; ++f) {
-        const float t[8] = {v[0][f], v[1][f], v[2][f], v[3][f], v[4][f], v[5][f], v[6][f], v[7][f]};
-        o[f] = trilerp_ref(t, c.ox, c.oy, c.oz);
-    }
-    float* dst = out + i * F;
-    if constexpr (F == 1) {
-        dst[0] = o[0];
-    } else if constexpr (F == 2) {
-        *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
-    } else if constexpr (F == 4) {
-        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-    } else {
-        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
-    }
-}
-
-template <int F, bool WITH_DX>
-__global__ void __launch_bounds__(256) hash_bwd_kernel(const float* __restrict__ x, int64_t P,
-                                                       const float* __restrict__ table, HashParams hp,
-                                                       const float* __restrict__ dout, float* __restrict__ dtable,
-                                                       float* __restrict__ dx) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P * hp.L) return;
-    const int64_t p = i / hp.L;
-    const int l = (int)(i - p * hp.L);
-    const float px = __ldg(x + 3 * p), py = __ldg(x + 3 * p + 1), pz = __ldg(x + 3 * p + 2);
-    const uint32_t mask = (1u << hp.log2_T) - 1u;
-    const float scale = hp.scale[l];
-    const Corner8 c = hash_corners(px, py, pz, scale, mask);
-    float g[F];
-    const float* src = dout + i * F;
-    if constexpr (F == 1) {
-        g[0] = __ldg(src);
-    } else if constexpr (F == 2) {
-        const float2 t = __ldg(reinterpret_cast<const float2*>(src));
-        g[0] = t.x; g[1] = t.y;
-    } else {
-#pragma unroll
-        for (int q = 0; q < F / 4; ++q) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(src) + q);
-            g[4 * q] = t.x; g[4 * q + 1] = t.y; g[4 * q + 2] = t.z; g[4 * q + 3] = t.w;
-        }
-    }
-    float w[8];
-    corner_weights(c.ox, c.oy, c.oz, w);
-    float* lg = dtable + ((size_t)l << hp.log2_T) * F;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        // a zero weight (exact-integer coordinate: ceil == floor) contributes nothing; skip the atomic
-        if (w[k] != 0.f) scatter_row<F>(lg, c.row[k], g, w[k]);
-    }
-    if constexpr (WITH_DX) {
-        // d out / d offset, then d offset / d x = scale (floor/ceil have zero gradient)
+    for (int i = 0; i < LPT; ++i) {
+        const int l = l0 + i;
+        const Corner8 c = hash_corners(px, py, pz, hp.scale[l], mask);
         const float* lt = table + ((size_t)l << hp.log2_T) * F;
         float v[8][F];
 #pragma unroll
         for (int k = 0; k < 8; ++k) gather_row<F>(lt, c.row[k], v[k]);
-        const float ox = c.ox, oy = c.oy, oz = c.oz, mx = 1.f - ox, my = 1.f - oy, mz = 1.f - oz;
-        float gx = 0.f, gy = 0.f, gz = 0.f;
 #pragma unroll
         for (int f = 0; f < F; ++f) {
-            const float f03 = v[0][f] * ox + v[3][f] * mx, f12 = v[1][f] * ox + v[2][f] * mx;
-            const float f56 = v[5][f] * ox + v[6][f] * mx, f47 = v[4][f] * ox + v[7][f] * mx;
-            const float f0312 = f03 * oy + f12 * my, f4756 = f47 * oy + f56 * my;
-            gz += g[f] * (f0312 - f4756);
-            gy += g[f] * (oz * (f03 - f12) + mz * (f47 - f56));
-            gx += g[f] * (oz * (oy * (v[0][f] - v[3][f]) + my * (v[1][f] - v[2][f])) +
-                          mz * (oy * (v[4][f] - v[7][f]) + my * (v[5][f] - v[6][f])));
+            const float t[8] = {v[0][f], v[1][f], v[2][f], v[3][f], v[4][f], v[5][f], v[6][f], v[7][f]};
+            o[i][f] = trilerp_ref(t, c.ox, c.oy, c.oz);
         }
-        atomicAdd(dx + 3 * p, gx * scale);
-        atomicAdd(dx + 3 * p + 1, gy * scale);
-        atomicAdd(dx + 3 * p + 2, gz * scale);
+    }
+    // LPT*F consecutive floats of this point's output row
+    float* dst = out + (p * hp.L + l0) * F;
+    constexpr int NV = LPT * F;
+    const float* src = &o[0][0];
+    if constexpr (NV % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < NV / 4; ++q)
+            reinterpret_cast<float4*>(dst)[q] = make_float4(src[4 * q], src[4 * q + 1], src[4 * q + 2], src[4 * q + 3]);
+    } else if constexpr (NV % 2 == 0) {
+#pragma unroll
+        for (int q = 0; q < NV / 2; ++q) reinterpret_cast<float2*>(dst)[q] = make_float2(src[2 * q], src[2 * q + 1]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) dst[q] = src[q];
+    }
+}
+
+// scatter the two x-corners of one (y,z) pair
+template <int F>
+__device__ __forceinline__ void scatter_xpair(float* __restrict__ lg, uint32_t r_hi, uint32_t r_lo, const float (&g)[F],
+                                              float w_hi, float w_lo) {
+    if constexpr (F <= 2) {
+        if ((r_hi ^ r_lo) == 1u && w_hi != 0.f) {
+            // rows r and r^1: one aligned slot of 2F floats
+            const uint32_t base = r_hi & ~1u;
+            const float wa = (r_hi & 1u) ? w_lo : w_hi, wb = (r_hi & 1u) ? w_hi : w_lo;
+            if constexpr (F == 1)
+                red_add_v2(lg + base, g[0] * wa, g[0] * wb);
+            else
+                red_add_v4(lg + (size_t)base * 2, g[0] * wa, g[1] * wa, g[0] * wb, g[1] * wb);
+            return;
+        }
+    }
+    // a zero weight (exact-integer coordinate: ceil == floor) contributes nothing; skip the atomic
+    if (w_hi != 0.f) scatter_row<F>(lg, r_hi, g, w_hi);
+    if (w_lo != 0.f) scatter_row<F>(lg, r_lo, g, w_lo);
+}
+
+template <int F, int LPT, bool WITH_DX>
+__global__ void __launch_bounds__(256) hash_bwd_kernel(const float* __restrict__ x, int64_t P,
+                                                       const float* __restrict__ table, HashParams hp,
+                                                       const float* __restrict__ dout, float* __restrict__ dtable,
+                                                       float* __restrict__ dx) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int l0 = blockIdx.y * LPT;
+    const float px = __ldg(x + 3 * p), py = __ldg(x + 3 * p + 1), pz = __ldg(x + 3 * p + 2);
+    const uint32_t mask = (1u << hp.log2_T) - 1u;
+    // LPT*F consecutive gradient values of this point
+    constexpr int NV = LPT * F;
+    float gin[NV];
+    const float* src = dout + (p * hp.L + l0) * F;
+    if constexpr (NV % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < NV / 4; ++q) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(src) + q);
+            gin[4 * q] = t.x; gin[4 * q + 1] = t.y; gin[4 * q + 2] = t.z; gin[4 * q + 3] = t.w;
+        }
+    } else if constexpr (NV % 2 == 0) {
+#pragma unroll
+        for (int q = 0; q < NV / 2; ++q) {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(src) + q);
+            gin[2 * q] = t.x; gin[2 * q + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) gin[q] = __ldg(src + q);
+    }
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+    for (int i = 0; i < LPT; ++i) {
+        const int l = l0 + i;
+        const float scale = hp.scale[l];
+        const Corner8 c = hash_corners(px, py, pz, scale, mask);
+        float g[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) g[f] = gin[i * F + f];
+        float w[8];
+        corner_weights(c.ox, c.oy, c.oz, w);
+        float* lg = dtable + ((size_t)l << hp.log2_T) * F;
+        // (y,z) corner pairs in reference order: {x-ceil corner, x-floor corner} = {h0,h3}, {h1,h2}, {h4,h7}, {h5,h6}
+        scatter_xpair<F>(lg, c.row[0], c.row[3], g, w[0], w[3]);
+        scatter_xpair<F>(lg, c.row[1], c.row[2], g, w[1], w[2]);
+        scatter_xpair<F>(lg, c.row[4], c.row[7], g, w[4], w[7]);
+        scatter_xpair<F>(lg, c.row[5], c.row[6], g, w[5], w[6]);
+        if constexpr (WITH_DX) {
+            // d out / d offset, then d offset / d x = scale (floor/ceil have zero gradient)
+            const float* lt = table + ((size_t)l << hp.log2_T) * F;
+            float v[8][F];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) gather_row<F>(lt, c.row[k], v[k]);
+            const float ox = c.ox, oy = c.oy, oz = c.oz, mx = 1.f - ox, my = 1.f - oy, mz = 1.f - oz;
+            float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                const float f03 = v[0][f] * ox + v[3][f] * mx, f12 = v[1][f] * ox + v[2][f] * mx;
+                const float f56 = v[5][f] * ox + v[6][f] * mx, f47 = v[4][f] * ox + v[7][f] * mx;
+                const float f0312 = f03 * oy + f12 * my, f4756 = f47 * oy + f56 * my;
+                az += g[f] * (f0312 - f4756);
+                ay += g[f] * (oz * (f03 - f12) + mz * (f47 - f56));
+                ax += g[f] * (oz * (oy * (v[0][f] - v[3][f]) + my * (v[1][f] - v[2][f])) +
+                              mz * (oy * (v[4][f] - v[7][f]) + my * (v[5][f] - v[6][f])));
+            }
+            gx += ax * scale; gy += ay * scale; gz += az * scale;
+        }
+    }
+    if constexpr (WITH_DX) {
+        atomicAdd(dx + 3 * p, gx);
+        atomicAdd(dx + 3 * p + 1, gy);
+        atomicAdd(dx + 3 * p + 2, gz);
     }
 }
 
@@ -126,28 +177,71 @@ static int fill_params(HashParams& hp, const float* scalings_host, int L, int lo
     return 0;
 }
 
+// levels per thread: the largest of {8,4,2,1} dividing L whose tables (LPT levels) stay well inside L2
+static int pick_lpt(int L, int F, int log2_T) {
+    const double level_bytes = (double)(1ull << log2_T) * F * 4.0;
+    const double budget = 40.0 * 1024 * 1024;
+    for (int lpt : {8, 4, 2}) {
+        if (lpt * F > 16) continue;  // register budget
+        if (L % lpt == 0 && lpt * level_bytes <= budget) return lpt;
+    }
+    return 1;
+}
+
 }  // namespace ps
 
 using namespace ps;
+
+#define PS_DISPATCH_F_LPT(F, LPT, MACRO)                                   \
+    switch (F) {                                                           \
+        case 1:                                                            \
+            switch (LPT) {                                                 \
+                case 8: MACRO(1, 8) break;                                 \
+                case 4: MACRO(1, 4) break;                                 \
+                case 2: MACRO(1, 2) break;                                 \
+                default: MACRO(1, 1) break;                                \
+            }                                                              \
+            break;                                                         \
+        case 2:                                                            \
+            switch (LPT) {                                                 \
+                case 8: MACRO(2, 8) break;                                 \
+                case 4: MACRO(2, 4) break;                                 \
+                case 2: MACRO(2, 2) break;                                 \
+                default: MACRO(2, 1) break;                                \
+            }                                                              \
+            break;                                                         \
+        case 4:                                                            \
+            switch (LPT) {                                                 \
+                case 4: MACRO(4, 4) break;                                 \
+                case 2: MACRO(4, 2) break;                                 \
+                default: MACRO(4, 1) break;                                \
+            }                                                              \
+            break;                                                         \
+        case 8:                                                            \
+            switch (LPT) {                                                 \
+                case 2: MACRO(8, 2) break;                                 \
+                default: MACRO(8, 1) break;                                \
+            }                                                              \
+            break;                                                         \
+    }
 
 extern "C" int ps_hash_fwd(const float* x01, int64_t P, const float* table, const float* scalings_host, int L, int F,
                            int log2_T, float* out, void* stream) {
     HashParams hp;
     if (int e = fill_params(hp, scalings_host, L, log2_T)) return e;
+    PS_REQUIRE(F == 1 || F == 2 || F == 4 || F == 8, "hash_fwd: features_per_level %d not in {1,2,4,8}", F);
     PS_REQUIRE(P >= 0, "hash_fwd: negative P");
     if (P == 0) return 0;
     PS_REQUIRE(x01 && table && out, "hash_fwd: null pointer");
     const int threads = 256;
-    const int64_t blocks = cdiv(P * L, threads);
+    const int64_t blocks = cdiv(P, threads);
     PS_REQUIRE(blocks < (1ll << 31), "hash_fwd: too many points");
     cudaStream_t s = (cudaStream_t)stream;
-    switch (F) {
-        case 1: hash_fwd_kernel<1><<<(unsigned)blocks, threads, 0, s>>>(x01, P, table, hp, out); break;
-        case 2: hash_fwd_kernel<2><<<(unsigned)blocks, threads, 0, s>>>(x01, P, table, hp, out); break;
-        case 4: hash_fwd_kernel<4><<<(unsigned)blocks, threads, 0, s>>>(x01, P, table, hp, out); break;
-        case 8: hash_fwd_kernel<8><<<(unsigned)blocks, threads, 0, s>>>(x01, P, table, hp, out); break;
-        default: PS_REQUIRE(false, "hash_fwd: features_per_level %d not in {1,2,4,8}", F);
-    }
+    const int lpt = pick_lpt(L, F, log2_T);
+    const dim3 grid((unsigned)blocks, (unsigned)(L / lpt));
+#define PS_FWD(FF, LL) hash_fwd_kernel<FF, LL><<<grid, threads, 0, s>>>(x01, P, table, hp, out);
+    PS_DISPATCH_F_LPT(F, lpt, PS_FWD)
+#undef PS_FWD
     return check_launch("hash_fwd");
 }
 
@@ -155,27 +249,24 @@ extern "C" int ps_hash_bwd(const float* x01, int64_t P, const float* table, cons
                            int log2_T, const float* dout, float* dtable, float* dx, void* stream) {
     HashParams hp;
     if (int e = fill_params(hp, scalings_host, L, log2_T)) return e;
+    PS_REQUIRE(F == 1 || F == 2 || F == 4 || F == 8, "hash_bwd: features_per_level %d not in {1,2,4,8}", F);
     PS_REQUIRE(P >= 0, "hash_bwd: negative P");
     if (P == 0) return 0;
     PS_REQUIRE(x01 && dout && dtable, "hash_bwd: null pointer");
     PS_REQUIRE(dx == nullptr || table != nullptr, "hash_bwd: dx requested but table is null");
     const int threads = 256;
-    const int64_t blocks = cdiv(P * L, threads);
+    const int64_t blocks = cdiv(P, threads);
     PS_REQUIRE(blocks < (1ll << 31), "hash_bwd: too many points");
     cudaStream_t s = (cudaStream_t)stream;
-#define PS_LAUNCH_BWD(FF)                                                                                     \
-    if (dx)                                                                                                   \
-        hash_bwd_kernel<FF, true><<<(unsigned)blocks, threads, 0, s>>>(x01, P, table, hp, dout, dtable, dx);  \
-    else                                                                                                      \
-        hash_bwd_kernel<FF, false><<<(unsigned)blocks, threads, 0, s>>>(x01, P, table, hp, dout, dtable, dx);
-    switch (F) {
-        case 1: PS_LAUNCH_BWD(1) break;
-        case 2: PS_LAUNCH_BWD(2) break;
-        case 4: PS_LAUNCH_BWD(4) break;
-        case 8: PS_LAUNCH_BWD(8) break;
-        default: PS_REQUIRE(false, "hash_bwd: features_per_level %d not in {1,2,4,8}", F);
-    }
-#undef PS_LAUNCH_BWD
+    const int lpt = pick_lpt(L, F, log2_T);
+    const dim3 grid((unsigned)blocks, (unsigned)(L / lpt));
+#define PS_BWD(FF, LL)                                                                                  \
+    if (dx)                                                                                             \
+        hash_bwd_kernel<FF, LL, true><<<grid, threads, 0, s>>>(x01, P, table, hp, dout, dtable, dx);    \
+    else                                                                                                \
+        hash_bwd_kernel<FF, LL, false><<<grid, threads, 0, s>>>(x01, P, table, hp, dout, dtable, dx);
+    PS_DISPATCH_F_LPT(F, lpt, PS_BWD)
+#undef PS_BWD
     return check_launch("hash_bwd");
 }
 
