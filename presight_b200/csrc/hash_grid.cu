@@ -54,25 +54,41 @@ __global__ void __launch_bounds__(256) hash_fwd_kernel(const float* __restrict__
     }
 }
 
-// scatter the two x-corners of one (y,z) pair
+// scatter the (already weighted) gradient of the two x-corners of one (y,z) pair; `live_*` is false when the
+// corner's interpolation weight was exactly zero for every contributing sample (ceil == floor), in which case the
+// atomic is skipped
 template <int F>
-__device__ __forceinline__ void scatter_xpair(float* __restrict__ lg, uint32_t r_hi, uint32_t r_lo, const float (&g)[F],
-                                              float w_hi, float w_lo) {
+__device__ __forceinline__ void scatter_xpair(float* __restrict__ lg, uint32_t r_hi, uint32_t r_lo,
+                                              const float (&v_hi)[F], const float (&v_lo)[F], bool live_hi,
+                                              bool live_lo) {
     if constexpr (F <= 2) {
-        if ((r_hi ^ r_lo) == 1u && w_hi != 0.f) {
+        if ((r_hi ^ r_lo) == 1u && live_hi && live_lo) {
             // rows r and r^1: one aligned slot of 2F floats
             const uint32_t base = r_hi & ~1u;
-            const float wa = (r_hi & 1u) ? w_lo : w_hi, wb = (r_hi & 1u) ? w_hi : w_lo;
+            const bool hi_first = !(r_hi & 1u);
             if constexpr (F == 1)
-                red_add_v2(lg + base, g[0] * wa, g[0] * wb);
+                red_add_v2(lg + base, hi_first ? v_hi[0] : v_lo[0], hi_first ? v_lo[0] : v_hi[0]);
             else
-                red_add_v4(lg + (size_t)base * 2, g[0] * wa, g[1] * wa, g[0] * wb, g[1] * wb);
+                red_add_v4(lg + (size_t)base * 2, hi_first ? v_hi[0] : v_lo[0], hi_first ? v_hi[1] : v_lo[1],
+                           hi_first ? v_lo[0] : v_hi[0], hi_first ? v_lo[1] : v_hi[1]);
             return;
         }
     }
-    // a zero weight (exact-integer coordinate: ceil == floor) contributes nothing; skip the atomic
-    if (w_hi != 0.f) scatter_row<F>(lg, r_hi, g, w_hi);
-    if (w_lo != 0.f) scatter_row<F>(lg, r_lo, g, w_lo);
+    if (live_hi) scatter_row<F>(lg, r_hi, v_hi, 1.f);
+    if (live_lo) scatter_row<F>(lg, r_lo, v_lo, 1.f);
+}
+
+// Segmented warp reduction: lanes of one segment (consecutive lanes, first lane flagged in `heads`) are summed
+// into the segment's head lane.
+__device__ __forceinline__ float seg_reduce(float v, uint32_t heads, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float other = __shfl_down_sync(0xffffffffu, v, o);
+        // add lane+o only if no segment starts in (lane, lane+o]
+        const bool same = (lane + o < 32) && ((((heads >> lane) >> 1) & ((1u << o) - 1u)) == 0u);
+        if (same) v += other;
+    }
+    return v;
 }
 
 template <int F, int LPT, bool WITH_DX>
@@ -80,8 +96,11 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const float* __restrict__
                                                        const float* __restrict__ table, HashParams hp,
                                                        const float* __restrict__ dout, float* __restrict__ dtable,
                                                        float* __restrict__ dx) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
+    // every lane stays alive (full-mask shuffles below); out-of-range lanes carry zero gradient
+    const int64_t pi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = pi < P;
+    const int64_t p = valid ? pi : P - 1;
+    const int lane = threadIdx.x & 31;
     const int l0 = blockIdx.y * LPT;
     const float px = __ldg(x + 3 * p), py = __ldg(x + 3 * p + 1), pz = __ldg(x + 3 * p + 2);
     const uint32_t mask = (1u << hp.log2_T) - 1u;
@@ -105,48 +124,88 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const float* __restrict__
 #pragma unroll
         for (int q = 0; q < NV; ++q) gin[q] = __ldg(src + q);
     }
+    if (!valid) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) gin[q] = 0.f;
+    }
     float gx = 0.f, gy = 0.f, gz = 0.f;
 #pragma unroll
     for (int i = 0; i < LPT; ++i) {
         const int l = l0 + i;
         const float scale = hp.scale[l];
         const Corner8 c = hash_corners(px, py, pz, scale, mask);
-        float g[F];
-#pragma unroll
-        for (int f = 0; f < F; ++f) g[f] = gin[i * F + f];
         float w[8];
         corner_weights(c.ox, c.oy, c.oz, w);
-        float* lg = dtable + ((size_t)l << hp.log2_T) * F;
-        // (y,z) corner pairs in reference order: {x-ceil corner, x-floor corner} = {h0,h3}, {h1,h2}, {h4,h7}, {h5,h6}
-        scatter_xpair<F>(lg, c.row[0], c.row[3], g, w[0], w[3]);
-        scatter_xpair<F>(lg, c.row[1], c.row[2], g, w[1], w[2]);
-        scatter_xpair<F>(lg, c.row[4], c.row[7], g, w[4], w[7]);
-        scatter_xpair<F>(lg, c.row[5], c.row[6], g, w[5], w[6]);
+        // weighted per-corner gradients and "weight was non-zero" flags
+        float v[8][F];
+        uint32_t live = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (w[k] != 0.f && valid) live |= 1u << k;
+#pragma unroll
+            for (int f = 0; f < F; ++f) v[k][f] = gin[i * F + f] * w[k];
+        }
+        // ---- warp pre-aggregation: consecutive samples of a ray that fall into the same grid cell hit the same
+        // 8 rows; sum them inside the warp and let the first lane of each run issue the atomics.  The cell is
+        // identified by its floor coordinates plus the three "exact integer" flags (ceil = floor + !exact).
+        const int kx = (int)floorf(__fmul_rn(px, scale)), ky = (int)floorf(__fmul_rn(py, scale)),
+                  kz = (int)floorf(__fmul_rn(pz, scale));
+        const int kf = (c.ox == 0.f ? 1 : 0) | (c.oy == 0.f ? 2 : 0) | (c.oz == 0.f ? 4 : 0) | (valid ? 0 : 8);
+        // (shuffles executed unconditionally by all 32 lanes, compared afterwards)
+        const int nx = __shfl_up_sync(0xffffffffu, kx, 1), ny = __shfl_up_sync(0xffffffffu, ky, 1),
+                  nz = __shfl_up_sync(0xffffffffu, kz, 1), nf = __shfl_up_sync(0xffffffffu, kf, 1);
+        const bool same_prev = lane > 0 && nx == kx && ny == ky && nz == kz && nf == kf;
+        const uint32_t heads = __ballot_sync(0xffffffffu, !same_prev);
+        bool issue = valid;
+        if (heads != 0xffffffffu) {   // warp-uniform: at least one run of length > 1
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int f = 0; f < F; ++f) v[k][f] = seg_reduce(v[k][f], heads, lane);
+            // a corner is live for the run if it was live for any member
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t other = __shfl_down_sync(0xffffffffu, live, o);
+                if ((lane + o < 32) && ((((heads >> lane) >> 1) & ((1u << o) - 1u)) == 0u)) live |= other;
+            }
+            issue = valid && !same_prev;
+        }
+        if (issue) {
+            float* lg = dtable + ((size_t)l << hp.log2_T) * F;
+            // (y,z) corner pairs in reference order: {x-ceil, x-floor} = {h0,h3}, {h1,h2}, {h4,h7}, {h5,h6}
+            scatter_xpair<F>(lg, c.row[0], c.row[3], v[0], v[3], live & 1u, live & 8u);
+            scatter_xpair<F>(lg, c.row[1], c.row[2], v[1], v[2], live & 2u, live & 4u);
+            scatter_xpair<F>(lg, c.row[4], c.row[7], v[4], v[7], live & 16u, live & 128u);
+            scatter_xpair<F>(lg, c.row[5], c.row[6], v[5], v[6], live & 32u, live & 64u);
+        }
         if constexpr (WITH_DX) {
             // d out / d offset, then d offset / d x = scale (floor/ceil have zero gradient)
             const float* lt = table + ((size_t)l << hp.log2_T) * F;
-            float v[8][F];
+            float t[8][F];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) gather_row<F>(lt, c.row[k], v[k]);
+            for (int k = 0; k < 8; ++k) gather_row<F>(lt, c.row[k], t[k]);
             const float ox = c.ox, oy = c.oy, oz = c.oz, mx = 1.f - ox, my = 1.f - oy, mz = 1.f - oz;
             float ax = 0.f, ay = 0.f, az = 0.f;
 #pragma unroll
             for (int f = 0; f < F; ++f) {
-                const float f03 = v[0][f] * ox + v[3][f] * mx, f12 = v[1][f] * ox + v[2][f] * mx;
-                const float f56 = v[5][f] * ox + v[6][f] * mx, f47 = v[4][f] * ox + v[7][f] * mx;
+                const float g = gin[i * F + f];
+                const float f03 = t[0][f] * ox + t[3][f] * mx, f12 = t[1][f] * ox + t[2][f] * mx;
+                const float f56 = t[5][f] * ox + t[6][f] * mx, f47 = t[4][f] * ox + t[7][f] * mx;
                 const float f0312 = f03 * oy + f12 * my, f4756 = f47 * oy + f56 * my;
-                az += g[f] * (f0312 - f4756);
-                ay += g[f] * (oz * (f03 - f12) + mz * (f47 - f56));
-                ax += g[f] * (oz * (oy * (v[0][f] - v[3][f]) + my * (v[1][f] - v[2][f])) +
-                              mz * (oy * (v[4][f] - v[7][f]) + my * (v[5][f] - v[6][f])));
+                az += g * (f0312 - f4756);
+                ay += g * (oz * (f03 - f12) + mz * (f47 - f56));
+                ax += g * (oz * (oy * (t[0][f] - t[3][f]) + my * (t[1][f] - t[2][f])) +
+                           mz * (oy * (t[4][f] - t[7][f]) + my * (t[5][f] - t[6][f])));
             }
             gx += ax * scale; gy += ay * scale; gz += az * scale;
         }
     }
     if constexpr (WITH_DX) {
-        atomicAdd(dx + 3 * p, gx);
-        atomicAdd(dx + 3 * p + 1, gy);
-        atomicAdd(dx + 3 * p + 2, gz);
+        if (valid) {
+            atomicAdd(dx + 3 * p, gx);
+            atomicAdd(dx + 3 * p + 1, gy);
+            atomicAdd(dx + 3 * p + 2, gz);
+        }
     }
 }
 

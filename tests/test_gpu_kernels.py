@@ -181,6 +181,10 @@ def test_mlp_forward_backward(ops, shape, prec):
 def test_mlp_multi_tile_and_empty(ops):
     g = torch.Generator().manual_seed(3)
     ws, bs = _make_mlp(g, 32, 64, 2, 80)
+    # With 2.4 M hidden units a few pre-activations land within float rounding of zero and flip their ReLU against
+    # the CPU oracle; their weight in dW grows like sqrt(P).  This test is about accumulation across tiles, so keep
+    # every unit active (hidden bias +8); mask handling is covered at P = 1000 above.
+    bs[0] = bs[0] + 8.0
     P = 128 * 300 + 17        # more tiles than the persistent grid has CTAs
     x = torch.randn(P, 32, generator=g)
     dy = torch.randn(P, 80, generator=g)
