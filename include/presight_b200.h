@@ -68,6 +68,9 @@ int ps_normalize_positions(const float* pos, int64_t P, const float* aabb_host, 
 /* Frustums.get_positions (cameras/rays.py:49-58): pos[n,s,:] = o[n] + d[n]*(bins[n,s]+bins[n,s+1])/2 */
 int ps_sample_positions(const float* origins, const float* dirs, const float* eu_bins, int64_t N, int S,
                         float* pos, void* stream);
+/* ps_sample_positions + ps_normalize_positions in one pass: bin edges -> unit-cube sample positions + selector. */
+int ps_ray_points(const float* origins, const float* dirs, const float* eu_bins, int64_t N, int S,
+                  const float* aabb_host, int contract, float* x01, uint8_t* selector, void* stream);
 /* SHEncoding(levels=4).pytorch_fwd on (d+1)/2 (utils/math.py:27-74, fields/base_field.py:136-142).
  * dirs [P,3]; mapped == 0: raw directions (the kernel applies (d+1)/2), mapped != 0: already (d+1)/2; out [P,16]. */
 int ps_sh4(const float* dirs, int64_t P, int mapped, float* out, void* stream);
@@ -80,7 +83,9 @@ int ps_nearest_centroid(const float* pos, int64_t P, const float* centroids, int
  *   x [P,dims[0]] -> y [P,dims[n_layers]];  W_host[i] -> device fp32 [dims[i+1], dims[i]] (nn.Linear layout),
  *   b_host[i] -> device fp32 [dims[i+1]].  W_host/b_host/dims_host are HOST arrays.
  *   Hidden activations are never written to HBM; backward recomputes them.
- *   precision: 0 = fp32 CUDA cores (1e-3 parity), 1 = bf16 tensor-core MMA with fp32 accumulate (1e-2 parity).
+ *   precision: 0 = error-compensated 3xTF32 tensor-core MMA, fp32-grade (1e-3 parity class),
+ *              1 = bf16 tensor-core MMA with fp32 accumulate (1e-2 parity class).
+ *   Supported shapes (padded to multiples of 16) are listed in csrc/mlp_dispatch.cuh; others return status 3.
  */
 int ps_mlp_fwd(const float* x, int64_t P, const float* const* W_host, const float* const* b_host,
                const int* dims_host, int n_layers, int out_act, int precision, float* y, void* stream);
@@ -89,6 +94,27 @@ int ps_mlp_fwd(const float* x, int64_t P, const float* const* W_host, const floa
 int ps_mlp_bwd(const float* x, const float* y, const float* dy, int64_t P, const float* const* W_host,
                const float* const* b_host, const int* dims_host, int n_layers, int out_act, int precision,
                float* dx, float* const* dW_host, float* const* db_host, void* stream);
+/* Segmented variant: the logical input row of point r is the concatenation of up to PS_MLP_MAX_SEGMENTS column
+ * segments (replaces the torch.cat / torch.split copies of ingp_field.py:186, 204-228): segment s supplies `width`
+ * columns from src[(r / group) * stride + col0 + c].  group > 1 = a per-ray vector shared by `group` consecutive
+ * points (view direction SH, appearance embedding).  On backward `dst` (nullable) receives the input gradient with the
+ * same addressing; for group > 1 the group's gradients are summed into dst (dst zero-filled by the caller).
+ * Density epilogue (ingp_field.py:187-190, prop_density_field.py:148-152): if density_out != NULL,
+ * density_out[r] = exp(y[r,0]) * sel[r] (sel nullable = 1); y may then be NULL.  On backward, d_density (nullable)
+ * replaces the gradient of column 0 by d_density[r]*sel[r]*exp(clamp(y[r,0],-15,15)) (activations.py:38-41); dy nullable. */
+#define PS_MLP_MAX_SEGMENTS 3
+typedef struct {
+    const float* src;
+    float* dst;
+    int64_t stride;
+    int col0, width, group;
+} ps_row_segment;
+int ps_mlp_fwd_ex(const ps_row_segment* segs_host, int n_seg, int64_t P, const float* const* W_host,
+                  const float* const* b_host, const int* dims_host, int n_layers, int out_act, int precision, float* y,
+                  const uint8_t* sel, float* density_out, void* stream);
+int ps_mlp_bwd_ex(const ps_row_segment* segs_host, int n_seg, const float* dy, int64_t P, const float* const* W_host,
+                  const float* const* b_host, const int* dims_host, int n_layers, int out_act, int precision,
+                  float* const* dW_host, float* const* db_host, const uint8_t* sel, const float* d_density, void* stream);
 /* trunc_exp (field_components/activations.py:28-41) fused with the selector multiply
  * (ingp_field.py:189-190): y = exp(x)*sel ; dx = dy*sel*exp(clamp(x,-15,15)). sel nullable. */
 int ps_trunc_exp_fwd(const float* x, const uint8_t* sel, int64_t P, int64_t x_stride, float* y, void* stream);

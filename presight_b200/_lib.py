@@ -29,6 +29,9 @@ SIGNATURES = {
     "ps_hash_indices": [_p, _i64, _fp, _i, _i, _p, _p, _p],
     "ps_normalize_positions": [_p, _i64, _fp, _i, _p, _p, _p],
     "ps_sample_positions": [_p, _p, _p, _i64, _i, _p, _p],
+    "ps_ray_points": [_p, _p, _p, _i64, _i, _fp, _i, _p, _p, _p],
+    "ps_mlp_fwd_ex": [_p, _i, _i64, _pp, _pp, _ip, _i, _i, _i, _p, _p, _p, _p],
+    "ps_mlp_bwd_ex": [_p, _i, _p, _i64, _pp, _pp, _ip, _i, _i, _i, _pp, _pp, _p, _p, _p],
     "ps_sh4": [_p, _i64, _i, _p, _p],
     "ps_nearest_centroid": [_p, _i64, _p, _i, _p, _p],
     "ps_mlp_fwd": [_p, _i64, _pp, _pp, _ip, _i, _i, _i, _p, _p],
@@ -109,6 +112,23 @@ def host_floats(vals: Sequence[float]):
 
 def host_ptrs(tensors: Sequence[Optional[torch.Tensor]]):
     arr = (C.c_void_p * len(tensors))(*[None if t is None else ptr(t) for t in tensors])
+    return arr
+
+
+class RowSegment(C.Structure):
+    """ps_row_segment of include/presight_b200.h."""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("stride", C.c_int64), ("col0", C.c_int),
+                ("width", C.c_int), ("group", C.c_int)]
+
+
+def host_segments(segs):
+    """segs: iterable of (src tensor, dst tensor|None, stride, col0, width, group)."""
+    segs = list(segs)
+    arr = (RowSegment * len(segs))()
+    for i, (src, dst, stride, col0, width, group) in enumerate(segs):
+        arr[i].src = src.data_ptr()
+        arr[i].dst = None if dst is None else dst.data_ptr()
+        arr[i].stride, arr[i].col0, arr[i].width, arr[i].group = int(stride), int(col0), int(width), int(group)
     return arr
 
 

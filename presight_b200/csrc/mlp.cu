@@ -34,14 +34,47 @@ static int run(int K0, int H, int NHID, int NOUT, int prec, bool bwd, const MlpA
     return r;
 }
 
-extern "C" int ps_mlp_fwd(const float* x, int64_t P, const float* const* W_host, const float* const* b_host,
-                          const int* dims_host, int n_layers, int out_act, int precision, float* y, void* stream) {
+static int fill_segments(MlpArgs& a, const ps_row_segment* segs, int n_seg, int in_dim, bool bwd) {
+    PS_REQUIRE(segs != nullptr && n_seg >= 1 && n_seg <= PS_MLP_MAX_SEGMENTS, "mlp: %d input segments (1..%d)", n_seg,
+               PS_MLP_MAX_SEGMENTS);
+    int col = 0;
+    a.nseg = n_seg;
+    a.any_group_dst = 0;
+    a.want_dx = 0;
+    for (int s = 0; s < n_seg; ++s) {
+        PS_REQUIRE(segs[s].src != nullptr, "mlp: segment %d has no source", s);
+        PS_REQUIRE(segs[s].width >= 1 && segs[s].group >= 1, "mlp: segment %d width/group invalid", s);
+        PS_REQUIRE(segs[s].group == 1 || segs[s].group % 16 == 0,
+                   "mlp: segment %d group %d must be 1 or a multiple of 16 (a warp's 16 rows share one group)", s,
+                   segs[s].group);
+        a.seg[s].src = segs[s].src;
+        a.seg[s].dst = bwd ? segs[s].dst : nullptr;
+        a.seg[s].stride = segs[s].stride;
+        a.seg[s].col0 = segs[s].col0;
+        a.seg[s].begin = col;
+        a.seg[s].end = col + segs[s].width;
+        a.seg[s].group = segs[s].group;
+        col += segs[s].width;
+        if (a.seg[s].dst) {
+            a.want_dx = 1;
+            if (segs[s].group > 1) a.any_group_dst = 1;
+        }
+    }
+    PS_REQUIRE(col == in_dim, "mlp: segments cover %d columns but the first layer expects %d", col, in_dim);
+    return 0;
+}
+
+extern "C" int ps_mlp_fwd_ex(const ps_row_segment* segs_host, int n_seg, int64_t P, const float* const* W_host,
+                             const float* const* b_host, const int* dims_host, int n_layers, int out_act,
+                             int precision, float* y, const uint8_t* sel, float* density_out, void* stream) {
     int K0, H, NHID, NOUT;
     if (int e = resolve(dims_host, n_layers, K0, H, NHID, NOUT)) return e;
-    if (P == 0) return 0;
-    PS_REQUIRE(x && y && W_host && b_host, "mlp_fwd: null pointer");
     MlpArgs a{};
-    a.x = x; a.y = y; a.P = P; a.in_dim = dims_host[0]; a.out_dim = dims_host[n_layers]; a.out_act = out_act;
+    if (int e = fill_segments(a, segs_host, n_seg, dims_host[0], false)) return e;
+    if (P == 0) return 0;
+    PS_REQUIRE((y || density_out) && W_host && b_host, "mlp_fwd: null pointer");
+    a.y = y; a.P = P; a.in_dim = dims_host[0]; a.out_dim = dims_host[n_layers]; a.out_act = out_act;
+    a.sel = sel; a.density_out = density_out;
     for (int i = 0; i < n_layers; ++i) {
         PS_REQUIRE(W_host[i] != nullptr, "mlp_fwd: weight %d is null", i);
         a.W[i] = W_host[i];
@@ -50,17 +83,18 @@ extern "C" int ps_mlp_fwd(const float* x, int64_t P, const float* const* W_host,
     return run(K0, H, NHID, NOUT, precision, false, a, (cudaStream_t)stream, dims_host, n_layers);
 }
 
-extern "C" int ps_mlp_bwd(const float* x, const float* y, const float* dy, int64_t P, const float* const* W_host,
-                          const float* const* b_host, const int* dims_host, int n_layers, int out_act, int precision,
-                          float* dx, float* const* dW_host, float* const* db_host, void* stream) {
-    (void)y;  // the forward is recomputed on chip
+extern "C" int ps_mlp_bwd_ex(const ps_row_segment* segs_host, int n_seg, const float* dy, int64_t P,
+                             const float* const* W_host, const float* const* b_host, const int* dims_host,
+                             int n_layers, int out_act, int precision, float* const* dW_host, float* const* db_host,
+                             const uint8_t* sel, const float* d_density, void* stream) {
     int K0, H, NHID, NOUT;
     if (int e = resolve(dims_host, n_layers, K0, H, NHID, NOUT)) return e;
-    if (P == 0) return 0;
-    PS_REQUIRE(x && dy && W_host && b_host && dW_host && db_host, "mlp_bwd: null pointer");
     MlpArgs a{};
-    a.x = x; a.dy = dy; a.dx = dx; a.P = P; a.in_dim = dims_host[0]; a.out_dim = dims_host[n_layers];
-    a.out_act = out_act;
+    if (int e = fill_segments(a, segs_host, n_seg, dims_host[0], true)) return e;
+    if (P == 0) return 0;
+    PS_REQUIRE((dy || d_density) && W_host && b_host && dW_host && db_host, "mlp_bwd: null pointer");
+    a.dy = dy; a.P = P; a.in_dim = dims_host[0]; a.out_dim = dims_host[n_layers]; a.out_act = out_act;
+    a.sel = sel; a.d_density = d_density;
     for (int i = 0; i < n_layers; ++i) {
         PS_REQUIRE(W_host[i] != nullptr && dW_host[i] != nullptr, "mlp_bwd: weight/grad %d is null", i);
         a.W[i] = W_host[i];
@@ -69,4 +103,26 @@ extern "C" int ps_mlp_bwd(const float* x, const float* y, const float* dy, int64
         a.db[i] = db_host[i];
     }
     return run(K0, H, NHID, NOUT, precision, true, a, (cudaStream_t)stream, dims_host, n_layers);
+}
+
+extern "C" int ps_mlp_fwd(const float* x, int64_t P, const float* const* W_host, const float* const* b_host,
+                          const int* dims_host, int n_layers, int out_act, int precision, float* y, void* stream) {
+    PS_REQUIRE(dims_host != nullptr, "mlp: dims_host is null");
+    PS_REQUIRE(P == 0 || x != nullptr, "mlp_fwd: x is null");
+    static const float dummy = 0.f;
+    ps_row_segment seg{x ? x : &dummy, nullptr, dims_host[0], 0, dims_host[0], 1};
+    return ps_mlp_fwd_ex(&seg, 1, P, W_host, b_host, dims_host, n_layers, out_act, precision, y, nullptr, nullptr,
+                         stream);
+}
+
+extern "C" int ps_mlp_bwd(const float* x, const float* y, const float* dy, int64_t P, const float* const* W_host,
+                          const float* const* b_host, const int* dims_host, int n_layers, int out_act, int precision,
+                          float* dx, float* const* dW_host, float* const* db_host, void* stream) {
+    (void)y;  // the forward is recomputed on chip
+    PS_REQUIRE(dims_host != nullptr, "mlp: dims_host is null");
+    PS_REQUIRE(P == 0 || x != nullptr, "mlp_bwd: x is null");
+    static const float dummy = 0.f;
+    ps_row_segment seg{x ? x : &dummy, dx, dims_host[0], 0, dims_host[0], 1};
+    return ps_mlp_bwd_ex(&seg, 1, dy, P, W_host, b_host, dims_host, n_layers, out_act, precision, dW_host, db_host,
+                         nullptr, nullptr, stream);
 }

@@ -11,11 +11,25 @@ constexpr int kTile = 128;
 constexpr int kWarps = kTile / 16;
 constexpr int kThreads = kWarps * 32;
 
+// One source of input columns.  The logical input row of point r is the concatenation of up to 3 segments;
+// segment s supplies columns [begin, end) from src[(r / group) * stride + col0 + (c - begin)].  group > 1 means
+// the segment is shared by `group` consecutive points (a per-ray vector broadcast to the ray's samples).
+// On backward, dst (nullable) receives the input gradient with the same addressing; for group > 1 the gradients
+// of the group's points are summed (warp reduction + atomicAdd, dst must be zero-filled by the caller).
+struct RowSeg {
+    const float* src;
+    float* dst;
+    int64_t stride;
+    int col0, begin, end, group;
+};
+
 struct MlpArgs {
-    const float* x;
-    float* y;
-    const float* dy;
-    float* dx;
+    RowSeg seg[PS_MLP_MAX_SEGMENTS];
+    int nseg;
+    int any_group_dst;  // some segment has group > 1 and dst != null
+    int want_dx;        // some segment has dst != null
+    float* y;           // [P, out_dim] (nullable when only density_out is wanted)
+    const float* dy;    // [P, out_dim] (nullable: zero)
     int64_t P;
     const float* W[PS_MAX_MLP_LAYERS];
     const float* b[PS_MAX_MLP_LAYERS];
@@ -23,6 +37,10 @@ struct MlpArgs {
     float* db[PS_MAX_MLP_LAYERS];
     int in_dim, out_dim;  // real (unpadded) sizes; hidden width is exact
     int out_act;
+    // density epilogue (ingp_field.py:189-190 / activations.py:28-41): density = exp(y[:,0]) * sel
+    const uint8_t* sel;        // [P] nullable (treated as 1)
+    float* density_out;        // [P] nullable
+    const float* d_density;    // [P] nullable; when set, the gradient of column 0 is d_density*sel*exp(clamp(raw))
 };
 
 // Network archetype: K0 -> H -> ... (NHID hidden layers) ... -> NOUT, all padded to multiples of 16.
@@ -63,6 +81,83 @@ __device__ __forceinline__ void store_rows(float* __restrict__ y, int64_t P, int
         if (r0 < P && col + 1 < dim) y[r0 * dim + col + 1] = c[j][1];
         if (r1 < P && col < dim) y[r1 * dim + col] = c[j][2];
         if (r1 < P && col + 1 < dim) y[r1 * dim + col + 1] = c[j][3];
+    }
+}
+
+// ---- segmented input rows -----------------------------------------------------------------------------
+__device__ __forceinline__ int seg_of(const MlpArgs& a, int col) {
+    int s = 0;
+    if (a.nseg > 1 && col >= a.seg[1].begin) s = 1;
+    if (a.nseg > 2 && col >= a.seg[2].begin) s = 2;
+    return s;
+}
+
+template <int KB>
+__device__ __forceinline__ void load_rows_seg(const MlpArgs& a, int64_t row0, int lane, float (&c)[KB][4]) {
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t r0 = row0 + g, r1 = r0 + 8;
+    const bool v0 = r0 < a.P, v1 = r1 < a.P;
+    // per-segment base addresses of the two rows
+    const float* b0[PS_MLP_MAX_SEGMENTS];
+    const float* b1[PS_MLP_MAX_SEGMENTS];
+#pragma unroll
+    for (int s = 0; s < PS_MLP_MAX_SEGMENTS; ++s) {
+        if (s < a.nseg) {
+            const RowSeg& sg = a.seg[s];
+            b0[s] = sg.src + (v0 ? r0 / sg.group : 0) * sg.stride + sg.col0 - sg.begin;
+            b1[s] = sg.src + (v1 ? r1 / sg.group : 0) * sg.stride + sg.col0 - sg.begin;
+        } else {
+            b0[s] = b1[s] = nullptr;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < KB; ++j) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int col = 8 * j + 2 * t + h;
+            float x0 = 0.f, x1 = 0.f;
+            if (col < a.in_dim) {
+                const int s = seg_of(a, col);
+                const float* p0 = s == 0 ? b0[0] : (s == 1 ? b0[1] : b0[2]);
+                const float* p1 = s == 0 ? b1[0] : (s == 1 ? b1[1] : b1[2]);
+                if (v0) x0 = __ldg(p0 + col);
+                if (v1) x1 = __ldg(p1 + col);
+            }
+            c[j][h] = x0;
+            c[j][2 + h] = x1;
+        }
+    }
+}
+
+// input-gradient rows: plain strided store for per-point segments, warp-reduced atomicAdd for per-group segments
+template <int KB>
+__device__ __forceinline__ void store_dx_seg(const MlpArgs& a, int64_t row0, int lane, const float (&d)[KB][4]) {
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t r0 = row0 + g, r1 = r0 + 8;
+    const bool v0 = r0 < a.P, v1 = r1 < a.P;
+#pragma unroll
+    for (int j = 0; j < KB; ++j) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int col = 8 * j + 2 * t + h;
+            const bool live = col < a.in_dim;
+            const int s = live ? seg_of(a, col) : 0;
+            const RowSeg& sg = a.seg[s];
+            if (a.any_group_dst) {
+                // column sum over the warp's 16 rows (all lanes take part; only group segments use it)
+                float sum = (v0 ? d[j][h] : 0.f) + (v1 ? d[j][2 + h] : 0.f);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+                if (live && sg.group > 1 && sg.dst && g == 0 && row0 < a.P)
+                    atomicAdd(sg.dst + (row0 / sg.group) * sg.stride + sg.col0 + (col - sg.begin), sum);
+            }
+            if (live && sg.group == 1 && sg.dst) {
+                float* base = sg.dst + sg.col0 + (col - sg.begin);
+                if (v0) base[r0 * sg.stride] = d[j][h];
+                if (v1) base[r1 * sg.stride] = d[j][2 + h];
+            }
+        }
     }
 }
 
@@ -157,7 +252,7 @@ __global__ void __launch_bounds__(kThreads) mlp_fwd_kernel(MlpArgs a) {
         const int64_t row0 = tile * kTile + warp * 16;
         if (row0 >= a.P) continue;
         float in[S::K0 / 8][4];
-        load_rows<S::K0 / 8>(a.x, a.P, a.in_dim, row0, lane, in);
+        load_rows_seg<S::K0 / 8>(a, row0, lane, in);
         float out[S::NOUT / 8][4];
         if constexpr (S::NHID == 0) {
             layer_forward<S::K0, S::NOUT, PREC>(in, w.w0, w.b0, out, lane);
@@ -185,7 +280,13 @@ __global__ void __launch_bounds__(kThreads) mlp_fwd_kernel(MlpArgs a) {
         } else if (a.out_act == PS_ACT_RELU) {
             relu_inplace<S::NOUT / 8>(out);
         }
-        store_rows<S::NOUT / 8>(a.y, a.P, a.out_dim, row0, lane, out);
+        if (a.density_out && (lane & 3) == 0) {
+            // column 0 lives in block 0 of the lanes with t == 0: q = 0 (row g) and q = 2 (row g + 8)
+            const int64_t r0 = row0 + (lane >> 2), r1 = r0 + 8;
+            if (r0 < a.P) a.density_out[r0] = expf(out[0][0]) * (a.sel ? (float)a.sel[r0] : 1.f);
+            if (r1 < a.P) a.density_out[r1] = expf(out[0][2]) * (a.sel ? (float)a.sel[r1] : 1.f);
+        }
+        if (a.y) store_rows<S::NOUT / 8>(a.y, a.P, a.out_dim, row0, lane, out);
     }
 }
 
@@ -272,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(MlpArgs a) {
         const int srow = warp * 16;
         // ---- recompute the forward, staging every layer's input --------------------------------
         float in[S::K0 / 8][4];
-        load_rows<S::K0 / 8>(a.x, a.P, a.in_dim, row0, lane, in);
+        load_rows_seg<S::K0 / 8>(a, row0, lane, in);
         stage_rows<S::K0, PREC>(in, acts0, srow, lane);
         float dz[S::NOUT / 8][4];
         uint32_t mask[S::NHID > 0 ? S::NHID : 1] = {};
@@ -299,7 +400,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(MlpArgs a) {
                 layer_forward<S::H, S::NOUT, PREC>(h, w.wlast, w.blast, out, lane);
             }
             // ---- gradient w.r.t. the last pre-activation ----------------------------------------
-            load_rows<S::NOUT / 8>(a.dy, a.P, a.out_dim, row0, lane, dz);
+            if (a.dy) {
+                load_rows<S::NOUT / 8>(a.dy, a.P, a.out_dim, row0, lane, dz);
+            } else {
+#pragma unroll
+                for (int j = 0; j < S::NOUT / 8; ++j) dz[j][0] = dz[j][1] = dz[j][2] = dz[j][3] = 0.f;
+            }
+            if (a.d_density && (lane & 3) == 0) {
+                // gradient of column 0 comes from the density: d raw = d density * sel * exp(clamp(raw, -15, 15))
+                const int64_t r0 = row0 + (lane >> 2), r1 = r0 + 8;
+                dz[0][0] = r0 < a.P ? a.d_density[r0] * (a.sel ? (float)a.sel[r0] : 1.f) *
+                                          expf(fminf(fmaxf(out[0][0], -15.f), 15.f)) : 0.f;
+                dz[0][2] = r1 < a.P ? a.d_density[r1] * (a.sel ? (float)a.sel[r1] : 1.f) *
+                                          expf(fminf(fmaxf(out[0][2], -15.f), 15.f)) : 0.f;
+            }
             if (a.out_act == PS_ACT_SIGMOID) {
 #pragma unroll
                 for (int j = 0; j < S::NOUT / 8; ++j)
@@ -321,10 +435,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(MlpArgs a) {
             stage_rows<S::NOUT, PREC>(dz, dZs, srow, lane);
             __syncthreads();
             accumulate_dw<S::K0, S::NOUT, PREC, MB0>(dZs, acts0, acc0, db0, warp, lane, tid);
-            if (a.dx) {
+            if (a.want_dx) {
                 float da[S::K0 / 8][4];
                 layer_backward_input<S::K0, S::NOUT, PREC>(dz, w.w0, da, lane);
-                store_rows<S::K0 / 8>(a.dx, a.P, a.in_dim, row0, lane, da);
+                store_dx_seg<S::K0 / 8>(a, row0, lane, da);
             }
             __syncthreads();
         } else {
@@ -352,10 +466,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(MlpArgs a) {
             stage_rows<S::H, PREC>(dzh, dZs, srow, lane);
             __syncthreads();
             accumulate_dw<S::K0, S::H, PREC, MB0>(dZs, acts0, acc0, db0, warp, lane, tid);
-            if (a.dx) {
+            if (a.want_dx) {
                 float da[S::K0 / 8][4];
                 layer_backward_input<S::K0, S::H, PREC>(dzh, w.w0, da, lane);
-                store_rows<S::K0 / 8>(a.dx, a.P, a.in_dim, row0, lane, da);
+                store_dx_seg<S::K0 / 8>(a, row0, lane, da);
             }
             __syncthreads();
         }

@@ -33,6 +33,24 @@ __global__ void __launch_bounds__(256) sample_positions_kernel(const float* __re
     pos[3 * i + 2] = out[2];
 }
 
+// frustum mid-point + aabb normalisation + contraction + selector in one pass (no world-space positions in HBM)
+__global__ void __launch_bounds__(256) ray_points_kernel(const float* __restrict__ o, const float* __restrict__ d,
+                                                         const float* __restrict__ bins, int64_t N, int S, Aabb box,
+                                                         int contract, float* __restrict__ x01,
+                                                         uint8_t* __restrict__ sel) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * S) return;
+    const int64_t n = i / S;
+    const int s = (int)(i - n * S);
+    float v[3];
+    frustum_midpoint(o + 3 * n, d + 3 * n, __ldg(bins + n * (S + 1) + s), __ldg(bins + n * (S + 1) + s + 1), v);
+    const bool inside = normalize_point(v, box, contract != 0);
+    x01[3 * i] = v[0];
+    x01[3 * i + 1] = v[1];
+    x01[3 * i + 2] = v[2];
+    sel[i] = inside ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(256) sh4_kernel(const float* __restrict__ dirs, int64_t P, int mapped,
                                                   float* __restrict__ out) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -116,6 +134,20 @@ extern "C" int ps_sample_positions(const float* origins, const float* dirs, cons
     sample_positions_kernel<<<(unsigned)cdiv(N * S, 256), 256, 0, (cudaStream_t)stream>>>(origins, dirs, eu_bins, N, S,
                                                                                           pos);
     return check_launch("sample_positions");
+}
+
+extern "C" int ps_ray_points(const float* origins, const float* dirs, const float* eu_bins, int64_t N, int S,
+                             const float* aabb_host, int contract, float* x01, uint8_t* selector, void* stream) {
+    if (N == 0 || S == 0) return 0;
+    PS_REQUIRE(origins && dirs && eu_bins && aabb_host && x01 && selector, "ray_points: null pointer");
+    Aabb box;
+    for (int k = 0; k < 3; ++k) {
+        box.lo[k] = aabb_host[k];
+        box.hi[k] = aabb_host[3 + k];
+    }
+    ray_points_kernel<<<(unsigned)cdiv(N * S, 256), 256, 0, (cudaStream_t)stream>>>(origins, dirs, eu_bins, N, S, box,
+                                                                                    contract, x01, selector);
+    return check_launch("ray_points");
 }
 
 extern "C" int ps_sh4(const float* dirs, int64_t P, int mapped, float* out, void* stream) {

@@ -117,6 +117,27 @@ class iNGPField(Field):
         field_outputs[FieldHeadNames.DENSITY] = density
         return field_outputs
 
+    def fused_level(self, origins: Tensor, directions: Tensor, eu_bins: Tensor, appearance: Optional[Tensor],
+                    threshold: float = 0.5):
+        """Fast path of forward() + compositing for contiguous bins (see presight_b200/fused.py).
+        appearance: per-ray [N, A] or None.  Returns (weights [N,S,1], rgb, acc, depth_expected_unclipped,
+        depth_threshold, semantics, tminmax)."""
+        from .. import fused
+        enc = self.mlp_base_grid
+
+        def meta(mlp):
+            ls = list(mlp.layers)
+            return (fused.MlpMeta((ls[0].weight.shape[1],) + tuple(l.weight.shape[0] for l in ls), mlp._out_act),
+                    ([l.weight for l in ls], [l.bias for l in ls]))
+        base_m, base_p = meta(self.mlp_base_mlp)
+        rgb_m, rgb_p = meta(self.rgb_head)
+        sem_m, sem_p = meta(self.semantic_head) if self.use_semantics else (None, None)
+        return fused.field_level(
+            origins, directions, eu_bins, appearance, enc.hash_table, self.aabb_host(),
+            self.spatial_distortion is not None,
+            fused.GridMeta(enc._scalings_host, enc.log2_hashmap_size, enc.features_per_level), base_m, sem_m, rgb_m,
+            self.geo_feat_dim, self.mlp_base_mlp.precision, threshold, base_p, sem_p, rgb_p)
+
     def semantic_fn(self, positions: Tensor) -> Tensor:
         """ingp_field.py:253-267."""
         assert self.use_semantics, "Cannot query semantics when `self.use_semantics` is set to False"

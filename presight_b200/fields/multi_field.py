@@ -72,6 +72,14 @@ class iNGPFieldMS(nn.Module):
         res = _dispatch(positions, self.centroids, len(self.fields), run, (directions, app))
         return {k: v.reshape(*output_shape, -1) for k, v in res.items()}
 
+    def supports_fused(self) -> bool:
+        return len(self.fields) == 1
+
+    def fused_level(self, origins: Tensor, directions: Tensor, eu_bins: Tensor, appearance: Optional[Tensor],
+                    threshold: float = 0.5):
+        """Single-sub-field fast path: see iNGPField.fused_level."""
+        return self.fields[0].fused_level(origins, directions, eu_bins, appearance, threshold)
+
     def density_fn(self, positions: Tensor) -> Tuple[Tensor, Tensor]:
         """ingp_field_ms.py:128-153."""
         output_shape = positions.shape[:-1]
@@ -102,6 +110,13 @@ class PropNetDensityFieldMS(nn.Module):
 
     def get_density(self, ray_samples: RaySamples) -> Tuple[Tensor, None]:
         return self.density_fn(ray_samples.frustums.get_positions()), None
+
+    def supports_fused(self) -> bool:
+        return len(self.fields) == 1
+
+    def level_weights(self, origins: Tensor, directions: Tensor, eu_bins: Tensor) -> Tensor:
+        """Single-sub-field fast path (no routing needed): see PropNetDensityField.level_weights."""
+        return self.fields[0].level_weights(origins, directions, eu_bins)
 
     def density_fn(self, positions: Tensor) -> Tensor:
         """prop_density_field_ms.py:86-105."""

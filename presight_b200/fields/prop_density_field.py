@@ -66,3 +66,18 @@ class PropNetDensityField(Field):
 
     def get_outputs(self, ray_samples: RaySamples, density_embedding: Optional[Tensor] = None) -> dict:
         return {}
+
+    def level_weights(self, origins: Tensor, directions: Tensor, eu_bins: Tensor) -> Tensor:
+        """Fast path of `get_weights(density_fn(positions))` for contiguous bins: one autograd node, a fixed chain
+        of kernels (ray_points -> hash -> MLP with density epilogue -> weights), no intermediate torch ops."""
+        from .. import fused
+        enc = self.encoding
+        if self.use_linear:
+            layers = [self.linear]
+        else:
+            layers = list(self.mlp_base[1].layers)
+        dims = (layers[0].weight.shape[1],) + tuple(l.weight.shape[0] for l in layers)
+        return fused.prop_level_weights(
+            origins, directions, eu_bins, enc.hash_table, self.aabb_host(), self.spatial_distortion is not None,
+            fused.GridMeta(enc._scalings_host, enc.log2_hashmap_size, enc.features_per_level),
+            fused.MlpMeta(dims, ops.ACT_NONE), self._precision, [l.weight for l in layers], [l.bias for l in layers])

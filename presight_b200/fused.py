@@ -1,0 +1,261 @@
+"""Level-fused fast paths: one autograd node per sampling level, a fixed chain of libpresight_b200 kernels inside.
+
+The drop-in modules (`HashEncoding`, `MLP`, `get_weights`, renderers) compose through torch autograd like the
+reference does; these two Functions are what the model driver uses when a level is served by a single sub-field:
+
+  proposal level (ray_samplers.py:600-609):   ray_points -> hash_fwd -> mlp(+density epilogue) -> weights
+  field level (nerfacto_nusc_ms.py:497-530):  ray_points -> hash_fwd -> base mlp(+density) -> semantic head ->
+                                              sh4 -> colour head -> one-pass compositing
+
+No torch.cat / split / expand copies: the heads read column windows of the base MLP's output `h` and per-ray vectors
+(SH of the view direction, appearance embedding) through segmented row descriptors, and their input gradients are
+written straight into the matching windows of one `dh` buffer (the appearance gradient is reduced per ray in-kernel).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import ops
+from ._lib import call, host_floats, host_ints, host_ptrs, host_segments, ptr, stream
+
+_f32c = ops._f32c
+
+
+@dataclass(frozen=True)
+class GridMeta:
+    scalings: Tuple[float, ...]
+    log2_T: int
+    F: int
+
+    @property
+    def L(self) -> int:
+        return len(self.scalings)
+
+
+@dataclass(frozen=True)
+class MlpMeta:
+    dims: Tuple[int, ...]
+    out_act: int
+
+    @property
+    def n_layers(self) -> int:
+        return len(self.dims) - 1
+
+
+def _mlp_fwd(segs, P, ws, bs, meta: MlpMeta, prec, y, sel=None, density_out=None, name="mlp"):
+    with ops._probe(f"mlp_fwd_{name}"):
+        call("ps_mlp_fwd_ex", host_segments(segs), len(segs), P, host_ptrs(ws), host_ptrs(bs), host_ints(meta.dims),
+             meta.n_layers, meta.out_act, prec, ptr(y), ptr(sel), ptr(density_out), stream())
+
+
+def _mlp_bwd(segs, dy, P, ws, bs, meta: MlpMeta, prec, dW, db, sel=None, d_density=None, name="mlp"):
+    with ops._probe(f"mlp_bwd_{name}"):
+        call("ps_mlp_bwd_ex", host_segments(segs), len(segs), ptr(dy), P, host_ptrs(ws), host_ptrs(bs),
+             host_ints(meta.dims), meta.n_layers, meta.out_act, prec, host_ptrs(dW), host_ptrs(db), ptr(sel),
+             ptr(d_density), stream())
+
+
+def _ray_points(origins, dirs, eu, aabb, contract):
+    N, S = eu.shape[0], eu.shape[1] - 1
+    x01 = torch.empty(N * S, 3, device=eu.device, dtype=torch.float32)
+    sel = torch.empty(N * S, device=eu.device, dtype=torch.uint8)
+    call("ps_ray_points", ptr(origins), ptr(dirs), ptr(eu), N, S, host_floats(aabb), 1 if contract else 0, ptr(x01),
+         ptr(sel), stream())
+    return x01, sel
+
+
+def _hash_fwd(x01, table, g: GridMeta):
+    P = x01.shape[0]
+    out = torch.empty(P, g.L * g.F, device=x01.device, dtype=torch.float32)
+    with ops._probe(f"hash_fwd_L{g.L}F{g.F}T{g.log2_T}"):
+        call("ps_hash_fwd", ptr(x01), P, ptr(table), host_floats(g.scalings), g.L, g.F, g.log2_T, ptr(out), stream())
+    return out
+
+
+def _hash_bwd(x01, dfeat, table, g: GridMeta):
+    dtable = torch.zeros_like(table)
+    with ops._probe(f"hash_bwd_L{g.L}F{g.F}T{g.log2_T}"):
+        call("ps_hash_bwd", ptr(x01), x01.shape[0], None, host_floats(g.scalings), g.L, g.F, g.log2_T, ptr(dfeat),
+             ptr(dtable), None, stream())
+    return dtable
+
+
+def _split_params(params: Sequence[Tensor], counts: Sequence[int]):
+    """params = [W..., b...] per network, concatenated; counts = layers per network."""
+    nets, i = [], 0
+    for n in counts:
+        ws = [p.detach() for p in params[i:i + n]]
+        bs = [p.detach() for p in params[i + n:i + 2 * n]]
+        nets.append((ws, bs))
+        i += 2 * n
+    return nets
+
+
+class _PropLevel(torch.autograd.Function):
+    """weights of one proposal level from bin edges (prop_density_field.py:129-153 + rays.py:128-150)."""
+
+    @staticmethod
+    def forward(ctx, origins, dirs, eu_bins, table, aabb, contract, grid: GridMeta, net: MlpMeta, prec, *params):
+        o, d, eu = _f32c(origins.detach()), _f32c(dirs.detach()), _f32c(eu_bins.detach())
+        N, S = eu.shape[0], eu.shape[1] - 1
+        P = N * S
+        (ws, bs), = _split_params(params, [net.n_layers])
+        x01, sel = _ray_points(o, d, eu, aabb, contract)
+        feat = _hash_fwd(x01, table.detach(), grid)
+        density = torch.empty(P, device=eu.device, dtype=torch.float32)
+        _mlp_fwd([(feat, None, feat.shape[1], 0, feat.shape[1], 1)], P, ws, bs, net, prec, None, sel, density, "prop")
+        w = torch.empty(N, S, device=eu.device, dtype=torch.float32)
+        call("ps_composite_fwd", ptr(eu), ptr(density), None, None, N, S, 0, 0.5, ptr(w), None, None, None, None, None,
+             None, stream())
+        ctx.save_for_backward(eu, x01, sel, feat, density, table, *params)
+        ctx.meta = (grid, net, prec, N, S)
+        return w.view(N, S, 1)
+
+    @staticmethod
+    def backward(ctx, dw):
+        grid, net, prec, N, S = ctx.meta
+        eu, x01, sel, feat, density, table, *params = ctx.saved_tensors
+        P = N * S
+        (ws, bs), = _split_params(params, [net.n_layers])
+        d_density = torch.empty(P, device=eu.device, dtype=torch.float32)
+        call("ps_composite_bwd", ptr(eu), ptr(density), None, None, None, None, None, N, S, 0,
+             ptr(_f32c(dw).view(N, S)), None, None, None, None, ptr(d_density), None, None, stream())
+        dfeat = torch.empty_like(feat)
+        dW = [torch.zeros_like(w) for w in ws]
+        db = [torch.zeros_like(b) for b in bs]
+        _mlp_bwd([(feat, dfeat, feat.shape[1], 0, feat.shape[1], 1)], None, P, ws, bs, net, prec, dW, db, sel,
+                 d_density, "prop")
+        dtable = _hash_bwd(x01, dfeat, table, grid)
+        return (None, None, None, dtable, None, None, None, None, None, *dW, *db)
+
+
+def prop_level_weights(origins, dirs, eu_bins, table, aabb, contract, grid: GridMeta, net: MlpMeta, prec,
+                       weights: Sequence[Tensor], biases: Sequence[Tensor]) -> Tensor:
+    return _PropLevel.apply(origins, dirs, eu_bins, table, aabb, contract, grid, net, prec, *weights, *biases)
+
+
+class _FieldLevel(torch.autograd.Function):
+    """Final level: field evaluation + one-pass compositing (ingp_field.py:163-251, nerfacto_nusc_ms.py:497-530)."""
+
+    @staticmethod
+    def forward(ctx, origins, dirs, eu_bins, app, table, aabb, contract, grid: GridMeta, base: MlpMeta,
+                sem: Optional[MlpMeta], rgb: MlpMeta, geo_dim: int, prec, threshold, *params):
+        o, d, eu = _f32c(origins.detach()), _f32c(dirs.detach()), _f32c(eu_bins.detach())
+        N, S = eu.shape[0], eu.shape[1] - 1
+        P = N * S
+        dev = eu.device
+        counts = [base.n_layers] + ([sem.n_layers] if sem is not None else []) + [rgb.n_layers]
+        nets = _split_params(params, counts)
+        (bw, bb) = nets[0]
+        (rw, rb) = nets[-1]
+        A = 0 if app is None else app.shape[1]
+        app_c = None if app is None else _f32c(app.detach())
+        hd = base.dims[-1]
+        sem_dim = 0 if sem is None else sem.dims[0]
+
+        x01, sel = _ray_points(o, d, eu, aabb, contract)
+        feat = _hash_fwd(x01, table.detach(), grid)
+        h = torch.empty(P, hd, device=dev, dtype=torch.float32)
+        density = torch.empty(P, device=dev, dtype=torch.float32)
+        _mlp_fwd([(feat, None, feat.shape[1], 0, feat.shape[1], 1)], P, bw, bb, base, prec, h, sel, density, "base")
+        sem_s = None
+        if sem is not None:
+            sw, sb = nets[1]
+            sem_s = torch.empty(P, sem.dims[-1], device=dev, dtype=torch.float32)
+            _mlp_fwd([(h, None, hd, 1 + geo_dim, sem_dim, 1)], P, sw, sb, sem, prec, sem_s, name="sem")
+        sh = ops.sh4(d)                                                   # [N,16], per ray
+        segs = [(sh, None, 16, 0, 16, S), (h, None, hd, 1, geo_dim, 1)]
+        if app_c is not None:
+            segs.append((app_c, None, A, 0, A, S))
+        rgb_s = torch.empty(P, 3, device=dev, dtype=torch.float32)
+        _mlp_fwd(segs, P, rw, rb, rgb, prec, rgb_s, name="rgb")
+
+        C = 0 if sem_s is None else sem_s.shape[1]
+        w = torch.empty(N, S, device=dev, dtype=torch.float32)
+        rgb_out = torch.empty(N, 3, device=dev, dtype=torch.float32)
+        acc = torch.empty(N, 1, device=dev, dtype=torch.float32)
+        dexp = torch.empty(N, 1, device=dev, dtype=torch.float32)
+        dthr = torch.empty(N, 1, device=dev, dtype=torch.float32)
+        sem_out = torch.empty(N, C, device=dev, dtype=torch.float32) if C else torch.empty(0, device=dev)
+        tmm = torch.tensor([float("inf"), float("-inf")], device=dev, dtype=torch.float32)
+        with ops._probe("composite_fwd"):
+            call("ps_composite_fwd", ptr(eu), ptr(density), ptr(rgb_s), ptr(sem_s), N, S, C, float(threshold), ptr(w),
+                 ptr(rgb_out), ptr(acc), ptr(dexp), ptr(dthr), ptr(sem_out) if C else None, ptr(tmm), stream())
+        saved = [eu, x01, sel, feat, h, density, rgb_s, sh, acc, dexp, table]
+        if sem_s is not None:
+            saved.append(sem_s)
+        if app_c is not None:
+            saved.append(app_c)
+        ctx.save_for_backward(*saved, *params)
+        ctx.meta = (grid, base, sem, rgb, geo_dim, prec, N, S, A, len(saved), app is not None and app.requires_grad)
+        ctx.mark_non_differentiable(dthr, tmm)
+        return w.view(N, S, 1), rgb_out, acc, dexp, dthr, sem_out, tmm
+
+    @staticmethod
+    def backward(ctx, dw, drgb, dacc, ddexp, _dthr, dsem, _dtmm):
+        grid, base, sem, rgb, geo_dim, prec, N, S, A, n_saved, app_grad = ctx.meta
+        saved = list(ctx.saved_tensors)
+        params = saved[n_saved:]
+        eu, x01, sel, feat, h, density, rgb_s, sh, acc, dexp, table = saved[:11]
+        rest = saved[11:n_saved]
+        sem_s = rest.pop(0) if sem is not None else None
+        app_c = rest.pop(0) if A else None
+        P = N * S
+        dev = eu.device
+        counts = [base.n_layers] + ([sem.n_layers] if sem is not None else []) + [rgb.n_layers]
+        nets = _split_params(params, counts)
+        (bw, bb) = nets[0]
+        (rw, rb) = nets[-1]
+        hd = base.dims[-1]
+        C = 0 if sem_s is None else sem_s.shape[1]
+
+        d_density = torch.empty(P, device=dev, dtype=torch.float32)
+        d_rgb_s = torch.empty(P, 3, device=dev, dtype=torch.float32)
+        d_sem_s = torch.empty(P, C, device=dev, dtype=torch.float32) if C else None
+        with ops._probe("composite_bwd"):
+            call("ps_composite_bwd", ptr(eu), ptr(density), ptr(rgb_s), ptr(sem_s), None, ptr(acc), ptr(dexp), N, S, C,
+                 ptr(_f32c(dw).view(N, S)), ptr(_f32c(drgb)), ptr(_f32c(dacc)), ptr(_f32c(ddexp)),
+                 ptr(_f32c(dsem)) if C else None, ptr(d_density), ptr(d_rgb_s), ptr(d_sem_s), stream())
+        # dh: column 0 is driven by d_density inside the base backward; [1, 1+geo) by the colour head;
+        # [1+geo, ...) by the semantic head (zero when there is none)
+        dh = torch.empty(P, hd, device=dev, dtype=torch.float32) if sem is not None \
+            else torch.zeros(P, hd, device=dev, dtype=torch.float32)
+        dapp = torch.zeros(N, A, device=dev, dtype=torch.float32) if (A and app_grad) else None
+        segs = [(sh, None, 16, 0, 16, S), (h, dh, hd, 1, geo_dim, 1)]
+        if app_c is not None:
+            segs.append((app_c, dapp, A, 0, A, S))
+        dWr = [torch.zeros_like(w) for w in rw]
+        dbr = [torch.zeros_like(b) for b in rb]
+        _mlp_bwd(segs, d_rgb_s, P, rw, rb, rgb, prec, dWr, dbr, name="rgb")
+        grads_sem: List[Tensor] = []
+        if sem is not None:
+            sw, sb = nets[1]
+            dWs = [torch.zeros_like(w) for w in sw]
+            dbs = [torch.zeros_like(b) for b in sb]
+            _mlp_bwd([(h, dh, hd, 1 + geo_dim, sem.dims[0], 1)], d_sem_s, P, sw, sb, sem, prec, dWs, dbs, name="sem")
+            grads_sem = [*dWs, *dbs]
+        dfeat = torch.empty_like(feat)
+        dWb = [torch.zeros_like(w) for w in bw]
+        dbb = [torch.zeros_like(b) for b in bb]
+        _mlp_bwd([(feat, dfeat, feat.shape[1], 0, feat.shape[1], 1)], dh, P, bw, bb, base, prec, dWb, dbb, sel,
+                 d_density, "base")
+        dtable = _hash_bwd(x01, dfeat, table, grid)
+        return (None, None, None, dapp, dtable, None, None, None, None, None, None, None, None, None,
+                *dWb, *dbb, *grads_sem, *dWr, *dbr)
+
+
+def field_level(origins, dirs, eu_bins, app, table, aabb, contract, grid: GridMeta, base: MlpMeta,
+                sem: Optional[MlpMeta], rgb: MlpMeta, geo_dim: int, prec, threshold, base_params, sem_params,
+                rgb_params):
+    """-> (weights [N,S,1], rgb [N,3], acc [N,1], depth_expected_unclipped [N,1], depth_threshold [N,1],
+    semantics [N,C], tminmax [2]).  *_params = (weights list, biases list)."""
+    flat = [*base_params[0], *base_params[1]]
+    if sem is not None:
+        flat += [*sem_params[0], *sem_params[1]]
+    flat += [*rgb_params[0], *rgb_params[1]]
+    return _FieldLevel.apply(origins, dirs, eu_bins, app, table, aabb, contract, grid, base, sem, rgb, geo_dim, prec,
+                             threshold, *flat)

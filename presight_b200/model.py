@@ -103,6 +103,7 @@ class NerfactoNuscMSModel(nn.Module):
                  num_train_videos: int = 1) -> None:
         super().__init__()
         self.config = config
+        self.use_fused = True      # level-fused fast paths for single-sub-field models (presight_b200/fused.py)
         self.centroids = centroids
         self.aabbs = aabbs
         c = config
@@ -215,13 +216,18 @@ class NerfactoNuscMSModel(nn.Module):
                                                                             jitters=jitters)
         N, S = ray_samples.shape
         app = self._appearance(ray_samples) if appearance is None else appearance[:, None, :].expand(N, S, -1)
-        fo = self.field.forward(ray_samples, appearance_embedding=app)
         eu = ray_samples.frustums.eu_bins
-        sem = fo.get(FieldHeadNames.SEMANTICS)
-        # one-pass compositing kernel: weights + rgb + accumulation + both depths + semantics (:503-511, :530)
-        w, rgb, acc_raw, dexp_raw, depth, sem_out, tmm = ops.composite(
-            eu, fo[FieldHeadNames.DENSITY].reshape(N, S), fo[FieldHeadNames.RGB], sem, 0.5)
-        weights = w.view(N, S, 1)
+        if self.use_fused and self.field.supports_fused():
+            # level-fused fast path (presight_b200/fused.py): field + compositing as one autograd node
+            weights, rgb, acc_raw, dexp_raw, depth, sem_out, tmm = self.field.fused_level(
+                ray_bundle.origins, ray_bundle.directions, eu, None if app is None else app[:, 0, :], 0.5)
+        else:
+            fo = self.field.forward(ray_samples, appearance_embedding=app)
+            sem = fo.get(FieldHeadNames.SEMANTICS)
+            # one-pass compositing kernel: weights + rgb + accumulation + both depths + semantics (:503-511, :530)
+            w, rgb, acc_raw, dexp_raw, depth, sem_out, tmm = ops.composite(
+                eu, fo[FieldHeadNames.DENSITY].reshape(N, S), fo[FieldHeadNames.RGB], sem, 0.5)
+            weights = w.view(N, S, 1)
         weights_list.append(weights)
         ray_samples_list.append(ray_samples)
         expected_depth = torch.clip(dexp_raw, tmm[0], tmm[1])            # renderers.py:379 (batch-global clip)

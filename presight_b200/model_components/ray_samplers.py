@@ -141,6 +141,7 @@ class ProposalNetworkSampler(Sampler):
             raise NotImplementedError("pass the piecewise SpacedSampler as initial_sampler (PreSight's configuration)")
         self.initial_sampler = initial_sampler
         self.pdf_sampler = PDFSampler(include_original=False, single_jitter=single_jitter)
+        self.use_fused = True      # take the level-fused fast path when a density fn's owner offers it
         self._anneal = 1.0
         self._steps_since_update = 0
         self._step = 0
@@ -173,12 +174,20 @@ class ProposalNetworkSampler(Sampler):
                 ray_samples = self.pdf_sampler(ray_bundle, ray_samples, weights, num_samples=num_samples,
                                                eps=torch.finfo(torch.float32).eps, rand=jit, anneal=self._anneal)
             if is_prop:
-                if updated:
-                    density = density_fns[i_level](ray_samples.frustums.get_positions())
+                owner = getattr(density_fns[i_level], "__self__", None)
+                fused_ok = self.use_fused and owner is not None and getattr(owner, "supports_fused", lambda: False)()
+                if fused_ok:
+                    # level-fused fast path: same maths, one autograd node (presight_b200/fused.py)
+                    with torch.set_grad_enabled(updated and torch.is_grad_enabled()):
+                        weights = owner.level_weights(ray_bundle.origins, ray_bundle.directions,
+                                                      ray_samples.frustums.eu_bins)
                 else:
-                    with torch.no_grad():
+                    if updated:
                         density = density_fns[i_level](ray_samples.frustums.get_positions())
-                weights = ray_samples.get_weights(density)
+                    else:
+                        with torch.no_grad():
+                            density = density_fns[i_level](ray_samples.frustums.get_positions())
+                    weights = ray_samples.get_weights(density)
                 weights_list.append(weights)
                 ray_samples_list.append(ray_samples)
         if updated:

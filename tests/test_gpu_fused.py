@@ -1,0 +1,201 @@
+"""The level-fused fast paths (presight_b200/fused.py) against the modular drop-in path and the CPU oracle."""
+import copy
+
+import pytest
+import torch
+
+import oracle as O
+from oracle import state as OS
+from helpers import FAR, NEAR, THR, Fixture, assert_close, field_meta, prop_meta
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def build_single_field_model(impl, samples=(48, 32, 32)):
+    """nf = 1 model with the golden fixture's network sizes (base 12->64->80, sem 64x3, rgb 47->64->64->3)."""
+    from presight_b200.model import NerfactoNuscMSModel, NerfactoNuscMSModelConfig
+    ffx = Fixture("fields.npz")
+    m = field_meta(ffx)
+    p0, p1 = prop_meta(ffx, "meta/prop0"), prop_meta(ffx, "meta/prop1")
+
+    def pargs(p):
+        return {"features_per_level": p["features_per_level"], "log2_hashmap_size": p["log2_hashmap_size"],
+                "num_levels": p["num_levels"], "base_res": p["base_res"], "max_res": p["max_res"],
+                "hidden_dim": p["hidden_dim"], "use_linear": False}
+    cfg = NerfactoNuscMSModelConfig(
+        near_plane=NEAR, far_plane=FAR, piecewise_sampler_threshold=THR, num_levels=m["num_levels"],
+        base_res=m["base_res"], max_res=m["max_res"], log2_hashmap_size=m["log2_hashmap_size"],
+        features_per_level=m["features_per_level"], num_proposal_samples_per_ray=samples[:2],
+        num_nerf_samples_per_ray=samples[2], proposal_net_args_list=[pargs(p0), pargs(p1)], implementation=impl,
+        appearance_embed_dim=4, video_embed_dim=12, sky_mlp_dims=32, semantic_dim=m["semantic_dim"])
+    torch.manual_seed(5)
+    aabb = torch.tensor([[[-1.0, -1.0, -0.25], [1.0, 1.0, 0.75]]])
+    model = NerfactoNuscMSModel(cfg, torch.zeros(1, 3), aabb, num_train_cameras=7, num_train_videos=3)
+    with torch.no_grad():
+        for f in model.field.fields:
+            f.mlp_base_grid.hash_table.mul_(300.0)
+        for p in model.proposal_networks:
+            for f in p.fields:
+                f.encoding.hash_table.mul_(300.0)
+    return model.to(DEV), cfg
+
+
+def make_batch(n, seed=0):
+    from presight_b200.cameras.rays import RayBundle
+    from presight_b200.model import VIDEO_ID
+    g = torch.Generator().manual_seed(seed)
+    o = (torch.rand(n, 3, generator=g) - 0.5) * torch.tensor([2.0, 2.0, 0.1])
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g) * torch.tensor([1.0, 1.0, 0.3]), dim=-1)
+    cam = torch.randint(0, 7, (n, 1), generator=g)
+    vid = torch.randint(0, 3, (n, 1), generator=g)
+    jit = [torch.rand(n, 1, generator=g) for _ in range(3)]
+    tgt = {"rgb": torch.rand(n, 3, generator=g), "sem": torch.rand(n, 64, generator=g),
+           "gw0": torch.randn(n, 48, 1, generator=g) * 0.1, "gw1": torch.randn(n, 32, 1, generator=g) * 0.1}
+
+    def bundle():
+        return RayBundle(origins=o.to(DEV), directions=d.to(DEV), camera_indices=cam.to(DEV),
+                         metadata={VIDEO_ID: vid.to(DEV)})
+    return bundle, [j.to(DEV) for j in jit], {k: v.to(DEV) for k, v in tgt.items()}, (o, d, cam, vid, jit)
+
+
+def loss_of(out, tgt, n):
+    wl = out["weights_list"]
+    return ((out["rgb"] - tgt["rgb"]) ** 2).mean() + 0.5 * ((out["semantics"] - tgt["sem"]) ** 2).mean() \
+        + 0.1 * out["expected_depth"].mean() + 0.01 * out["accumulation"].mean() \
+        + (wl[0] * tgt["gw0"]).sum() / n + (wl[1] * tgt["gw1"]).sum() / n
+
+
+@pytest.mark.parametrize("impl", ["b200+fp32", "b200"])
+def test_fused_matches_modular(impl):
+    n = 300
+    fused_model, _ = build_single_field_model(impl)
+    modular = copy.deepcopy(fused_model)
+    modular.use_fused = False
+    modular.proposal_sampler.use_fused = False
+    bundle, jit, tgt, _ = make_batch(n)
+    for m in (fused_model, modular):
+        m.train()
+    out_f = fused_model(bundle(), jitters=jit)
+    out_m = modular(bundle(), jitters=jit)
+    tol = 1e-5 if impl == "b200+fp32" else 1e-4          # same kernels, same inputs: differences are only fp32 order
+    for k in ("rgb", "accumulation", "expected_depth", "semantics", "depth"):
+        assert_close(out_f[k], out_m[k], tol, k)
+    for i in range(3):
+        assert_close(out_f["weights_list"][i], out_m["weights_list"][i], tol, f"weights {i}")
+    loss_of(out_f, tgt, n).backward()
+    loss_of(out_m, tgt, n).backward()
+    pf, pm = dict(fused_model.named_parameters()), dict(modular.named_parameters())
+    checked = 0
+    for k, p in pm.items():
+        if p.grad is None:
+            assert pf[k].grad is None or float(pf[k].grad.abs().max()) == 0.0, k
+            continue
+        assert pf[k].grad is not None, f"fused path produced no gradient for {k}"
+        assert rel_l2(pf[k].grad, p.grad) < (1e-4 if impl == "b200+fp32" else 2e-2), \
+            f"{k}: {rel_l2(pf[k].grad, p.grad):.2e}"
+        checked += 1
+    assert checked >= 25
+
+
+def test_fused_matches_oracle_fp32():
+    n = 200
+    model, cfg = build_single_field_model("b200+fp32")
+    model.train()
+    bundle, jit, tgt, (o, d, cam, vid, jit_cpu) = make_batch(n, seed=3)
+    out = model(bundle(), jitters=jit)
+    # oracle with the same weights
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ffx = Fixture("fields.npz")
+    fm = field_meta(ffx)
+    field = OS.ngp_from_state(sd, "field.fields.0.", fm, True)
+    props = [[OS.prop_from_state(sd, f"proposal_networks.{i}.fields.0.", prop_meta(ffx, f"meta/prop{i}"), True)]
+             for i in range(2)]
+    sky = [OS.sky_from_state(sd, "sky_model.fields.0.", True, True)]
+    ocfg = O.ModelCfg(num_proposal_samples=(48, 32), num_nerf_samples=32, near=NEAR, far=FAR, piecewise_thr=THR)
+    om = O.Model(ocfg, torch.zeros(1, 3), [field], props, sky)
+    app = torch.cat([sd["appearance_embedding.embedding.weight"][cam[:, 0]],
+                     sd["video_embedding.embedding.weight"][vid[:, 0]]], dim=-1)
+    oo = O.model_outputs(om, o, d, app, jit_cpu)
+    for k in ("rgb", "accumulation", "expected_depth", "semantics"):
+        assert_close(out[k].detach().cpu(), oo[k], 1e-3, k)
+    for i in range(3):
+        assert_close(out["weights_list"][i].detach().cpu(), oo["weights_list"][i], 1e-3, f"weights {i}")
+    tgt_c = {k: v.cpu() for k, v in tgt.items()}
+    loss_of(out, tgt, n).backward()
+    loss_of(oo, tgt_c, n).backward()
+    g = dict(model.named_parameters())
+    assert rel_l2(g["field.fields.0.mlp_base_grid.hash_table"].grad.cpu(), field.grid.table.grad) < 5e-3
+    assert rel_l2(g["field.fields.0.rgb_head.layers.0.weight"].grad.cpu(), field.rgb.weights[0].grad) < 5e-3
+    assert rel_l2(g["field.fields.0.semantic_head.layers.2.weight"].grad.cpu(), field.sem.weights[2].grad) < 5e-3
+    assert rel_l2(g["field.fields.0.mlp_base_mlp.layers.0.weight"].grad.cpu(), field.base.weights[0].grad) < 5e-3
+    assert rel_l2(g["proposal_networks.0.fields.0.encoding.hash_table"].grad.cpu(), props[0][0].grid.table.grad) < 5e-3
+    assert rel_l2(g["proposal_networks.1.fields.0.mlp_base.1.layers.0.weight"].grad.cpu(),
+                  props[1][0].net.weights[0].grad) < 5e-3
+
+
+def test_mlp_segments_and_density_epilogue():
+    """ps_mlp_*_ex: [per-ray | strided window | per-ray] inputs equal torch.cat of the pieces; the per-ray input
+    gradient equals the sum over the ray's samples; the density epilogue equals trunc_exp * selector."""
+    from presight_b200 import fused, ops
+    g = torch.Generator().manual_seed(12)
+    N, S, hd = 37, 32, 80
+    P = N * S
+    sh = torch.randn(N, 16, generator=g)
+    h = torch.randn(P, hd, generator=g)
+    app = torch.randn(N, 16, generator=g)
+    ws = [torch.randn(64, 47, generator=g) / 7, torch.randn(64, 64, generator=g) / 8, torch.randn(3, 64, generator=g) / 8]
+    bs = [torch.randn(64, generator=g) * 0.1, torch.randn(64, generator=g) * 0.1, torch.randn(3, generator=g) * 0.1]
+    dy = torch.randn(P, 3, generator=g)
+    # oracle: explicit concatenation
+    shc, hc, appc = sh.clone().requires_grad_(True), h.clone().requires_grad_(True), app.clone().requires_grad_(True)
+    x = torch.cat([shc[:, None, :].expand(N, S, 16).reshape(P, 16), hc[:, 1:16],
+                   appc[:, None, :].expand(N, S, 16).reshape(P, 16)], dim=-1)
+    wc = [w.clone().requires_grad_(True) for w in ws]
+    yc = O.mlp_forward(x, O.Mlp(wc, [b.clone() for b in bs], "sigmoid"))
+    yc.backward(dy)
+    # kernel
+    meta = fused.MlpMeta((47, 64, 64, 3), ops.ACT_SIGMOID)
+    shg, hg, appg = sh.to(DEV), h.to(DEV), app.to(DEV)
+    wg, bg = [w.to(DEV) for w in ws], [b.to(DEV) for b in bs]
+    y = torch.empty(P, 3, device=DEV)
+    segs = [(shg, None, 16, 0, 16, S), (hg, None, hd, 1, 15, 1), (appg, None, 16, 0, 16, S)]
+    fused._mlp_fwd(segs, P, wg, bg, meta, 0, y)
+    assert_close(y.cpu(), yc, 1e-3, "segmented forward")
+    dh = torch.zeros(P, hd, device=DEV)
+    dapp = torch.zeros(N, 16, device=DEV)
+    dW, db = [torch.zeros_like(w) for w in wg], [torch.zeros_like(b) for b in bg]
+    segs_b = [(shg, None, 16, 0, 16, S), (hg, dh, hd, 1, 15, 1), (appg, dapp, 16, 0, 16, S)]
+    fused._mlp_bwd(segs_b, dy.to(DEV), P, wg, bg, meta, 0, dW, db)
+    assert_close(dh.cpu(), hc.grad, 1e-3, "strided-window input gradient")
+    assert_close(dapp.cpu(), appc.grad, 1e-3, "per-ray input gradient")
+    assert_close(dW[0].cpu(), wc[0].grad, 1e-3, "dW0")
+    # density epilogue on an 80-wide base MLP
+    ws2 = [torch.randn(64, 32, generator=g) / 6, torch.randn(80, 64, generator=g) / 8]
+    bs2 = [torch.randn(64, generator=g) * 0.1, torch.randn(80, generator=g) * 0.1]
+    feat = torch.randn(P, 32, generator=g)
+    sel = torch.rand(P, generator=g) > 0.1
+    gd, gh = torch.randn(P, generator=g), torch.randn(P, 80, generator=g)
+    fc = feat.clone().requires_grad_(True)
+    hh = O.mlp_forward(fc, O.Mlp([w.clone() for w in ws2], [b.clone() for b in bs2]))
+    dens = O.trunc_exp(hh[:, 0]) * sel
+    gh0 = gh.clone()
+    gh0[:, 0] = 0
+    ((dens * gd).sum() + (hh * gh0).sum()).backward()
+    meta2 = fused.MlpMeta((32, 64, 80), ops.ACT_NONE)
+    w2, b2 = [w.to(DEV) for w in ws2], [b.to(DEV) for b in bs2]
+    fg, selg = feat.to(DEV), sel.to(DEV).to(torch.uint8)
+    hout, dout = torch.empty(P, 80, device=DEV), torch.empty(P, device=DEV)
+    fused._mlp_fwd([(fg, None, 32, 0, 32, 1)], P, w2, b2, meta2, 0, hout, selg, dout)
+    assert_close(hout.cpu(), hh, 1e-3, "h")
+    assert_close(dout.cpu(), dens, 1e-3, "density epilogue")
+    dfeat = torch.empty(P, 32, device=DEV)
+    dW2, db2 = [torch.zeros_like(w) for w in w2], [torch.zeros_like(b) for b in b2]
+    gh_dev = gh.to(DEV)      # column 0 deliberately NOT zeroed: the kernel must ignore it when d_density is given
+    fused._mlp_bwd([(fg, dfeat, 32, 0, 32, 1)], gh_dev, P, w2, b2, meta2, 0, dW2, db2, selg, gd.to(DEV))
+    assert_close(dfeat.cpu(), fc.grad, 1e-3, "d features through the density epilogue")
