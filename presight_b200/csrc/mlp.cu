@@ -34,7 +34,8 @@ static int run(int K0, int H, int NHID, int NOUT, int prec, bool bwd, const MlpA
     return r;
 }
 
-static int fill_segments(MlpArgs& a, const ps_row_segment* segs, int n_seg, int in_dim, bool bwd) {
+static int fill_segments(MlpArgs& a, const ps_row_segment* segs, int n_seg, int in_dim, bool bwd, int64_t P) {
+    PS_REQUIRE(P >= 0 && P < (1ll << 31), "mlp: number of points %lld out of range", (long long)P);
     PS_REQUIRE(segs != nullptr && n_seg >= 1 && n_seg <= PS_MLP_MAX_SEGMENTS, "mlp: %d input segments (1..%d)", n_seg,
                PS_MLP_MAX_SEGMENTS);
     int col = 0;
@@ -70,7 +71,7 @@ extern "C" int ps_mlp_fwd_ex(const ps_row_segment* segs_host, int n_seg, int64_t
     int K0, H, NHID, NOUT;
     if (int e = resolve(dims_host, n_layers, K0, H, NHID, NOUT)) return e;
     MlpArgs a{};
-    if (int e = fill_segments(a, segs_host, n_seg, dims_host[0], false)) return e;
+    if (int e = fill_segments(a, segs_host, n_seg, dims_host[0], false, P)) return e;
     if (P == 0) return 0;
     PS_REQUIRE((y || density_out) && W_host && b_host, "mlp_fwd: null pointer");
     a.y = y; a.P = P; a.in_dim = dims_host[0]; a.out_dim = dims_host[n_layers]; a.out_act = out_act;
@@ -90,7 +91,7 @@ extern "C" int ps_mlp_bwd_ex(const ps_row_segment* segs_host, int n_seg, const f
     int K0, H, NHID, NOUT;
     if (int e = resolve(dims_host, n_layers, K0, H, NHID, NOUT)) return e;
     MlpArgs a{};
-    if (int e = fill_segments(a, segs_host, n_seg, dims_host[0], true)) return e;
+    if (int e = fill_segments(a, segs_host, n_seg, dims_host[0], true, P)) return e;
     if (P == 0) return 0;
     PS_REQUIRE((dy || d_density) && W_host && b_host && dW_host && db_host, "mlp_bwd: null pointer");
     a.dy = dy; a.P = P; a.in_dim = dims_host[0]; a.out_dim = dims_host[n_layers]; a.out_act = out_act;

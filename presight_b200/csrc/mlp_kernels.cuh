@@ -97,15 +97,37 @@ __device__ __forceinline__ void load_rows_seg(const MlpArgs& a, int64_t row0, in
     const int g = lane >> 2, t = lane & 3;
     const int64_t r0 = row0 + g, r1 = r0 + 8;
     const bool v0 = r0 < a.P, v1 = r1 < a.P;
-    // per-segment base addresses of the two rows
+    if (a.nseg == 1 && a.seg[0].group == 1) {
+        // common case: one per-point source (possibly a strided column window)
+        const float* p0 = a.seg[0].src + r0 * a.seg[0].stride + a.seg[0].col0;
+        const float* p1 = a.seg[0].src + r1 * a.seg[0].stride + a.seg[0].col0;
+#pragma unroll
+        for (int j = 0; j < KB; ++j) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = 8 * j + 2 * t + h;
+                const bool live = col < a.in_dim;
+                c[j][h] = (live && v0) ? __ldg(p0 + col) : 0.f;
+                c[j][2 + h] = (live && v1) ? __ldg(p1 + col) : 0.f;
+            }
+        }
+        return;
+    }
+    // per-segment base addresses of the two rows.  A warp's 16 rows (row0 is a multiple of 16, groups are multiples
+    // of 16) always share one group index, so the division is done once per warp in 32 bits.
     const float* b0[PS_MLP_MAX_SEGMENTS];
     const float* b1[PS_MLP_MAX_SEGMENTS];
 #pragma unroll
     for (int s = 0; s < PS_MLP_MAX_SEGMENTS; ++s) {
         if (s < a.nseg) {
             const RowSeg& sg = a.seg[s];
-            b0[s] = sg.src + (v0 ? r0 / sg.group : 0) * sg.stride + sg.col0 - sg.begin;
-            b1[s] = sg.src + (v1 ? r1 / sg.group : 0) * sg.stride + sg.col0 - sg.begin;
+            if (sg.group == 1) {
+                b0[s] = sg.src + (v0 ? r0 : 0) * sg.stride + sg.col0 - sg.begin;
+                b1[s] = sg.src + (v1 ? r1 : 0) * sg.stride + sg.col0 - sg.begin;
+            } else {
+                const int64_t q = (int64_t)((uint32_t)row0 / (uint32_t)sg.group);
+                b0[s] = b1[s] = sg.src + q * sg.stride + sg.col0 - sg.begin;
+            }
         } else {
             b0[s] = b1[s] = nullptr;
         }
@@ -135,6 +157,22 @@ __device__ __forceinline__ void store_dx_seg(const MlpArgs& a, int64_t row0, int
     const int g = lane >> 2, t = lane & 3;
     const int64_t r0 = row0 + g, r1 = r0 + 8;
     const bool v0 = r0 < a.P, v1 = r1 < a.P;
+    if (a.nseg == 1 && a.seg[0].group == 1) {
+        float* p0 = a.seg[0].dst + r0 * a.seg[0].stride + a.seg[0].col0;
+        float* p1 = a.seg[0].dst + r1 * a.seg[0].stride + a.seg[0].col0;
+#pragma unroll
+        for (int j = 0; j < KB; ++j) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = 8 * j + 2 * t + h;
+                if (col < a.in_dim) {
+                    if (v0) p0[col] = d[j][h];
+                    if (v1) p1[col] = d[j][2 + h];
+                }
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < KB; ++j) {
 #pragma unroll
@@ -150,7 +188,7 @@ __device__ __forceinline__ void store_dx_seg(const MlpArgs& a, int64_t row0, int
                 sum += __shfl_xor_sync(0xffffffffu, sum, 8);
                 sum += __shfl_xor_sync(0xffffffffu, sum, 16);
                 if (live && sg.group > 1 && sg.dst && g == 0 && row0 < a.P)
-                    atomicAdd(sg.dst + (row0 / sg.group) * sg.stride + sg.col0 + (col - sg.begin), sum);
+                    atomicAdd(sg.dst + (int64_t)((uint32_t)row0 / (uint32_t)sg.group) * sg.stride + sg.col0 + (col - sg.begin), sum);
             }
             if (live && sg.group == 1 && sg.dst) {
                 float* base = sg.dst + sg.col0 + (col - sg.begin);
