@@ -77,6 +77,11 @@ int ps_sh4(const float* dirs, int64_t P, int mapped, float* out, void* stream);
 /* nearest-centroid routing (fields/PreSight/ingp_field_ms.py:97): assign[p] = argmin_j |pos_p - c_j| */
 int ps_nearest_centroid(const float* pos, int64_t P, const float* centroids, int nf, int32_t* assign, void* stream);
 
+/* Prior query epilogue (scripts/extract_priors.py:137-138): mean[i] = (1/k) sum_j densities_host[j][i];
+ * feats_half[i,c] = half(clip(sem[i,c], 0, 1)).  densities_host: HOST array of k device pointers (k <= 8). */
+int ps_prior_finalize(const float* const* densities_host, int k, const float* sem, int64_t M, int C, float* mean,
+                      void* feats_half, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Kernel #2 — fused MLP (Linear+ReLU stack, optional output activation).
  * Replaces MLP.pytorch_fwd (field_components/mlp.py:157-174) and its autograd.

@@ -32,6 +32,7 @@ SIGNATURES = {
     "ps_ray_points": [_p, _p, _p, _i64, _i, _fp, _i, _p, _p, _p],
     "ps_mlp_fwd_ex": [_p, _i, _i64, _pp, _pp, _ip, _i, _i, _i, _p, _p, _p, _p],
     "ps_mlp_bwd_ex": [_p, _i, _p, _i64, _pp, _pp, _ip, _i, _i, _i, _pp, _pp, _p, _p, _p],
+    "ps_prior_finalize": [_pp, _i, _p, _i64, _i, _p, _p, _p],
     "ps_sh4": [_p, _i64, _i, _p, _p],
     "ps_nearest_centroid": [_p, _i64, _p, _i, _p, _p],
     "ps_mlp_fwd": [_p, _i64, _pp, _pp, _ip, _i, _i, _i, _p, _p],

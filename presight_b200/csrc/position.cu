@@ -1,5 +1,7 @@
 // Position prologue / small per-point kernels: aabb normalisation + L-inf contraction + selector,
 // frustum mid-points, degree-4 SH, nearest-centroid routing, trunc_exp.
+#include <cuda_fp16.h>
+
 #include "position.cuh"
 
 namespace ps {
@@ -110,9 +112,51 @@ __global__ void __launch_bounds__(256) trunc_exp_bwd_kernel(const float* __restr
     dx[p * dxs] = g * expf(fminf(fmaxf(x[p * xs], -15.f), 15.f));
 }
 
+struct DensityPtrs {
+    const float* p[8];
+    int k;
+};
+
+// scripts/extract_priors.py:137-138: mean over the k density estimates, features clipped to [0,1] and cast to fp16
+__global__ void __launch_bounds__(256) prior_finalize_kernel(DensityPtrs d, const float* __restrict__ sem, int64_t M,
+                                                             int C, float* __restrict__ mean,
+                                                             __half* __restrict__ feats) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M && mean) {
+        float s = 0.f;
+        for (int j = 0; j < d.k; ++j) s += __ldg(d.p[j] + i);
+        mean[i] = s / (float)d.k;
+    }
+    if (feats) {
+        // C is a multiple of 2: one half2 per thread-iteration, grid-stride over M*C/2 pairs
+        const int64_t pairs = M * C / 2;
+        for (int64_t q = i; q < pairs; q += (int64_t)gridDim.x * blockDim.x) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(sem) + q);
+            reinterpret_cast<__half2*>(feats)[q] =
+                __floats2half2_rn(fminf(fmaxf(v.x, 0.f), 1.f), fminf(fmaxf(v.y, 0.f), 1.f));
+        }
+    }
+}
+
 }  // namespace ps
 
 using namespace ps;
+
+extern "C" int ps_prior_finalize(const float* const* densities_host, int k, const float* sem, int64_t M, int C,
+                                 float* mean, void* feats_half, void* stream) {
+    if (M == 0) return 0;
+    PS_REQUIRE(k >= 1 && k <= 8 && densities_host, "prior_finalize: need 1..8 density arrays");
+    PS_REQUIRE(feats_half == nullptr || (sem != nullptr && C % 2 == 0), "prior_finalize: C must be even");
+    DensityPtrs d;
+    d.k = k;
+    for (int j = 0; j < k; ++j) {
+        PS_REQUIRE(densities_host[j] != nullptr, "prior_finalize: density %d is null", j);
+        d.p[j] = densities_host[j];
+    }
+    prior_finalize_kernel<<<(unsigned)cdiv(M, 256), 256, 0, (cudaStream_t)stream>>>(d, sem, M, C, mean,
+                                                                                    (__half*)feats_half);
+    return check_launch("prior_finalize");
+}
 
 extern "C" int ps_normalize_positions(const float* pos, int64_t P, const float* aabb_host, int contract, float* x01,
                                       uint8_t* selector, void* stream) {

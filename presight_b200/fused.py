@@ -259,3 +259,52 @@ def field_level(origins, dirs, eu_bins, app, table, aabb, contract, grid: GridMe
     flat += [*rgb_params[0], *rgb_params[1]]
     return _FieldLevel.apply(origins, dirs, eu_bins, app, table, aabb, contract, grid, base, sem, rgb, geo_dim, prec,
                              threshold, *flat)
+
+
+@torch.no_grad()
+def query_priors(points_scaled: Tensor, prop_fields, field) -> Tuple[Tensor, Tensor]:
+    """Dense prior query for one sub-field (scripts/extract_priors.py:130-138): mean of the proposal and field
+    densities [M] fp32 and the clipped semantic features [M,C] fp16.
+
+    The reference evaluates the main hash grid + base MLP twice (density_fn, then semantic_fn,
+    fields/PreSight/ingp_field.py:256); both evaluations are identical, so one pass serves both outputs.
+    prop_fields: PropNetDensityField list; field: iNGPField with semantics."""
+    pts = _f32c(points_scaled).view(-1, 3)
+    M, dev = pts.shape[0], pts.device
+    dens = []
+    x01 = sel = None
+    for f in [*prop_fields, field]:
+        key = (tuple(f.aabb_host()), f.spatial_distortion is not None)
+        if x01 is None or key != last_key:      # every network of a sub-field shares the aabb: normalise once
+            x01, sel = ops.normalize_positions(pts, f.aabb_host(), f.spatial_distortion is not None)
+            sel = sel.reshape(-1)
+            last_key = key
+        if f is field:
+            enc, mlp = f.mlp_base_grid, f.mlp_base_mlp
+            layers = list(mlp.layers)
+            prec = mlp.precision
+        else:
+            enc = f.encoding
+            layers = [f.linear] if f.use_linear else list(f.mlp_base[1].layers)
+            prec = f._precision
+        g = GridMeta(enc._scalings_host, enc.log2_hashmap_size, enc.features_per_level)
+        feat = _hash_fwd(x01, enc.hash_table.detach(), g)
+        meta = MlpMeta((layers[0].weight.shape[1],) + tuple(l.weight.shape[0] for l in layers), ops.ACT_NONE)
+        ws, bs = [l.weight.detach() for l in layers], [l.bias.detach() for l in layers]
+        d = torch.empty(M, device=dev, dtype=torch.float32)
+        if f is field:
+            h = torch.empty(M, meta.dims[-1], device=dev, dtype=torch.float32)
+            _mlp_fwd([(feat, None, feat.shape[1], 0, feat.shape[1], 1)], M, ws, bs, meta, prec, h, sel, d, "base")
+        else:
+            _mlp_fwd([(feat, None, feat.shape[1], 0, feat.shape[1], 1)], M, ws, bs, meta, prec, None, sel, d, "prop")
+        dens.append(d)
+    sl = list(field.semantic_head.layers)
+    smeta = MlpMeta((sl[0].weight.shape[1],) + tuple(l.weight.shape[0] for l in sl), ops.ACT_NONE)
+    sem = torch.empty(M, smeta.dims[-1], device=dev, dtype=torch.float32)
+    _mlp_fwd([(h, None, h.shape[1], 1 + field.geo_feat_dim, field.semantic_dim, 1)], M,
+             [l.weight.detach() for l in sl], [l.bias.detach() for l in sl], smeta, field.semantic_head.precision, sem,
+             name="sem")
+    mean = torch.empty(M, device=dev, dtype=torch.float32)
+    feats = torch.empty(M, smeta.dims[-1], device=dev, dtype=torch.float16)
+    call("ps_prior_finalize", host_ptrs(dens), len(dens), ptr(sem), M, smeta.dims[-1], ptr(mean), ptr(feats), stream())
+    return mean, feats

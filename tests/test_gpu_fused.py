@@ -199,3 +199,29 @@ def test_mlp_segments_and_density_epilogue():
     gh_dev = gh.to(DEV)      # column 0 deliberately NOT zeroed: the kernel must ignore it when d_density is given
     fused._mlp_bwd([(fg, dfeat, 32, 0, 32, 1)], gh_dev, P, w2, b2, meta2, 0, dW2, db2, selg, gd.to(DEV))
     assert_close(dfeat.cpu(), fc.grad, 1e-3, "d features through the density epilogue")
+
+
+def test_fused_prior_query_matches_modular_and_oracle():
+    model, cfg = build_single_field_model("b200+fp32")
+    model.eval()
+    modular = copy.deepcopy(model)
+    modular.use_fused = False
+    g = torch.Generator().manual_seed(4)
+    pts = (torch.rand(5000, 3, generator=g) - 0.5) * torch.tensor([3.0, 2.5, 1.0])
+    mean_f, feats_f = model.query_priors(pts.to(DEV))
+    mean_m, feats_m = modular.query_priors(pts.to(DEV))
+    assert feats_f.dtype == torch.float16 and feats_f.shape == (5000, 64)
+    assert_close(mean_f, mean_m, 1e-5, "mean density fused vs modular")
+    assert_close(feats_f.float(), feats_m.float(), 1e-3, "features fused vs modular")
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ffx = Fixture("fields.npz")
+    field = OS.ngp_from_state(sd, "field.fields.0.", field_meta(ffx))
+    props = [[OS.prop_from_state(sd, f"proposal_networks.{i}.fields.0.", prop_meta(ffx, f"meta/prop{i}"))]
+             for i in range(2)]
+    om = O.Model(O.ModelCfg(), torch.zeros(1, 3), [field], props, None)
+    mean_o, feats_o = O.prior_query(om, pts)
+    assert_close(mean_f.cpu(), mean_o, 1e-3, "mean density vs oracle")
+    assert_close(feats_f.float().cpu(), feats_o.float(), 2e-3, "features vs oracle")
+    # empty query
+    m0, f0 = model.query_priors(torch.zeros(0, 3, device=DEV))
+    assert m0.shape == (0,) and f0.shape == (0, 64)

@@ -16,7 +16,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, overlap, q):
+def _worker(rank, world, port, overlap, outdir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -37,23 +37,22 @@ def _worker(rank, world, port, overlap, q):
     sync.finish()
     out = {"big": big.grad.clone(), "s0": small[0].grad.clone(), "s1": small[1].grad.clone(),
            "unused": None if unused.grad is None else unused.grad.clone(), "range": (lo, hi)}
-    q.put((rank, out))
+    torch.save(out, os.path.join(outdir, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("overlap", [True, False])
-def test_grad_synchronizer_gloo_world2(overlap):
+def test_grad_synchronizer_gloo_world2(overlap, tmp_path):
     ctx = mp.get_context("spawn")
-    q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, overlap, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, overlap, str(tmp_path))) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=120) for _ in range(2))
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=180)
         assert p.exitcode == 0
+    res = {r: torch.load(os.path.join(str(tmp_path), f"rank{r}.pt")) for r in range(2)}
     assert res[0]["range"] == (0, 500) and res[1]["range"] == (500, 1000)
     # mean over ranks of the per-rank gradients
     want_big = torch.zeros(1 << 17)
