@@ -62,6 +62,9 @@ static int fill_segments(MlpArgs& a, const ps_row_segment* segs, int n_seg, int 
         }
     }
     PS_REQUIRE(col == in_dim, "mlp: segments cover %d columns but the first layer expects %d", col, in_dim);
+    auto aligned8 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 7u) == 0; };
+    a.vec2_x = n_seg == 1 && segs[0].group == 1 && in_dim % 2 == 0 && segs[0].stride % 2 == 0 && segs[0].col0 % 2 == 0 &&
+               aligned8(segs[0].src) && aligned8(a.seg[0].dst);
     return 0;
 }
 
@@ -71,11 +74,12 @@ extern "C" int ps_mlp_fwd_ex(const ps_row_segment* segs_host, int n_seg, int64_t
     int K0, H, NHID, NOUT;
     if (int e = resolve(dims_host, n_layers, K0, H, NHID, NOUT)) return e;
     MlpArgs a{};
+    if (P == 0) return 0;   // empty batches are a no-op (their tensors have null data pointers)
     if (int e = fill_segments(a, segs_host, n_seg, dims_host[0], false, P)) return e;
-    if (P == 0) return 0;
     PS_REQUIRE((y || density_out) && W_host && b_host, "mlp_fwd: null pointer");
     a.y = y; a.P = P; a.in_dim = dims_host[0]; a.out_dim = dims_host[n_layers]; a.out_act = out_act;
     a.sel = sel; a.density_out = density_out;
+    a.vec2_y = a.out_dim % 2 == 0 && (reinterpret_cast<uintptr_t>(y) & 7u) == 0;
     for (int i = 0; i < n_layers; ++i) {
         PS_REQUIRE(W_host[i] != nullptr, "mlp_fwd: weight %d is null", i);
         a.W[i] = W_host[i];
@@ -91,11 +95,12 @@ extern "C" int ps_mlp_bwd_ex(const ps_row_segment* segs_host, int n_seg, const f
     int K0, H, NHID, NOUT;
     if (int e = resolve(dims_host, n_layers, K0, H, NHID, NOUT)) return e;
     MlpArgs a{};
-    if (int e = fill_segments(a, segs_host, n_seg, dims_host[0], true, P)) return e;
     if (P == 0) return 0;
+    if (int e = fill_segments(a, segs_host, n_seg, dims_host[0], true, P)) return e;
     PS_REQUIRE((dy || d_density) && W_host && b_host && dW_host && db_host, "mlp_bwd: null pointer");
     a.dy = dy; a.P = P; a.in_dim = dims_host[0]; a.out_dim = dims_host[n_layers]; a.out_act = out_act;
     a.sel = sel; a.d_density = d_density;
+    a.vec2_y = a.out_dim % 2 == 0 && (reinterpret_cast<uintptr_t>(dy) & 7u) == 0;
     for (int i = 0; i < n_layers; ++i) {
         PS_REQUIRE(W_host[i] != nullptr && dW_host[i] != nullptr, "mlp_bwd: weight/grad %d is null", i);
         a.W[i] = W_host[i];

@@ -28,6 +28,8 @@ struct MlpArgs {
     int nseg;
     int any_group_dst;  // some segment has group > 1 and dst != null
     int want_dx;        // some segment has dst != null
+    int vec2_x;         // single per-point segment whose src/dst rows can be accessed as aligned float2 pairs
+    int vec2_y;         // y / dy rows can be accessed as aligned float2 pairs
     float* y;           // [P, out_dim] (nullable when only density_out is wanted)
     const float* dy;    // [P, out_dim] (nullable: zero)
     int64_t P;
@@ -70,6 +72,33 @@ __device__ __forceinline__ void load_rows(const float* __restrict__ x, int64_t P
 }
 
 template <int KB>
+__device__ __forceinline__ void load_rows_v2(const float* __restrict__ x, int64_t P, int dim, int64_t row0, int lane,
+                                             float (&c)[KB][4]) {
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t r0 = row0 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int j = 0; j < KB; ++j) {
+        const int col = 8 * j + 2 * t;
+        const float2 a = (r0 < P && col < dim) ? __ldg(reinterpret_cast<const float2*>(x + r0 * dim + col)) : make_float2(0.f, 0.f);
+        const float2 b = (r1 < P && col < dim) ? __ldg(reinterpret_cast<const float2*>(x + r1 * dim + col)) : make_float2(0.f, 0.f);
+        c[j][0] = a.x; c[j][1] = a.y; c[j][2] = b.x; c[j][3] = b.y;
+    }
+}
+
+template <int KB>
+__device__ __forceinline__ void store_rows_v2(float* __restrict__ y, int64_t P, int dim, int64_t row0, int lane,
+                                              const float (&c)[KB][4]) {
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t r0 = row0 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int j = 0; j < KB; ++j) {
+        const int col = 8 * j + 2 * t;
+        if (r0 < P && col < dim) *reinterpret_cast<float2*>(y + r0 * dim + col) = make_float2(c[j][0], c[j][1]);
+        if (r1 < P && col < dim) *reinterpret_cast<float2*>(y + r1 * dim + col) = make_float2(c[j][2], c[j][3]);
+    }
+}
+
+template <int KB>
 __device__ __forceinline__ void store_rows(float* __restrict__ y, int64_t P, int dim, int64_t row0, int lane,
                                            const float (&c)[KB][4]) {
     const int g = lane >> 2, t = lane & 3;
@@ -101,6 +130,17 @@ __device__ __forceinline__ void load_rows_seg(const MlpArgs& a, int64_t row0, in
         // common case: one per-point source (possibly a strided column window)
         const float* p0 = a.seg[0].src + r0 * a.seg[0].stride + a.seg[0].col0;
         const float* p1 = a.seg[0].src + r1 * a.seg[0].stride + a.seg[0].col0;
+        if (a.vec2_x) {
+#pragma unroll
+            for (int j = 0; j < KB; ++j) {
+                const int col = 8 * j + 2 * t;          // in_dim is even: the pair is live or dead as a whole
+                const bool live = col < a.in_dim;
+                const float2 x0 = (live && v0) ? __ldg(reinterpret_cast<const float2*>(p0 + col)) : make_float2(0.f, 0.f);
+                const float2 x1 = (live && v1) ? __ldg(reinterpret_cast<const float2*>(p1 + col)) : make_float2(0.f, 0.f);
+                c[j][0] = x0.x; c[j][1] = x0.y; c[j][2] = x1.x; c[j][3] = x1.y;
+            }
+            return;
+        }
 #pragma unroll
         for (int j = 0; j < KB; ++j) {
 #pragma unroll
@@ -160,6 +200,17 @@ __device__ __forceinline__ void store_dx_seg(const MlpArgs& a, int64_t row0, int
     if (a.nseg == 1 && a.seg[0].group == 1) {
         float* p0 = a.seg[0].dst + r0 * a.seg[0].stride + a.seg[0].col0;
         float* p1 = a.seg[0].dst + r1 * a.seg[0].stride + a.seg[0].col0;
+        if (a.vec2_x) {
+#pragma unroll
+            for (int j = 0; j < KB; ++j) {
+                const int col = 8 * j + 2 * t;
+                if (col < a.in_dim) {
+                    if (v0) *reinterpret_cast<float2*>(p0 + col) = make_float2(d[j][0], d[j][1]);
+                    if (v1) *reinterpret_cast<float2*>(p1 + col) = make_float2(d[j][2], d[j][3]);
+                }
+            }
+            return;
+        }
 #pragma unroll
         for (int j = 0; j < KB; ++j) {
 #pragma unroll
@@ -324,7 +375,12 @@ __global__ void __launch_bounds__(kThreads) mlp_fwd_kernel(MlpArgs a) {
             if (r0 < a.P) a.density_out[r0] = expf(out[0][0]) * (a.sel ? (float)a.sel[r0] : 1.f);
             if (r1 < a.P) a.density_out[r1] = expf(out[0][2]) * (a.sel ? (float)a.sel[r1] : 1.f);
         }
-        if (a.y) store_rows<S::NOUT / 8>(a.y, a.P, a.out_dim, row0, lane, out);
+        if (a.y) {
+            if (a.vec2_y)
+                store_rows_v2<S::NOUT / 8>(a.y, a.P, a.out_dim, row0, lane, out);
+            else
+                store_rows<S::NOUT / 8>(a.y, a.P, a.out_dim, row0, lane, out);
+        }
     }
 }
 
@@ -342,17 +398,27 @@ __device__ __forceinline__ void accumulate_dw(const typename Elem<PREC>::type* d
             dw_block<kTile, PREC>(dZs, stride_of<PREC>(N), n0, Acts, stride_of<PREC>(K), f0, acc[i], lane);
         }
     }
-    if (tid < N) {
+    // bias gradient = column sums of dZ: the tile's rows are split over R = kThreads / N thread groups so the
+    // dependent-add chain is kTile / R long; partial sums stay in one persistent register per thread
+    {
         constexpr int SZ = stride_of<PREC>(N);
-        float s = 0.f;
-#pragma unroll 8
-        for (int p = 0; p < kTile; ++p) {
-            if constexpr (PREC == kBF16)
-                s += __bfloat162float(dZs[p * SZ + tid]);
-            else
-                s += dZs[p * SZ + tid];
+        constexpr int R = kThreads / N, ROWS = (kTile + R - 1) / R;
+        if (tid < R * N) {
+            const int col = tid % N, r0 = (tid / N) * ROWS;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+            for (int p = 0; p < ROWS; p += 2) {
+                const int pa = r0 + p, pb = r0 + p + 1;
+                if constexpr (PREC == kBF16) {
+                    if (pa < kTile) s0 += __bfloat162float(dZs[pa * SZ + col]);
+                    if (pb < kTile && p + 1 < ROWS) s1 += __bfloat162float(dZs[pb * SZ + col]);
+                } else {
+                    if (pa < kTile) s0 += dZs[pa * SZ + col];
+                    if (pb < kTile && p + 1 < ROWS) s1 += dZs[pb * SZ + col];
+                }
+            }
+            db += s0 + s1;
         }
-        db += s;
     }
 }
 
@@ -375,7 +441,7 @@ __device__ __forceinline__ void flush_dw(float* __restrict__ dW, float* __restri
                 }
         }
     }
-    if (dbg && tid < n_real) atomicAdd(dbg + tid, db);
+    if (dbg && tid < (kThreads / N) * N && (tid % N) < n_real) atomicAdd(dbg + (tid % N), db);
 }
 
 template <int K, int N>
@@ -439,7 +505,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(MlpArgs a) {
             }
             // ---- gradient w.r.t. the last pre-activation ----------------------------------------
             if (a.dy) {
-                load_rows<S::NOUT / 8>(a.dy, a.P, a.out_dim, row0, lane, dz);
+                if (a.vec2_y)
+                    load_rows_v2<S::NOUT / 8>(a.dy, a.P, a.out_dim, row0, lane, dz);
+                else
+                    load_rows<S::NOUT / 8>(a.dy, a.P, a.out_dim, row0, lane, dz);
             } else {
 #pragma unroll
                 for (int j = 0; j < S::NOUT / 8; ++j) dz[j][0] = dz[j][1] = dz[j][2] = dz[j][3] = 0.f;
