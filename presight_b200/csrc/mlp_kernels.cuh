@@ -450,7 +450,7 @@ constexpr int max_blocks() {
 }
 
 template <class S, int PREC>
-__global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(MlpArgs a) {
+__global__ void __launch_bounds__(kThreads, PREC == kBF16 ? 2 : 1) mlp_bwd_kernel(MlpArgs a) {
     using E = typename Elem<PREC>::type;
     using SM = Smem<S, PREC>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -606,8 +606,13 @@ int launch_fwd(const MlpArgs& a, cudaStream_t stream) {
         }
         configured = true;
     }
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, mlp_fwd_kernel<S, PREC>, kThreads, smem) !=
+                cudaSuccess || ctas_per_sm < 1)
+            ctas_per_sm = 1;
+    }
     const int64_t ntiles = (a.P + kTile - 1) / kTile;
-    const int ctas_per_sm = smem > 100 * 1024 ? 1 : 2;
     const int grid = (int)(ntiles < (int64_t)kNumSMs * ctas_per_sm ? ntiles : (int64_t)kNumSMs * ctas_per_sm);
     mlp_fwd_kernel<S, PREC><<<grid, kThreads, smem, stream>>>(a);
     return check_launch("mlp_fwd");
@@ -626,8 +631,14 @@ int launch_bwd(const MlpArgs& a, cudaStream_t stream) {
         }
         configured = true;
     }
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, mlp_bwd_kernel<S, PREC>, kThreads, smem) !=
+                cudaSuccess || ctas_per_sm < 1)
+            ctas_per_sm = 1;
+    }
     const int64_t ntiles = (a.P + kTile - 1) / kTile;
-    const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+    const int grid = (int)(ntiles < (int64_t)kNumSMs * ctas_per_sm ? ntiles : (int64_t)kNumSMs * ctas_per_sm);
     mlp_bwd_kernel<S, PREC><<<grid, kThreads, smem, stream>>>(a);
     return check_launch("mlp_bwd");
 }
