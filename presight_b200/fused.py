@@ -49,7 +49,7 @@ class MlpMeta:
 def _mlp_fwd(segs, P, ws, bs, meta: MlpMeta, prec, y, sel=None, density_out=None, name="mlp"):
     with ops._probe(f"mlp_fwd_{name}"):
         call("ps_mlp_fwd_ex", host_segments(segs), len(segs), P, host_ptrs(ws), host_ptrs(bs), host_ints(meta.dims),
-             meta.n_layers, meta.out_act, prec, ptr(y), ptr(sel), ptr(density_out), stream())
+             meta.n_layers, meta.out_act, ops.fwd_precision(prec), ptr(y), ptr(sel), ptr(density_out), stream())
 
 
 def _mlp_bwd(segs, dy, P, ws, bs, meta: MlpMeta, prec, dW, db, sel=None, d_density=None, name="mlp"):

@@ -6,6 +6,7 @@ There is no CPU / PyTorch fallback.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -15,7 +16,16 @@ from . import _lib
 from ._lib import call, host_floats, host_ints, host_ptrs, ptr, stream
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
-PREC_TF32X3, PREC_BF16 = 0, 1
+PREC_TF32X3, PREC_BF16, PREC_BF16_TCGEN05 = 0, 1, 2
+# PS_TCGEN05_FWD=1 routes bf16 forward passes through the tcgen05 / TMEM kernel (csrc/mlp_tc5.cu).  It is correct
+# (tests/test_gpu_kernels.py::test_mlp_tcgen05_forward) but, un-pipelined as it is, 0.7 ms/step slower than the
+# register-chained mma.sync kernel on C2 (profiles/r1_d_*), so it is opt-in for now.
+TCGEN05_FWD = os.environ.get("PS_TCGEN05_FWD", "0") == "1"
+
+
+def fwd_precision(precision: int) -> int:
+    return PREC_BF16_TCGEN05 if (precision == PREC_BF16 and TCGEN05_FWD) else precision
+
 
 
 class KernelProbe:
@@ -173,7 +183,7 @@ class _Mlp(torch.autograd.Function):
         bd = [None if b is None else b.detach().contiguous() for b in bs]
         with _probe("mlp_fwd_" + "x".join(map(str, dims))):
             call("ps_mlp_fwd", ptr(x2), x2.shape[0], host_ptrs(wd), host_ptrs(bd), host_ints(dims), n_layers, out_act,
-                 precision, ptr(y), stream())
+                 fwd_precision(precision), ptr(y), stream())
         ctx.save_for_backward(x2, *wd, *[b for b in bd if b is not None])
         ctx.meta = (out_act, precision, n_layers, dims, [b is not None for b in bd], x.shape)
         return y.view(*lead, dims[-1])
