@@ -51,6 +51,15 @@ int ps_hash_fwd(const float* x01, int64_t P, const float* table, const float* sc
 /* dtable [L*T,F] += scatter of dout [P,L*F];  dx [P,3] (nullable, caller-zeroed) += d/dx01.  */
 int ps_hash_bwd(const float* x01, int64_t P, const float* table, const float* scalings_host, int L, int F,
                 int log2_T, const float* dout, float* dtable, float* dx, void* stream);
+/* Same kernels with the features / feature gradients stored level-major, [L][P][F] instead of [P][L*F]: every level's
+ * F-vector of consecutive points is contiguous, so the per-level passes read and write full sectors.  Used by the
+ * level-fused path together with ps_row_segment.feat_per_level. */
+int ps_hash_fwd_lm(const float* x01, int64_t P, const float* table, const float* scalings_host, int L, int F,
+                   int log2_T, float* out, void* stream);
+int ps_hash_bwd_lm(const float* x01, int64_t P, const float* table, const float* scalings_host, int L, int F,
+                   int log2_T, const float* dout, float* dtable, float* dx, void* stream);
+/* Levels handled per thread for this grid shape (level groups are chosen so that the live tables stay L2-resident). */
+int ps_hash_levels_per_thread(int L, int F, int log2_T);
 /* Parity probe: the 8 corner rows (incl. level*T) in the reference's corner order h0..h7
  * (encodings.py:354-361) and the fractional offsets.  idx [P,L,8] int64, offset [P,L,3] fp32 (nullable). */
 int ps_hash_indices(const float* x01, int64_t P, const float* scalings_host, int L, int log2_T, int64_t* idx,
@@ -113,6 +122,9 @@ typedef struct {
     float* dst;
     int64_t stride;
     int col0, width, group;
+    int feat_per_level; /* 0: rows are contiguous (src[r*stride + col0 + c]).  F > 0 (single-segment inputs only): the
+                           columns are hash features stored level-major [L][P][F], element (r, c) at
+                           src[((c / F) * P + r) * F + c % F] — the layout of ps_hash_fwd_lm / ps_hash_bwd_lm. */
 } ps_row_segment;
 int ps_mlp_fwd_ex(const ps_row_segment* segs_host, int n_seg, int64_t P, const float* const* W_host,
                   const float* const* b_host, const int* dims_host, int n_layers, int out_act, int precision, float* y,

@@ -26,6 +26,9 @@ _ip = C.POINTER(C.c_int)
 SIGNATURES = {
     "ps_hash_fwd": [_p, _i64, _p, _fp, _i, _i, _i, _p, _p],
     "ps_hash_bwd": [_p, _i64, _p, _fp, _i, _i, _i, _p, _p, _p, _p],
+    "ps_hash_fwd_lm": [_p, _i64, _p, _fp, _i, _i, _i, _p, _p],
+    "ps_hash_bwd_lm": [_p, _i64, _p, _fp, _i, _i, _i, _p, _p, _p, _p],
+    "ps_hash_levels_per_thread": [_i, _i, _i],
     "ps_hash_indices": [_p, _i64, _fp, _i, _i, _p, _p, _p],
     "ps_normalize_positions": [_p, _i64, _fp, _i, _p, _p, _p],
     "ps_sample_positions": [_p, _p, _p, _i64, _i, _p, _p],
@@ -85,6 +88,10 @@ def launch_count() -> int:
     return int(load().ps_launch_count())
 
 
+def hash_levels_per_thread(L: int, F: int, log2_T: int) -> int:
+    return int(load().ps_hash_levels_per_thread(int(L), int(F), int(log2_T)))
+
+
 def check(status: int, what: str) -> None:
     if status != 0:
         msg = load().ps_last_error().decode("utf-8", "replace")
@@ -119,14 +126,16 @@ def host_ptrs(tensors: Sequence[Optional[torch.Tensor]]):
 class RowSegment(C.Structure):
     """ps_row_segment of include/presight_b200.h."""
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("stride", C.c_int64), ("col0", C.c_int),
-                ("width", C.c_int), ("group", C.c_int)]
+                ("width", C.c_int), ("group", C.c_int), ("feat_per_level", C.c_int)]
 
 
 def host_segments(segs):
-    """segs: iterable of (src tensor, dst tensor|None, stride, col0, width, group)."""
+    """segs: iterable of (src tensor, dst tensor|None, stride, col0, width, group[, feat_per_level])."""
     segs = list(segs)
     arr = (RowSegment * len(segs))()
-    for i, (src, dst, stride, col0, width, group) in enumerate(segs):
+    for i, seg in enumerate(segs):
+        src, dst, stride, col0, width, group = seg[:6]
+        arr[i].feat_per_level = int(seg[6]) if len(seg) > 6 else 0
         arr[i].src = src.data_ptr()
         arr[i].dst = None if dst is None else dst.data_ptr()
         arr[i].stride, arr[i].col0, arr[i].width, arr[i].group = int(stride), int(col0), int(width), int(group)

@@ -16,7 +16,7 @@ namespace ps {
 template <int F, int LPT>
 __global__ void __launch_bounds__(256) hash_fwd_kernel(const float* __restrict__ x, int64_t P,
                                                        const float* __restrict__ table, HashParams hp,
-                                                       float* __restrict__ out) {
+                                                       float* __restrict__ out, int level_major) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
     const int l0 = blockIdx.y * LPT;
@@ -36,6 +36,23 @@ __global__ void __launch_bounds__(256) hash_fwd_kernel(const float* __restrict__
             const float t[8] = {v[0][f], v[1][f], v[2][f], v[3][f], v[4][f], v[5][f], v[6][f], v[7][f]};
             o[i][f] = trilerp_ref(t, c.ox, c.oy, c.oz);
         }
+    }
+    if (level_major) {
+        // features stored [L][P][F]: consecutive threads write consecutive F-vectors of one level (coalesced)
+#pragma unroll
+        for (int i = 0; i < LPT; ++i) {
+            float* d = out + ((size_t)(l0 + i) * P + p) * F;
+            if constexpr (F == 1) {
+                d[0] = o[i][0];
+            } else if constexpr (F == 2) {
+                *reinterpret_cast<float2*>(d) = make_float2(o[i][0], o[i][1]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < F / 4; ++q)
+                    reinterpret_cast<float4*>(d)[q] = make_float4(o[i][4 * q], o[i][4 * q + 1], o[i][4 * q + 2], o[i][4 * q + 3]);
+            }
+        }
+        return;
     }
     // LPT*F consecutive floats of this point's output row
     float* dst = out + (p * hp.L + l0) * F;
@@ -95,7 +112,7 @@ template <int F, int LPT, bool WITH_DX>
 __global__ void __launch_bounds__(256) hash_bwd_kernel(const float* __restrict__ x, int64_t P,
                                                        const float* __restrict__ table, HashParams hp,
                                                        const float* __restrict__ dout, float* __restrict__ dtable,
-                                                       float* __restrict__ dx) {
+                                                       float* __restrict__ dx, int level_major) {
     // every lane stays alive (full-mask shuffles below); out-of-range lanes carry zero gradient
     const int64_t pi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = pi < P;
@@ -108,7 +125,24 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const float* __restrict__
     constexpr int NV = LPT * F;
     float gin[NV];
     const float* src = dout + (p * hp.L + l0) * F;
-    if constexpr (NV % 4 == 0) {
+    if (level_major) {
+#pragma unroll
+        for (int i = 0; i < LPT; ++i) {
+            const float* d = dout + ((size_t)(l0 + i) * P + p) * F;
+            if constexpr (F == 1) {
+                gin[i] = __ldg(d);
+            } else if constexpr (F == 2) {
+                const float2 t = __ldg(reinterpret_cast<const float2*>(d));
+                gin[2 * i] = t.x; gin[2 * i + 1] = t.y;
+            } else {
+#pragma unroll
+                for (int q = 0; q < F / 4; ++q) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(d) + q);
+                    gin[i * F + 4 * q] = t.x; gin[i * F + 4 * q + 1] = t.y; gin[i * F + 4 * q + 2] = t.z; gin[i * F + 4 * q + 3] = t.w;
+                }
+            }
+        }
+    } else if constexpr (NV % 4 == 0) {
 #pragma unroll
         for (int q = 0; q < NV / 4; ++q) {
             const float4 t = __ldg(reinterpret_cast<const float4*>(src) + q);
@@ -284,8 +318,8 @@ using namespace ps;
             break;                                                         \
     }
 
-extern "C" int ps_hash_fwd(const float* x01, int64_t P, const float* table, const float* scalings_host, int L, int F,
-                           int log2_T, float* out, void* stream) {
+static int hash_fwd_impl(const float* x01, int64_t P, const float* table, const float* scalings_host, int L, int F,
+                         int log2_T, float* out, int level_major, void* stream) {
     HashParams hp;
     if (int e = fill_params(hp, scalings_host, L, log2_T)) return e;
     PS_REQUIRE(F == 1 || F == 2 || F == 4 || F == 8, "hash_fwd: features_per_level %d not in {1,2,4,8}", F);
@@ -298,14 +332,14 @@ extern "C" int ps_hash_fwd(const float* x01, int64_t P, const float* table, cons
     cudaStream_t s = (cudaStream_t)stream;
     const int lpt = pick_lpt(L, F, log2_T);
     const dim3 grid((unsigned)blocks, (unsigned)(L / lpt));
-#define PS_FWD(FF, LL) hash_fwd_kernel<FF, LL><<<grid, threads, 0, s>>>(x01, P, table, hp, out);
+#define PS_FWD(FF, LL) hash_fwd_kernel<FF, LL><<<grid, threads, 0, s>>>(x01, P, table, hp, out, level_major);
     PS_DISPATCH_F_LPT(F, lpt, PS_FWD)
 #undef PS_FWD
     return check_launch("hash_fwd");
 }
 
-extern "C" int ps_hash_bwd(const float* x01, int64_t P, const float* table, const float* scalings_host, int L, int F,
-                           int log2_T, const float* dout, float* dtable, float* dx, void* stream) {
+static int hash_bwd_impl(const float* x01, int64_t P, const float* table, const float* scalings_host, int L, int F,
+                         int log2_T, const float* dout, float* dtable, float* dx, int level_major, void* stream) {
     HashParams hp;
     if (int e = fill_params(hp, scalings_host, L, log2_T)) return e;
     PS_REQUIRE(F == 1 || F == 2 || F == 4 || F == 8, "hash_bwd: features_per_level %d not in {1,2,4,8}", F);
@@ -321,13 +355,35 @@ extern "C" int ps_hash_bwd(const float* x01, int64_t P, const float* table, cons
     const dim3 grid((unsigned)blocks, (unsigned)(L / lpt));
 #define PS_BWD(FF, LL)                                                                                  \
     if (dx)                                                                                             \
-        hash_bwd_kernel<FF, LL, true><<<grid, threads, 0, s>>>(x01, P, table, hp, dout, dtable, dx);    \
+        hash_bwd_kernel<FF, LL, true><<<grid, threads, 0, s>>>(x01, P, table, hp, dout, dtable, dx, level_major); \
     else                                                                                                \
-        hash_bwd_kernel<FF, LL, false><<<grid, threads, 0, s>>>(x01, P, table, hp, dout, dtable, dx);
+        hash_bwd_kernel<FF, LL, false><<<grid, threads, 0, s>>>(x01, P, table, hp, dout, dtable, dx, level_major);
     PS_DISPATCH_F_LPT(F, lpt, PS_BWD)
 #undef PS_BWD
     return check_launch("hash_bwd");
 }
+
+extern "C" int ps_hash_fwd(const float* x01, int64_t P, const float* table, const float* scalings_host, int L, int F,
+                           int log2_T, float* out, void* stream) {
+    return hash_fwd_impl(x01, P, table, scalings_host, L, F, log2_T, out, 0, stream);
+}
+extern "C" int ps_hash_bwd(const float* x01, int64_t P, const float* table, const float* scalings_host, int L, int F,
+                           int log2_T, const float* dout, float* dtable, float* dx, void* stream) {
+    return hash_bwd_impl(x01, P, table, scalings_host, L, F, log2_T, dout, dtable, dx, 0, stream);
+}
+// level-major feature layout [L][P][F] (fused path: coalesced per-level stores / loads)
+extern "C" int ps_hash_fwd_lm(const float* x01, int64_t P, const float* table, const float* scalings_host, int L,
+                              int F, int log2_T, float* out, void* stream) {
+    return hash_fwd_impl(x01, P, table, scalings_host, L, F, log2_T, out, 1, stream);
+}
+extern "C" int ps_hash_bwd_lm(const float* x01, int64_t P, const float* table, const float* scalings_host, int L,
+                              int F, int log2_T, const float* dout, float* dtable, float* dx, void* stream) {
+    return hash_bwd_impl(x01, P, table, scalings_host, L, F, log2_T, dout, dtable, dx, 1, stream);
+}
+
+// how many consecutive levels one thread handles for this grid shape (callers use it to choose the feature layout:
+// level-major pays off when a thread's LPT*F floats do not fill a 32-byte sector)
+extern "C" int ps_hash_levels_per_thread(int L, int F, int log2_T) { return pick_lpt(L, F, log2_T); }
 
 extern "C" int ps_hash_indices(const float* x01, int64_t P, const float* scalings_host, int L, int log2_T,
                                int64_t* idx, float* offset, void* stream) {

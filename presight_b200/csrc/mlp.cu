@@ -22,6 +22,7 @@ static int resolve(const int* dims, int n_layers, int& K0, int& H, int& NHID, in
 
 static int run(int K0, int H, int NHID, int NOUT, int prec, bool bwd, const MlpArgs& a, cudaStream_t s,
                const int* dims, int n_layers) {
+    if (a.lm_F > 0 && prec == 2) prec = 1;   // the tcgen05 forward reads row-major inputs only
     PS_REQUIRE(prec >= 0 && prec <= 2, "mlp: precision %d (0 = tf32x3 fp32-grade, 1 = bf16 mma.sync, 2 = bf16 tcgen05)",
                prec);
     if (prec == 2) {
@@ -71,6 +72,16 @@ static int fill_segments(MlpArgs& a, const ps_row_segment* segs, int n_seg, int 
         }
     }
     PS_REQUIRE(col == in_dim, "mlp: segments cover %d columns but the first layer expects %d", col, in_dim);
+    a.lm_F = 0;
+    if (segs[0].feat_per_level > 0) {
+        const int F = segs[0].feat_per_level;
+        PS_REQUIRE(n_seg == 1 && segs[0].group == 1 && segs[0].col0 == 0, "mlp: level-major features need one plain segment");
+        PS_REQUIRE((F == 1 || F == 2 || F == 4 || F == 8) && in_dim % F == 0, "mlp: feat_per_level %d invalid for %d columns",
+                   F, in_dim);
+        PS_REQUIRE((reinterpret_cast<uintptr_t>(segs[0].src) & 7u) == 0 && (reinterpret_cast<uintptr_t>(a.seg[0].dst) & 7u) == 0,
+                   "mlp: level-major features must be 8-byte aligned");
+        a.lm_F = F;
+    }
     auto aligned8 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 7u) == 0; };
     a.vec2_x = n_seg == 1 && segs[0].group == 1 && in_dim % 2 == 0 && segs[0].stride % 2 == 0 && segs[0].col0 % 2 == 0 &&
                aligned8(segs[0].src) && aligned8(a.seg[0].dst);

@@ -29,6 +29,7 @@ struct MlpArgs {
     int any_group_dst;  // some segment has group > 1 and dst != null
     int want_dx;        // some segment has dst != null
     int vec2_x;         // single per-point segment whose src/dst rows can be accessed as aligned float2 pairs
+    int lm_F;           // > 0: the single segment is level-major hash features [L][P][F] (see ps_row_segment)
     int vec2_y;         // y / dy rows can be accessed as aligned float2 pairs
     float* y;           // [P, out_dim] (nullable when only density_out is wanted)
     const float* dy;    // [P, out_dim] (nullable: zero)
@@ -126,6 +127,31 @@ __device__ __forceinline__ void load_rows_seg(const MlpArgs& a, int64_t row0, in
     const int g = lane >> 2, t = lane & 3;
     const int64_t r0 = row0 + g, r1 = r0 + 8;
     const bool v0 = r0 < a.P, v1 = r1 < a.P;
+    if (a.lm_F > 0) {
+        // level-major hash features [L][P][F]: element (r, c) at ((c / F) * P + r) * F + c % F.  For a fixed level
+        // the 8 rows of a lane group are contiguous, so every request moves full sectors.
+        const int F = a.lm_F;
+        const float* src = a.seg[0].src;
+#pragma unroll
+        for (int j = 0; j < KB; ++j) {
+            const int col = 8 * j + 2 * t;
+            float x00 = 0.f, x01 = 0.f, x10 = 0.f, x11 = 0.f;
+            if (col < a.in_dim) {
+                if (F >= 2) {       // the pair (col, col+1) lies inside one level's F-vector
+                    const int64_t lv = (int64_t)(col / F) * a.P;
+                    const int f = col % F;
+                    if (v0) { const float2 q = __ldg(reinterpret_cast<const float2*>(src + (lv + r0) * F + f)); x00 = q.x; x01 = q.y; }
+                    if (v1) { const float2 q = __ldg(reinterpret_cast<const float2*>(src + (lv + r1) * F + f)); x10 = q.x; x11 = q.y; }
+                } else {
+                    const bool second = col + 1 < a.in_dim;
+                    if (v0) { x00 = __ldg(src + (int64_t)col * a.P + r0); if (second) x01 = __ldg(src + (int64_t)(col + 1) * a.P + r0); }
+                    if (v1) { x10 = __ldg(src + (int64_t)col * a.P + r1); if (second) x11 = __ldg(src + (int64_t)(col + 1) * a.P + r1); }
+                }
+            }
+            c[j][0] = x00; c[j][1] = x01; c[j][2] = x10; c[j][3] = x11;
+        }
+        return;
+    }
     if (a.nseg == 1 && a.seg[0].group == 1) {
         // common case: one per-point source (possibly a strided column window)
         const float* p0 = a.seg[0].src + r0 * a.seg[0].stride + a.seg[0].col0;
@@ -197,6 +223,27 @@ __device__ __forceinline__ void store_dx_seg(const MlpArgs& a, int64_t row0, int
     const int g = lane >> 2, t = lane & 3;
     const int64_t r0 = row0 + g, r1 = r0 + 8;
     const bool v0 = r0 < a.P, v1 = r1 < a.P;
+    if (a.lm_F > 0) {
+        const int F = a.lm_F;
+        float* dst = a.seg[0].dst;
+#pragma unroll
+        for (int j = 0; j < KB; ++j) {
+            const int col = 8 * j + 2 * t;
+            if (col < a.in_dim) {
+                if (F >= 2) {
+                    const int64_t lv = (int64_t)(col / F) * a.P;
+                    const int f = col % F;
+                    if (v0) *reinterpret_cast<float2*>(dst + (lv + r0) * F + f) = make_float2(d[j][0], d[j][1]);
+                    if (v1) *reinterpret_cast<float2*>(dst + (lv + r1) * F + f) = make_float2(d[j][2], d[j][3]);
+                } else {
+                    const bool second = col + 1 < a.in_dim;
+                    if (v0) { dst[(int64_t)col * a.P + r0] = d[j][0]; if (second) dst[(int64_t)(col + 1) * a.P + r0] = d[j][1]; }
+                    if (v1) { dst[(int64_t)col * a.P + r1] = d[j][2]; if (second) dst[(int64_t)(col + 1) * a.P + r1] = d[j][3]; }
+                }
+            }
+        }
+        return;
+    }
     if (a.nseg == 1 && a.seg[0].group == 1) {
         float* p0 = a.seg[0].dst + r0 * a.seg[0].stride + a.seg[0].col0;
         float* p1 = a.seg[0].dst + r1 * a.seg[0].stride + a.seg[0].col0;

@@ -35,6 +35,13 @@ class GridMeta:
     def L(self) -> int:
         return len(self.scalings)
 
+    @property
+    def level_major(self) -> bool:
+        """Store features [L][P][F] when a thread's levels-per-thread x F floats would not fill a 32-byte sector of
+        the row-major [P][L*F] layout (C2 main grid: 1 level x 2 floats per thread); small grids keep row-major."""
+        from ._lib import hash_levels_per_thread
+        return hash_levels_per_thread(self.L, self.F, self.log2_T) * self.F < 8
+
 
 @dataclass(frozen=True)
 class MlpMeta:
@@ -69,17 +76,24 @@ def _ray_points(origins, dirs, eu, aabb, contract):
 
 
 def _hash_fwd(x01, table, g: GridMeta):
+    """-> features as a flat tensor of P*L*F floats: level-major [L][P][F] (ps_hash_fwd_lm) when `g.level_major`,
+    else the reference's row-major [P][L*F]."""
     P = x01.shape[0]
-    out = torch.empty(P, g.L * g.F, device=x01.device, dtype=torch.float32)
+    out = torch.empty(P * g.L * g.F, device=x01.device, dtype=torch.float32)
     with ops._probe(f"hash_fwd_L{g.L}F{g.F}T{g.log2_T}"):
-        call("ps_hash_fwd", ptr(x01), P, ptr(table), host_floats(g.scalings), g.L, g.F, g.log2_T, ptr(out), stream())
+        call("ps_hash_fwd_lm" if g.level_major else "ps_hash_fwd", ptr(x01), P, ptr(table), host_floats(g.scalings), g.L, g.F, g.log2_T, ptr(out), stream())
     return out
+
+
+def _feat_seg(feat, dfeat, g: GridMeta):
+    """Row-segment descriptor of level-major hash features (and their gradient buffer)."""
+    return (feat, dfeat, g.L * g.F, 0, g.L * g.F, 1, g.F if g.level_major else 0)
 
 
 def _hash_bwd(x01, dfeat, table, g: GridMeta):
     dtable = torch.zeros_like(table)
     with ops._probe(f"hash_bwd_L{g.L}F{g.F}T{g.log2_T}"):
-        call("ps_hash_bwd", ptr(x01), x01.shape[0], None, host_floats(g.scalings), g.L, g.F, g.log2_T, ptr(dfeat),
+        call("ps_hash_bwd_lm" if g.level_major else "ps_hash_bwd", ptr(x01), x01.shape[0], None, host_floats(g.scalings), g.L, g.F, g.log2_T, ptr(dfeat),
              ptr(dtable), None, stream())
     return dtable
 
@@ -107,7 +121,7 @@ class _PropLevel(torch.autograd.Function):
         x01, sel = _ray_points(o, d, eu, aabb, contract)
         feat = _hash_fwd(x01, table.detach(), grid)
         density = torch.empty(P, device=eu.device, dtype=torch.float32)
-        _mlp_fwd([(feat, None, feat.shape[1], 0, feat.shape[1], 1)], P, ws, bs, net, prec, None, sel, density, "prop")
+        _mlp_fwd([_feat_seg(feat, None, grid)], P, ws, bs, net, prec, None, sel, density, "prop")
         w = torch.empty(N, S, device=eu.device, dtype=torch.float32)
         call("ps_composite_fwd", ptr(eu), ptr(density), None, None, N, S, 0, 0.5, ptr(w), None, None, None, None, None,
              None, stream())
@@ -127,8 +141,7 @@ class _PropLevel(torch.autograd.Function):
         dfeat = torch.empty_like(feat)
         dW = [torch.zeros_like(w) for w in ws]
         db = [torch.zeros_like(b) for b in bs]
-        _mlp_bwd([(feat, dfeat, feat.shape[1], 0, feat.shape[1], 1)], None, P, ws, bs, net, prec, dW, db, sel,
-                 d_density, "prop")
+        _mlp_bwd([_feat_seg(feat, dfeat, grid)], None, P, ws, bs, net, prec, dW, db, sel, d_density, "prop")
         dtable = _hash_bwd(x01, dfeat, table, grid)
         return (None, None, None, dtable, None, None, None, None, None, *dW, *db)
 
@@ -161,7 +174,7 @@ class _FieldLevel(torch.autograd.Function):
         feat = _hash_fwd(x01, table.detach(), grid)
         h = torch.empty(P, hd, device=dev, dtype=torch.float32)
         density = torch.empty(P, device=dev, dtype=torch.float32)
-        _mlp_fwd([(feat, None, feat.shape[1], 0, feat.shape[1], 1)], P, bw, bb, base, prec, h, sel, density, "base")
+        _mlp_fwd([_feat_seg(feat, None, grid)], P, bw, bb, base, prec, h, sel, density, "base")
         sem_s = None
         if sem is not None:
             sw, sb = nets[1]
@@ -241,8 +254,7 @@ class _FieldLevel(torch.autograd.Function):
         dfeat = torch.empty_like(feat)
         dWb = [torch.zeros_like(w) for w in bw]
         dbb = [torch.zeros_like(b) for b in bb]
-        _mlp_bwd([(feat, dfeat, feat.shape[1], 0, feat.shape[1], 1)], dh, P, bw, bb, base, prec, dWb, dbb, sel,
-                 d_density, "base")
+        _mlp_bwd([_feat_seg(feat, dfeat, grid)], dh, P, bw, bb, base, prec, dWb, dbb, sel, d_density, "base")
         dtable = _hash_bwd(x01, dfeat, table, grid)
         return (None, None, None, dapp, dtable, None, None, None, None, None, None, None, None, None,
                 *dWb, *dbb, *grads_sem, *dWr, *dbr)
@@ -294,9 +306,9 @@ def query_priors(points_scaled: Tensor, prop_fields, field) -> Tuple[Tensor, Ten
         d = torch.empty(M, device=dev, dtype=torch.float32)
         if f is field:
             h = torch.empty(M, meta.dims[-1], device=dev, dtype=torch.float32)
-            _mlp_fwd([(feat, None, feat.shape[1], 0, feat.shape[1], 1)], M, ws, bs, meta, prec, h, sel, d, "base")
+            _mlp_fwd([_feat_seg(feat, None, g)], M, ws, bs, meta, prec, h, sel, d, "base")
         else:
-            _mlp_fwd([(feat, None, feat.shape[1], 0, feat.shape[1], 1)], M, ws, bs, meta, prec, None, sel, d, "prop")
+            _mlp_fwd([_feat_seg(feat, None, g)], M, ws, bs, meta, prec, None, sel, d, "prop")
         dens.append(d)
     sl = list(field.semantic_head.layers)
     smeta = MlpMeta((sl[0].weight.shape[1],) + tuple(l.weight.shape[0] for l in sl), ops.ACT_NONE)

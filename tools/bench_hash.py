@@ -43,7 +43,7 @@ def main():
     P = args.points
     pts = {"uniform": torch.rand(P, 3, device=dev), "rays64": ray_points(P, 64, dev)}
     print(f"{'config':34s} {'points':8s} {'fwd ms':>8s} {'fwd GB/s':>9s} {'bwd ms':>8s} {'bwd GB/s':>9s} {'Gelem/s':>8s}")
-    for (L, F, log2T, hi) in [(16, 2, 22, 2048), (16, 2, 19, 2048), (16, 1, 22, 2048), (16, 1, 19, 2048),
+    for (L, F, log2T, hi) in [(16, 2, 22, 2048), (16, 2, 21, 2048), (16, 2, 20, 2048), (16, 2, 19, 2048), (16, 1, 22, 2048), (16, 1, 19, 2048),
                               (8, 1, 20, 4096), (8, 2, 20, 4096), (10, 4, 20, 16384), (16, 2, 16, 2048)]:
         enc = HashEncoding(num_levels=L, min_res=16, max_res=hi, log2_hashmap_size=log2T, features_per_level=F).to(dev)
         table = enc.hash_table.detach()
@@ -60,6 +60,15 @@ def main():
             def bwd():
                 ops.call("ps_hash_bwd", ops.ptr(x), P, None, ops.host_floats(sc), L, F, log2T, ops.ptr(dout),
                          ops.ptr(dtable), None, ops.stream())
+            def fwd_lm():
+                ops.call("ps_hash_fwd_lm", ops.ptr(x), P, ops.ptr(table), ops.host_floats(sc), L, F, log2T, ops.ptr(out),
+                         ops.stream())
+
+            def bwd_lm():
+                ops.call("ps_hash_bwd_lm", ops.ptr(x), P, None, ops.host_floats(sc), L, F, log2T, ops.ptr(dout),
+                         ops.ptr(dtable), None, ops.stream())
+            if os.environ.get("LM") == "1":
+                fwd, bwd = fwd_lm, bwd_lm
             tf, tb = time_it(fwd), time_it(bwd)
             bf, bb = synthetic.hash_bytes_fwd(L, F) * P, synthetic.hash_bytes_bwd(L, F) * P
             print(f"L{L} F{F} T2^{log2T} {name:18s} {P:8d} {tf:8.3f} {bf/tf/1e6:9.0f} {tb:8.3f} {bb/tb/1e6:9.0f} "
