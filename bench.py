@@ -147,7 +147,7 @@ def cpu_reference_step(omodel, emb, cfg, batch, n):
         loss = loss + 0.001 * losses.sky_loss(out["accumulation"].view(-1, 1), batch["sky"][:n])
     if cfg.use_semantics:
         loss = loss + 0.5 * losses.semantic_loss(out["semantics"], batch["features"][:n])
-    loss = loss + losses.interlevel_loss(out["weights_list"], [b[0] for b in out["bins_list"]])
+    loss = loss + O.interlevel_loss(out["weights_list"], [b[0] for b in out["bins_list"]])
     params = [f.grid.table for f in omodel.fields] + [p.grid.table for lvl in omodel.props for p in lvl]
     for p in params:
         p.grad = None

@@ -196,6 +196,17 @@ int ps_composite_bwd(const float* eu_bins, const float* density, const float* rg
                      const float* d_weights_in, const float* d_rgb_out, const float* d_acc, const float* d_depth_exp,
                      const float* d_sem_out, float* d_density, float* d_rgb, float* d_sem, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Loss stack: proposal / interlevel loss of mip-NeRF 360 as one kernel.
+ * Replaces outer + lossfun_outer + the per-level body of interlevel_loss (model_components/losses.py:48-126).
+ *   c [N,S+1], w [N,S]        final level's spacing-domain bin edges and weights (treated as constants)
+ *   t_env [N,Sp+1], w_env [N,Sp]  proposal level's bin edges and weights
+ *   loss_sum [1]  += sum over rays and samples of max(w - w_outer, 0)^2 / (w + 1e-7)   (caller-zeroed)
+ *   grad_w_env [N,Sp] (nullable) = d loss_sum / d w_env (written, not accumulated).  Sp <= 2048.
+ */
+int ps_interlevel_loss(const float* c, const float* w, const float* t_env, const float* w_env, int64_t N, int S,
+                       int Sp, float* loss_sum, float* grad_w_env, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,7 @@ __all__ = [
     "pdf_resample", "sample_positions", "get_weights", "render_rgb", "render_accumulation",
     "render_depth_expected", "render_depth_threshold", "proposal_sample", "model_outputs",
     "model_depth", "prior_query", "sky_outputs", "PRIME_Y", "PRIME_Z", "mlp_forward_bf16_emulated",
+    "loss_outer", "lossfun_outer", "interlevel_loss",
 ]
 
 PRIME_Y = 2654435761  # ENC:336
@@ -450,6 +451,39 @@ def sample_positions(origins: Tensor, dirs: Tensor, eu_bins: Tensor) -> Tuple[Te
     starts, ends = eu_bins[..., :-1, None], eu_bins[..., 1:, None]
     pos = origins[:, None, :] + dirs[:, None, :] * (starts + ends) / 2
     return pos, starts, ends, ends - starts
+
+
+# --------------------------------------------------------------------------------------
+# 8f-1  loss stack: proposal (interlevel) loss.  LS = model_components/losses.py
+# --------------------------------------------------------------------------------------
+LOSS_EPS = 1.0e-7   # LS:38 (torch.finfo-free constant EPS)
+
+
+def loss_outer(t0_starts: Tensor, t0_ends: Tensor, t1_starts: Tensor, t1_ends: Tensor, y1: Tensor) -> Tensor:
+    """Upper envelope of the step function (t1, y1) on the intervals t0.  Restates LS:47-77."""
+    cy1 = torch.cat([torch.zeros_like(y1[..., :1]), torch.cumsum(y1, dim=-1)], dim=-1)
+    idx_lo = torch.searchsorted(t1_starts.contiguous(), t0_starts.contiguous(), side="right") - 1
+    idx_lo = torch.clamp(idx_lo, min=0, max=y1.shape[-1] - 1)
+    idx_hi = torch.searchsorted(t1_ends.contiguous(), t0_ends.contiguous(), side="right")
+    idx_hi = torch.clamp(idx_hi, min=0, max=y1.shape[-1] - 1)
+    return torch.take_along_dim(cy1[..., 1:], idx_hi, dim=-1) - torch.take_along_dim(cy1[..., :-1], idx_lo, dim=-1)
+
+
+def lossfun_outer(t: Tensor, w: Tensor, t_env: Tensor, w_env: Tensor) -> Tensor:
+    """Restates LS:80-97."""
+    w_outer = loss_outer(t[..., :-1], t[..., 1:], t_env[..., :-1], t_env[..., 1:], w_env)
+    return torch.clip(w - w_outer, min=0) ** 2 / (w + LOSS_EPS)
+
+
+def interlevel_loss(weights_list: Sequence[Tensor], sp_bins_list: Sequence[Tensor]) -> Tensor:
+    """Proposal loss (LS:108-126): weights_list [N,S_k,1] per level, sp_bins_list [N,S_k+1] spacing-domain bin edges
+    (= ray_samples_to_sdist, LS:100-105); the last level is the detached target."""
+    c = sp_bins_list[-1].detach()
+    w = weights_list[-1][..., 0].detach()
+    loss = 0.0
+    for sdist, weights in zip(sp_bins_list[:-1], weights_list[:-1]):
+        loss = loss + torch.mean(lossfun_outer(c, w, sdist, weights[..., 0]))
+    return loss
 
 
 # --------------------------------------------------------------------------------------

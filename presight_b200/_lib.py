@@ -52,6 +52,7 @@ SIGNATURES = {
     "ps_depth_threshold": [_p, _p, _i64, _i, _f, _p, _p, _p],
     "ps_composite_fwd": [_p, _p, _p, _p, _i64, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p],
     "ps_composite_bwd": [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "ps_interlevel_loss": [_p, _p, _p, _p, _i64, _i, _i, _p, _p, _p],
 }
 _RESTYPES = {"ps_last_error": C.c_char_p, "ps_abi_version": C.c_int, "ps_launch_count": C.c_int64}
 

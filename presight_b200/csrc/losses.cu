@@ -1,0 +1,91 @@
+// Proposal ("interlevel") loss of mip-NeRF 360 as ONE kernel: loss and its gradient w.r.t. the proposal weights.
+// Reference: model_components/losses.py:48-126 (outer / lossfun_outer / interlevel_loss).  One warp per ray.
+//
+//   w_outer_i = cy[idx_hi_i + 1] - cy[idx_lo_i],   cy = [0, cumsum(w_env)]
+//   idx_lo_i  = clamp(searchsorted(t_env[:-1], c_i,   right) - 1, 0, Sp-1)
+//   idx_hi_i  = clamp(searchsorted(t_env[1:],  c_i+1, right),     0, Sp-1)
+//   loss_i    = max(w_i - w_outer_i, 0)^2 / (w_i + 1e-7)
+// d loss_i / d w_env[k] = g_i * ([k <= idx_hi_i] - [k < idx_lo_i]),  g_i = -2 max(w_i - w_outer_i, 0) / (w_i + 1e-7),
+// accumulated through two per-ray histograms (A over idx_hi, B over idx_lo) and suffix sums.
+#include "sampler.cuh"
+
+namespace ps {
+
+constexpr int kLossWarps = 4;
+
+__global__ void __launch_bounds__(kLossWarps * 32) interlevel_kernel(const float* __restrict__ c,
+                                                                     const float* __restrict__ w,
+                                                                     const float* __restrict__ t_env,
+                                                                     const float* __restrict__ w_env, int64_t N, int S,
+                                                                     int Sp, float* __restrict__ loss_sum,
+                                                                     float* __restrict__ grad_w_env) {
+    extern __shared__ float smem[];  // per warp: te[Sp+1] | cy[Sp+1] | A[Sp] | B[Sp]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * kLossWarps + warp;
+    if (n >= N) return;
+    float* te = smem + (size_t)warp * (4 * Sp + 2);
+    float* cy = te + Sp + 1;
+    float* A = cy + Sp + 1;
+    float* B = A + Sp;
+    for (int k = lane; k <= Sp; k += 32) te[k] = __ldg(t_env + n * (Sp + 1) + k);
+    for (int k = lane; k < Sp; k += 32) { A[k] = 0.f; B[k] = 0.f; }
+    // cy = [0, cumsum(w_env)] with fp64 accumulation (torch's CPU cumsum)
+    double carry = 0.0;
+    for (int base = 0; base < Sp; base += 32) {
+        const int k = base + lane;
+        const float v = k < Sp ? __ldg(w_env + n * Sp + k) : 0.f;
+        const double incl = warp_scan_incl((double)v, lane) + carry;
+        if (k < Sp) cy[k + 1] = (float)incl;
+        carry = __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) cy[0] = 0.f;
+    __syncwarp();
+    float loss = 0.f;
+    for (int i = lane; i < S; i += 32) {
+        const float t0s = __ldg(c + n * (S + 1) + i), t0e = __ldg(c + n * (S + 1) + i + 1);
+        const float wi = __ldg(w + n * S + i);
+        int lo = upper_bound(te, Sp, t0s) - 1;          // starts = te[0..Sp-1]
+        lo = min(max(lo, 0), Sp - 1);
+        int hi = upper_bound(te + 1, Sp, t0e);          // ends   = te[1..Sp]
+        hi = min(max(hi, 0), Sp - 1);
+        const float w_outer = cy[hi + 1] - cy[lo];
+        const float r = fmaxf(wi - w_outer, 0.f);
+        const float inv = 1.f / (wi + 1.0e-7f);
+        loss += r * r * inv;
+        if (grad_w_env && r > 0.f) {
+            const float g = -2.f * r * inv;
+            atomicAdd(A + hi, g);
+            atomicAdd(B + lo, g);
+        }
+    }
+    loss = warp_sum(loss);
+    if (lane == 0) atomicAdd(loss_sum, loss);
+    if (!grad_w_env) return;
+    __syncwarp();
+    // grad[k] = sum_{m >= k} A[m] - sum_{m > k} B[m]   (reverse scans, 32 entries at a time from the top)
+    float carryA = 0.f, carryB = 0.f;
+    for (int top = ((Sp + 31) / 32) * 32; top > 0; top -= 32) {
+        const int k = top - 1 - lane;                   // lane 0 handles the highest index of the chunk
+        const float a = k < Sp ? A[k] : 0.f, b = k < Sp ? B[k] : 0.f;
+        const float sa = warp_scan_incl(a, lane) + carryA;      // inclusive suffix sum of A at k
+        const float sb = warp_scan_incl(b, lane) + carryB;      // inclusive suffix sum of B at k
+        if (k < Sp && k >= 0) grad_w_env[n * Sp + k] = sa - (sb - b);
+        carryA = __shfl_sync(0xffffffffu, sa, 31);
+        carryB = __shfl_sync(0xffffffffu, sb, 31);
+    }
+}
+
+}  // namespace ps
+
+using namespace ps;
+
+extern "C" int ps_interlevel_loss(const float* c, const float* w, const float* t_env, const float* w_env, int64_t N,
+                                  int S, int Sp, float* loss_sum, float* grad_w_env, void* stream) {
+    if (N == 0) return 0;
+    PS_REQUIRE(c && w && t_env && w_env && loss_sum, "interlevel_loss: null pointer");
+    PS_REQUIRE(S >= 1 && Sp >= 1 && Sp <= 2048, "interlevel_loss: sample counts out of range");
+    const size_t smem = (size_t)kLossWarps * (4 * Sp + 2) * sizeof(float);
+    interlevel_kernel<<<(unsigned)cdiv(N, kLossWarps), kLossWarps * 32, smem, (cudaStream_t)stream>>>(
+        c, w, t_env, w_env, N, S, Sp, loss_sum, grad_w_env);
+    return check_launch("interlevel_loss");
+}

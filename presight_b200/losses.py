@@ -1,6 +1,8 @@
 """Loss terms that seed the backward pass of the hot path (reference: model_components/losses.py and
-model_components/PreSight/losses.py).  They consume `weights_list` / rendered outputs and stay in torch, as
-SURVEY §8(f)-1 scopes them ("next" row); only the terms needed to drive every gradient path are restated."""
+model_components/PreSight/losses.py).  They consume `weights_list` / rendered outputs (the "next" row); only the terms needed to drive
+every gradient path are restated.  On CUDA tensors the interlevel loss runs as one kernel per proposal level
+(`ps_interlevel_loss`); the torch expressions below are the host-side restatement used for CPU tensors (tests,
+the oracle leg of bench.py) and document the arithmetic."""
 from __future__ import annotations
 
 from typing import List
@@ -36,7 +38,12 @@ def interlevel_loss(weights_list: List[Tensor], sp_bins_list: List[Tensor]) -> T
     w = weights_list[-1][..., 0].detach()
     loss = 0.0
     for sdist, weights in zip(sp_bins_list[:-1], weights_list[:-1]):
-        loss = loss + torch.mean(lossfun_outer(c, w, sdist, weights[..., 0]))
+        if w.is_cuda:
+            # one kernel per proposal level: loss and d loss / d proposal weights (csrc/losses.cu)
+            from . import ops
+            loss = loss + ops.interlevel_loss_level(c, w, sdist, weights[..., 0])
+        else:
+            loss = loss + torch.mean(lossfun_outer(c, w, sdist, weights[..., 0]))
     return loss
 
 

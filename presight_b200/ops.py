@@ -400,5 +400,38 @@ def composite(eu_bins: Tensor, density: Tensor, rgb: Optional[Tensor], sem: Opti
     return _Composite.apply(eu_bins, density, rgb, sem, float(threshold))
 
 
+# --------------------------------------------------------------------------------------------------
+# loss stack: proposal (interlevel) loss
+# --------------------------------------------------------------------------------------------------
+class _InterlevelLoss(torch.autograd.Function):
+    """mean(lossfun_outer(c, w, t_env, w_env)) (model_components/losses.py:80-126) with the gradient w.r.t. the
+    proposal weights produced in the same kernel; c and w are constants (the reference detaches them)."""
+
+    @staticmethod
+    def forward(ctx, c, w, t_env, w_env):
+        c, w, t_env, we = _f32c(c.detach()), _f32c(w.detach()), _f32c(t_env.detach()), _f32c(w_env.detach())
+        N, S = w.shape
+        Sp = we.shape[1]
+        loss = torch.zeros(1, device=w.device, dtype=torch.float32)
+        need = ctx.needs_input_grad[3]
+        grad = torch.empty_like(we) if need else None
+        with _probe("interlevel_loss"):
+            call("ps_interlevel_loss", ptr(c), ptr(w), ptr(t_env), ptr(we), N, S, Sp, ptr(loss), ptr(grad), stream())
+        ctx.scale = 1.0 / float(N * S)
+        if need:
+            ctx.save_for_backward(grad)
+        return loss[0] * ctx.scale
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return None, None, None, grad * (g * ctx.scale)
+
+
+def interlevel_loss_level(c: Tensor, w: Tensor, t_env: Tensor, w_env: Tensor) -> Tensor:
+    """One proposal level's term of interlevel_loss: c [N,S+1], w [N,S], t_env [N,Sp+1], w_env [N,Sp] -> scalar."""
+    return _InterlevelLoss.apply(c, w, t_env, w_env)
+
+
 def launch_count() -> int:
     return _lib.launch_count()

@@ -402,3 +402,38 @@ def test_mlp_tcgen05_forward(ops, shape):
         finally:
             ops.TCGEN05_FWD = old
         assert_close(y_tc5, y_sync, 3e-3, f"tcgen05 vs mma.sync P={P}")
+
+
+# ------------------------------------------------------------------------------------------ loss stack (8f-1)
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_interlevel_loss_kernel_golden(ops, case):
+    """ps_interlevel_loss (loss + gradient in one kernel) vs the live reference's fixture."""
+    from presight_b200 import losses
+    fx = Fixture("losses.npz")
+    n = int(fx.np(f"{case}/n_levels"))
+    c, w = fx[f"{case}/c"].to(DEV), fx[f"{case}/w"].to(DEV)
+    ws = [fx[f"{case}/w{i}"].to(DEV).requires_grad_(True) for i in range(n)]
+    ts = [fx[f"{case}/t{i}"].to(DEV) for i in range(n)]
+    loss = losses.interlevel_loss([x[..., None] for x in ws] + [w[..., None]], ts + [c])
+    assert_close(loss.cpu(), fx[f"{case}/loss"], 1e-5, "interlevel loss")
+    (loss * 3.0).backward()
+    for i in range(n):
+        assert_close(ws[i].grad.cpu(), 3.0 * fx[f"{case}/g{i}"], TOL32, f"grad level {i}")
+
+
+def test_interlevel_loss_kernel_random(ops):
+    """large ragged shapes against the oracle (incl. S not a multiple of 32 and weights with exact zeros)."""
+    g = torch.Generator().manual_seed(11)
+    for (N, S, Sp) in [(1000, 64, 128), (513, 48, 256), (300, 33, 7)]:
+        c = torch.rand(N, S + 1, generator=g).sort(-1).values
+        t = torch.rand(N, Sp + 1, generator=g).sort(-1).values
+        w = torch.rand(N, S, generator=g) ** 3
+        w[torch.rand(N, S, generator=g) < 0.3] = 0
+        we = (torch.rand(N, Sp, generator=g) ** 3 * 0.05).requires_grad_(True)
+        want = O.lossfun_outer(c, w, t, we).mean()
+        want.backward()
+        wg = we.detach().to(DEV).requires_grad_(True)
+        got = ops.interlevel_loss_level(c.to(DEV), w.to(DEV), t.to(DEV), wg)
+        got.backward()
+        assert_close(got.cpu(), want, 1e-5, f"loss {N}x{S}x{Sp}")
+        assert_close(wg.grad.cpu(), we.grad, TOL32, f"grad {N}x{S}x{Sp}")
