@@ -207,6 +207,37 @@ int ps_composite_bwd(const float* eu_bins, const float* density, const float* rg
 int ps_interlevel_loss(const float* c, const float* w, const float* t_env, const float* w_env, int64_t N, int S,
                        int Sp, float* loss_sum, float* grad_w_env, void* stream);
 
+/* Self-test of the tcgen05 operand conventions used by the fused kernels (csrc/tc5.cuh): one CTA computes, from
+ * X [128,64], Y [128,64], W [64,64] (fp32, rounded to bf16 on chip), C1 = X W^T (K-major operands), C2 = X W
+ * (MN-major B: the input-gradient form) and C3 = 2 X^T Y (MN-major A and B, reduction over rows, accumulated over two
+ * calls: the weight-gradient form; rows 64..127 of C3 are padding).  All outputs [128,64] fp32. */
+int ps_tc5_probe(const float* X, const float* Y, const float* W, float* C1, float* C2, float* C3, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused field level on tcgen05 tensor cores (bf16 parity class).  One kernel evaluates, per 128-point tile,
+ * iNGPField.get_density/get_outputs/semantic head (fields/PreSight/ingp_field.py:163-267) and the compositing of
+ * nerfacto_nusc_ms.py:497-530 (weights, rgb, accumulation, expected / threshold depth, semantics); the backward
+ * kernel recomputes the forward on chip and produces the hash-feature gradient, the appearance gradient and all
+ * weight / bias gradients.  Only the architecture of the reference's field is supported: hidden width 64,
+ * geo_feat_dim 15, semantic width 64, 3-layer heads, appearance dim <= 16, L*F <= 48 with F in {2,4},
+ * samples per ray S in {32,64,96,128}.  Layer order in W/B/dW/dB: base0 [64,L*F], base1 [80,64], sem0..2 [64,64],
+ * rgb0 [64,31+A], rgb1 [64,64], rgb2 [3,64] (nn.Linear layout, fp32, device pointers).
+ */
+typedef struct {
+    const float* W[8];
+    const float* B[8];
+    float* dW[8]; /* backward only: accumulated into caller-zeroed buffers */
+    float* dB[8];
+    int app_dim;
+} ps_field_net;
+/* feat_lm: level-major hash features [L][P][F] (ps_hash_fwd_lm), sel [P] (nullable), eu_bins [N,S+1], dirs [N,3],
+ * app [N,A] -> weights [N,S], rgb_out [N,3], acc [N] (unclamped), depth_exp [N] (unclipped), depth_thr [N],
+ * sem_out [N,64], tminmax [2] (nullable; caller-initialised +inf/-inf). */
+int ps_field_level_fwd(const ps_field_net* net, const float* feat_lm, int L, int F, const uint8_t* sel,
+                       const float* eu_bins, const float* dirs, const float* app, int64_t N, int S, float threshold,
+                       float* weights, float* rgb_out, float* acc, float* depth_exp, float* depth_thr, float* sem_out,
+                       float* tminmax, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

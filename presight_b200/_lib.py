@@ -53,6 +53,8 @@ SIGNATURES = {
     "ps_composite_fwd": [_p, _p, _p, _p, _i64, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p],
     "ps_composite_bwd": [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "ps_interlevel_loss": [_p, _p, _p, _p, _i64, _i, _i, _p, _p, _p],
+    "ps_tc5_probe": [_p, _p, _p, _p, _p, _p, _p],
+    "ps_field_level_fwd": [_p, _p, _i, _i, _p, _p, _p, _p, _i64, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p],
 }
 _RESTYPES = {"ps_last_error": C.c_char_p, "ps_abi_version": C.c_int, "ps_launch_count": C.c_int64}
 
@@ -141,6 +143,24 @@ def host_segments(segs):
         arr[i].dst = None if dst is None else dst.data_ptr()
         arr[i].stride, arr[i].col0, arr[i].width, arr[i].group = int(stride), int(col0), int(width), int(group)
     return arr
+
+
+class FieldNet(C.Structure):
+    """ps_field_net of include/presight_b200.h."""
+    _fields_ = [("W", C.c_void_p * 8), ("B", C.c_void_p * 8), ("dW", C.c_void_p * 8), ("dB", C.c_void_p * 8),
+                ("app_dim", C.c_int)]
+
+
+def host_field_net(weights, biases, app_dim, dweights=None, dbiases=None):
+    """weights / biases: the 8 layers in the order base0, base1, sem0..2, rgb0..2 (CUDA fp32 tensors)."""
+    net = FieldNet()
+    for i in range(8):
+        net.W[i] = ptr(weights[i])
+        net.B[i] = ptr(biases[i])
+        net.dW[i] = None if dweights is None else ptr(dweights[i])
+        net.dB[i] = None if dbiases is None else ptr(dbiases[i])
+    net.app_dim = int(app_dim)
+    return net
 
 
 def host_ints(vals: Sequence[int]):

@@ -1,0 +1,169 @@
+// Shared definitions of the fused field-level kernels (field_tc5_fwd.cu / field_tc5_bwd.cu):
+// the PreSight field of fields/PreSight/ingp_field.py:118-161 with semantics, evaluated per 128-point tile on
+// tcgen05 tensor cores with one thread per point.
+//
+//   base  : feat[K0] -> 64 relu -> 80 = [raw density | geo 15 | semantic input 64]           (ingp_field.py:130-138)
+//   sem   : h[16:80] -> 64 relu -> 64 relu -> 64                                              (:142-151)
+//   rgb   : [sh16(dir) | geo 15 | app A<=16] -> 64 relu -> 64 relu -> 3 sigmoid               (:153-161)
+//
+// Column bookkeeping of the colour head: the kernel feeds [sh 16 | h[0:16] | app 16] (48 columns) and the staged
+// weight has a zero column where h[0] (the raw density) sits, so no shifted copy of h is ever made:
+//   staged column 0..15 = reference column 0..15 (sh), 16 = zero, 17..31 = reference 16..30 (geo),
+//   32..32+A-1 = reference 31..31+A-1 (appearance), rest zero.
+#pragma once
+#include "composite.cuh"
+#include "position.cuh"
+#include "tc5.cuh"
+
+namespace ps {
+namespace ftc5 {
+
+using namespace tc5;
+
+constexpr int kHid = 64;      // hidden width of all three networks
+constexpr int kBaseOut = 80;  // 1 + 15 + 64
+constexpr int kGeo = 15;
+constexpr int kSem = 64;      // semantic input and output width
+constexpr int kRgbIn = 48;    // staged colour-head input width
+constexpr int kRgbOut = 16;   // padded (3 real)
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+// layer indices into FieldNet::W / B / dW / dB
+enum { B0 = 0, B1 = 1, S0 = 2, S1 = 3, S2 = 4, R0 = 5, R1 = 6, R2 = 7, kLayers = 8 };
+
+struct FieldNet {
+    const float* W[kLayers];
+    const float* B[kLayers];
+    float* dW[kLayers];   // backward only (accumulated)
+    float* dB[kLayers];
+    int in_dim;           // L * F (real)
+    int app_dim;          // A <= 16
+};
+
+struct FieldArgs {
+    FieldNet net;
+    const float* feat;     // level-major hash features [L][P][F]
+    float* dfeat;          // backward: gradient, same layout (written)
+    int L, F;
+    const uint8_t* sel;    // [P]
+    const float* eu;       // [N, S+1] euclidean bin edges
+    const float* dirs;     // [N, 3]
+    const float* app;      // [N, A] (nullable when A == 0)
+    float* dapp;           // backward: [N, A] accumulated (nullable)
+    int64_t N;
+    int S;
+    float thr;
+    // forward outputs
+    float* weights;        // [N, S]
+    float* rgb_out;        // [N, 3]
+    float* acc;            // [N]
+    float* dexp;           // [N]
+    float* dthr;           // [N]
+    float* sem_out;        // [N, 64]
+    float* tminmax;        // [2]
+    // backward inputs (acc / dexp above are then inputs)
+    const float* d_w;      // [N, S] nullable
+    const float* d_rgb;    // [N, 3] nullable
+    const float* d_acc;    // [N] nullable
+    const float* d_dexp;   // [N] nullable
+    const float* d_sem;    // [N, 64] nullable
+};
+
+// shared-memory weight tiles (bf16 chunk-major, rows = out features)
+template <int K0>
+struct WLayout {
+    static constexpr uint32_t b0 = 0;
+    static constexpr uint32_t b1 = b0 + cm_bytes(kHid, K0);
+    static constexpr uint32_t s0 = b1 + cm_bytes(kBaseOut, kHid);
+    static constexpr uint32_t s1 = s0 + cm_bytes(kHid, kSem);
+    static constexpr uint32_t s2 = s1 + cm_bytes(kHid, kHid);
+    static constexpr uint32_t r0 = s2 + cm_bytes(kSem, kHid);
+    static constexpr uint32_t r1 = r0 + cm_bytes(kHid, kRgbIn);
+    static constexpr uint32_t r2 = r1 + cm_bytes(kHid, kHid);
+    static constexpr uint32_t bias = r2 + cm_bytes(kRgbOut, kHid);           // fp32 biases
+    // bias offsets (floats)
+    static constexpr int bb0 = 0, bb1 = 64, bs0 = 144, bs1 = 208, bs2 = 272, br0 = 336, br1 = 400, br2 = 464;
+    static constexpr int n_bias = 480;
+    static constexpr uint32_t end = bias + n_bias * 4;
+};
+
+template <int K0>
+__device__ __forceinline__ void load_all_weights(const FieldNet& net, unsigned char* wbase, int tid, int nthreads) {
+    using WL = WLayout<K0>;
+    __shared__ int kmap[kRgbIn];
+    if (tid < kRgbIn) {
+        int src = -1;
+        if (tid < 16) src = tid;
+        else if (tid >= 17 && tid < 32) src = tid - 1;
+        else if (tid >= 32 && tid - 32 < net.app_dim) src = tid - 1;
+        kmap[tid] = src;
+    }
+    __syncthreads();
+    load_weight_cm(net.W[B0], kHid, net.in_dim, kHid, K0, wbase + WL::b0, nullptr, tid, nthreads);
+    load_weight_cm(net.W[B1], kBaseOut, kHid, kBaseOut, kHid, wbase + WL::b1, nullptr, tid, nthreads);
+    load_weight_cm(net.W[S0], kHid, kSem, kHid, kSem, wbase + WL::s0, nullptr, tid, nthreads);
+    load_weight_cm(net.W[S1], kHid, kHid, kHid, kHid, wbase + WL::s1, nullptr, tid, nthreads);
+    load_weight_cm(net.W[S2], kSem, kHid, kSem, kHid, wbase + WL::s2, nullptr, tid, nthreads);
+    load_weight_cm(net.W[R0], kHid, 16 + kGeo + net.app_dim, kHid, kRgbIn, wbase + WL::r0, kmap, tid, nthreads);
+    load_weight_cm(net.W[R1], kHid, kHid, kHid, kHid, wbase + WL::r1, nullptr, tid, nthreads);
+    load_weight_cm(net.W[R2], 3, kHid, kRgbOut, kHid, wbase + WL::r2, nullptr, tid, nthreads);
+    float* bias = reinterpret_cast<float*>(wbase + WL::bias);
+    const int off[kLayers] = {WL::bb0, WL::bb1, WL::bs0, WL::bs1, WL::bs2, WL::br0, WL::br1, WL::br2};
+    const int nreal[kLayers] = {kHid, kBaseOut, kHid, kHid, kSem, kHid, kHid, 3};
+    const int npad[kLayers] = {kHid, kBaseOut, kHid, kHid, kSem, kHid, kHid, kRgbOut};
+    for (int l = 0; l < kLayers; ++l)
+        for (int i = tid; i < npad[l]; i += nthreads)
+            bias[off[l] + i] = (i < nreal[l] && net.B[l]) ? __ldg(net.B[l] + i) : 0.f;
+}
+
+// stage this row's hash features (level-major [L][P][F] fp32) as bf16 into the first K0 columns of `tile`
+template <int K0>
+__device__ __forceinline__ void stage_features(const FieldArgs& a, int64_t P, int64_t p, bool valid, unsigned char* tile,
+                                               int r) {
+    float v[K0];
+#pragma unroll
+    for (int c = 0; c < K0; ++c) v[c] = 0.f;
+    if (valid) {
+        if (a.F == 2) {
+#pragma unroll
+            for (int l = 0; l < K0 / 2; ++l)
+                if (l < a.L) {
+                    const float2 q = __ldg(reinterpret_cast<const float2*>(a.feat + ((int64_t)l * P + p) * 2));
+                    v[2 * l] = q.x;
+                    v[2 * l + 1] = q.y;
+                }
+        } else {  // F == 4
+#pragma unroll
+            for (int l = 0; l < K0 / 4; ++l)
+                if (l < a.L) {
+                    const float4 q = __ldg(reinterpret_cast<const float4*>(a.feat + ((int64_t)l * P + p) * 4));
+                    v[4 * l] = q.x; v[4 * l + 1] = q.y; v[4 * l + 2] = q.z; v[4 * l + 3] = q.w;
+                }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < K0; c += 8) store_chunk(tile, kRows, r, c, v + c);
+}
+
+// stage [sh16(direction) | appearance (zero padded to 16)] of this row's ray into the 32-column SHAPP tile
+__device__ __forceinline__ void stage_shapp(const FieldArgs& a, int64_t ray, bool valid, unsigned char* tile, int r) {
+    float v[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] = 0.f;
+    if (valid) {
+        float sh[16];
+        sh4_of_direction(__ldg(a.dirs + 3 * ray), __ldg(a.dirs + 3 * ray + 1), __ldg(a.dirs + 3 * ray + 2), sh);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = sh[c];
+        if (a.app)
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+                if (c < a.net.app_dim) v[16 + c] = __ldg(a.app + ray * a.net.app_dim + c);
+    }
+#pragma unroll
+    for (int c = 0; c < 32; c += 8) store_chunk(tile, kRows, r, c, v + c);
+}
+
+}  // namespace ftc5
+}  // namespace ps

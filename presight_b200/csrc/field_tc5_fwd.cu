@@ -1,0 +1,364 @@
+// Fused field level, forward: hash features -> base MLP -> density -> semantic head -> colour head -> compositing,
+// one kernel, nothing but the per-ray results and the weights written to HBM.
+// Reference: fields/PreSight/ingp_field.py:163-251, cameras/rays.py:128-150, model_components/renderers.py:70-117,
+// 286-314, 332-383, models/PreSight/nerfacto_nusc_ms.py:497-530.
+//
+// CTA = 256 threads = two independent groups of 128; a group owns one 128-point tile at a time (128 / S rays) with
+// one thread per point (row).  All eight layers run on tcgen05.mma (bf16 x bf16 -> fp32 in TMEM, M = 128); the
+// epilogues (bias, ReLU, bf16 re-pack into the next layer's A tile) are thread-per-row, so everything that is "per
+// sample" — density, weights, the dot products of compositing — is plain per-thread code.  While one group waits for
+// its MMA the other runs its epilogue; the weights (54 KB bf16) are staged once per CTA and shared by both groups.
+#include "field_tc5.cuh"
+
+namespace ps {
+namespace ftc5 {
+
+constexpr int kFwdThreads = 256;
+constexpr int kGroups = 2;
+
+template <int K0>
+struct FwdSmem {
+    using WL = WLayout<K0>;
+    // per group
+    static constexpr uint32_t h = 0;                                    // [128 x 80]
+    static constexpr uint32_t shapp = h + cm_bytes(kRows, kBaseOut);    // [128 x 32]
+    static constexpr uint32_t bufa = shapp + cm_bytes(kRows, 32);       // [128 x 64]  X0 / S1 / R1
+    static constexpr uint32_t bufb = bufa + cm_bytes(kRows, 64);        // [128 x 64]  H1 / S2 / R2
+    static constexpr uint32_t red = bufb + cm_bytes(kRows, 64);         // float [4 warps][72]
+    static constexpr uint32_t tails = red + 4 * 72 * 4;                 // double [4][2]
+    static constexpr uint32_t found = tails + 4 * 2 * 8;                // int [4]
+    static constexpr uint32_t group_bytes = ((found + 16 + 127) / 128) * 128;
+    static constexpr uint32_t groups = ((WL::end + 127) / 128) * 128;
+    static constexpr uint32_t bars = groups + kGroups * group_bytes;    // 2 mbarriers + tmem slot
+    static constexpr uint32_t total = bars + 32;
+};
+
+// epilogue of a hidden layer: accumulator row -> +bias, ReLU -> bf16 -> columns [0, 64) of `tile`
+__device__ __forceinline__ void hidden_epilogue64(uint32_t trow, const float* bias, unsigned char* tile, int r) {
+#pragma unroll
+    for (int c = 0; c < 64; c += 32) {
+        float v[32];
+        tmem_ld32_nowait(trow + c, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[c + i], 0.f);
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) store_chunk(tile, kRows, r, c + i, v + i);
+    }
+}
+
+// sum v[0..n) over the 32 lanes with a butterfly that halves the live values each step; afterwards lane l holds the
+// warp totals of channels  l * n / 32 + j  in v[j], j < n / 32  (n = 64 -> two channels per lane)
+template <int NV>
+__device__ __forceinline__ void warp_transpose_reduce(float (&v)[NV], int lane) {
+    static_assert(NV == 64 || NV == 32, "NV");
+#pragma unroll
+    for (int step = 0, half = NV / 2; step < 5; ++step, half >>= 1) {
+        const int bit = 16 >> step;
+        const bool upper = (lane & bit) != 0;
+#pragma unroll
+        for (int j = 0; j < NV / 2; ++j) {
+            if (j < half) {
+                // keep the half selected by this lane's bit, send the other half to the partner
+                const float keep = upper ? v[j + half] : v[j];
+                const float send = upper ? v[j] : v[j + half];
+                v[j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+            }
+        }
+    }
+}
+
+template <int K0>
+__global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) {
+    using WL = WLayout<K0>;
+    using SM = FwdSmem<K0>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, g = tid >> 7, t = tid & 127, warp = t >> 5, lane = tid & 31;
+    unsigned char* wbase = smem;
+    const float* bias = reinterpret_cast<const float*>(smem + WL::bias);
+    unsigned char* gs = smem + SM::groups + g * SM::group_bytes;
+    unsigned char* Ht = gs + SM::h;
+    unsigned char* SHAPPt = gs + SM::shapp;
+    unsigned char* BufA = gs + SM::bufa;
+    unsigned char* BufB = gs + SM::bufb;
+    float* red = reinterpret_cast<float*>(gs + SM::red);
+    double* tails = reinterpret_cast<double*>(gs + SM::tails);
+    int* foundw = reinterpret_cast<int*>(gs + SM::found);
+    uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(smem + SM::bars);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::bars + 16);
+
+    load_all_weights<K0>(a.net, wbase, tid, kFwdThreads);
+    if (tid < 32) tmem_alloc(tmem_slot, 256);
+    if (tid == 0) {
+        mbar_init(smem_u32(bar_ptr), 1);
+        mbar_init(smem_u32(bar_ptr + 1), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot + g * 128;                        // this group's 80-column accumulator
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t bar = smem_u32(bar_ptr + g);
+    const uint32_t wb = smem_u32(wbase);
+    const uint32_t aH = smem_u32(Ht), aSH = smem_u32(SHAPPt), aA = smem_u32(BufA), aB = smem_u32(BufB);
+    const int barid = 1 + g;
+    uint32_t phase = 0;
+
+    const int S = a.S;
+    const int rpt = kRows / S;                 // rays per tile (S is a multiple of 32, <= 128)
+    const int rows_used = rpt * S;
+    const int wpr = S / 32;                    // warps per ray
+    const int64_t P = a.N * S;
+    const int64_t ntiles = (a.N + rpt - 1) / rpt;
+    float tmin = INFINITY, tmax = -INFINITY;
+
+#define FT_SYNC_ISSUE(...)                 \
+    fence_async_smem();                    \
+    fence_before();                        \
+    bar_sync(barid, 128);                  \
+    if (t == 0) {                          \
+        fence_after();                     \
+        __VA_ARGS__;                       \
+        umma_commit(bar);                  \
+    }
+#define FT_WAIT()           \
+    mbar_wait(bar, phase);  \
+    phase ^= 1;             \
+    fence_after();
+
+    for (int64_t tile = (int64_t)blockIdx.x * kGroups + g; tile < ntiles; tile += (int64_t)gridDim.x * kGroups) {
+        const int q = t / S;                                   // ray within the tile
+        const int s = t - q * S;
+        const int64_t ray = tile * rpt + q;
+        const bool valid = t < rows_used && ray < a.N;
+        const int64_t p = ray * S + s;
+        // ---- stage inputs -----------------------------------------------------------------------------
+        stage_features<K0>(a, P, p, valid, BufA, t);
+        stage_shapp(a, ray, valid, SHAPPt, t);
+        float t0 = 0.f, t1 = 0.f, selv = 0.f;
+        if (valid) {
+            t0 = __ldg(a.eu + ray * (S + 1) + s);
+            t1 = __ldg(a.eu + ray * (S + 1) + s + 1);
+            selv = a.sel ? (float)a.sel[p] : 1.f;
+        }
+        // ---- base network ------------------------------------------------------------------------------
+        FT_SYNC_ISSUE(gemm_kk(tmem, aA, kRows, wb + WL::b0, kHid, kHid, K0, false))
+        FT_WAIT()
+        hidden_epilogue64(trow, bias + WL::bb0, BufB, t);
+        FT_SYNC_ISSUE(gemm_kk(tmem, aB, kRows, wb + WL::b1, kBaseOut, kBaseOut, kHid, false))
+        FT_WAIT()
+        float raw;
+        {
+            float v[32];
+            tmem_ld32_nowait(trow, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += bias[WL::bb1 + i];
+            raw = v[0];
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) store_chunk(Ht, kRows, t, i, v + i);
+            tmem_ld32_nowait(trow + 32, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += bias[WL::bb1 + 32 + i];
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) store_chunk(Ht, kRows, t, 32 + i, v + i);
+            float u[16];
+            tmem_ld16_nowait(trow + 64, u);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) u[i] += bias[WL::bb1 + 64 + i];
+            store_chunk(Ht, kRows, t, 64, u);
+            store_chunk(Ht, kRows, t, 72, u + 8);
+        }
+        // semantic head layer 0 reads h[16:80] = chunks 2..9 of the H tile
+        FT_SYNC_ISSUE(gemm_kk(tmem, aH + 2 * kRows * 16, kRows, wb + WL::s0, kHid, kHid, kSem, false))
+        // ---- weights of this ray (overlaps the MMA): rays.py:138-148 -------------------------------------
+        const float density = valid ? expf(raw) * selv : 0.f;
+        const float dd = __fmul_rn(__fsub_rn(t1, t0), density);
+        const double dd_incl = warp_scan_incl((double)dd, lane);
+        if (lane == 31) tails[warp * 2] = dd_incl;
+        bar_sync(barid, 128);
+        const int w_first = (warp / wpr) * wpr;                // first warp of this warp's ray
+        double carry = 0.0;
+        for (int k = w_first; k < warp; ++k) carry += tails[k * 2];
+        float w, T;
+        {
+            const double incl = dd_incl + carry;
+            const double prev = __shfl_up_sync(0xffffffffu, incl, 1);
+            const double excl = lane == 0 ? carry : prev;
+            T = expf(-(float)excl);
+            const float alpha = __fsub_rn(1.f, expf(-dd));
+            w = nan_to_num(__fmul_rn(alpha, T));
+            if (!valid) w = 0.f;
+        }
+        const float tm = __fdiv_rn(__fadd_rn(t0, t1), 2.f);
+        if (valid) {
+            a.weights[p] = w;
+            tmin = fminf(tmin, tm);
+            tmax = fmaxf(tmax, tm);
+        }
+        // threshold depth (renderers.py:352-362): first sample whose inclusive cumsum of weights reaches thr
+        const double w_incl = warp_scan_incl((double)w, lane);
+        if (lane == 31) tails[warp * 2 + 1] = w_incl;
+        const float acc_w = warp_sum(w), dnum_w = warp_sum(w * tm);
+        if (lane == 0) { red[warp * 72 + 64] = acc_w; red[warp * 72 + 65] = dnum_w; }
+        // ---- semantic head -------------------------------------------------------------------------------
+        FT_WAIT()
+        hidden_epilogue64(trow, bias + WL::bs0, BufA, t);
+        FT_SYNC_ISSUE(gemm_kk(tmem, aA, kRows, wb + WL::s1, kHid, kHid, kHid, false))
+        {   // (after the barrier inside FT_SYNC_ISSUE the weight tails of all warps are visible)
+            double wc = 0.0;
+            for (int k = w_first; k < warp; ++k) wc += tails[k * 2 + 1];
+            const unsigned hit = __ballot_sync(0xffffffffu, valid && (float)(w_incl + wc) >= a.thr);
+            if (lane == 0) foundw[warp] = hit ? (warp - w_first) * 32 + __ffs(hit) - 1 : 0x7fffffff;
+        }
+        FT_WAIT()
+        hidden_epilogue64(trow, bias + WL::bs1, BufB, t);
+        FT_SYNC_ISSUE(gemm_kk(tmem, aB, kRows, wb + WL::s2, kSem, kSem, kHid, false))
+        FT_WAIT()
+        {
+            float v[64];
+            tmem_ld32_nowait(trow, *reinterpret_cast<float(*)[32]>(v));
+            tmem_ld32_nowait(trow + 32, *reinterpret_cast<float(*)[32]>(v + 32));
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = w * (v[i] + bias[WL::bs2 + i]);
+            warp_transpose_reduce<64>(v, lane);
+            red[warp * 72 + 2 * lane] = v[0];
+            red[warp * 72 + 2 * lane + 1] = v[1];
+        }
+        // ---- colour head: [sh | h[0:16] | app] ------------------------------------------------------------
+        FT_SYNC_ISSUE(gemm_kk(tmem, aSH, kRows, wb + WL::r0, kHid, kHid, 16, false);
+                      gemm_kk(tmem, aH, kRows, wb + WL::r0 + 2 * kHid * 16, kHid, kHid, 16, true);
+                      gemm_kk(tmem, aSH + 2 * kRows * 16, kRows, wb + WL::r0 + 4 * kHid * 16, kHid, kHid, 16, true))
+        // per-ray semantics / accumulation / depths (the barrier above published red[] and foundw[])
+        for (int i = t; i < rpt * 64; i += 128) {
+            const int qq = i >> 6, c = i & 63;
+            const int64_t rr = tile * rpt + qq;
+            if (rr < a.N) {
+                float sum = 0.f;
+                for (int k = 0; k < wpr; ++k) sum += red[(qq * wpr + k) * 72 + c];
+                a.sem_out[rr * kSem + c] = sum;
+                if (c == 0) {
+                    float accv = 0.f, dn = 0.f;
+                    int fnd = 0x7fffffff;
+                    for (int k = 0; k < wpr; ++k) {
+                        accv += red[(qq * wpr + k) * 72 + 64];
+                        dn += red[(qq * wpr + k) * 72 + 65];
+                        fnd = min(fnd, foundw[qq * wpr + k]);
+                    }
+                    fnd = min(fnd, S - 1);
+                    a.acc[rr] = accv;
+                    a.dexp[rr] = dn / (accv + 1e-10f);
+                    const float* b = a.eu + rr * (S + 1);
+                    a.dthr[rr] = __fdiv_rn(__fadd_rn(__ldg(b + fnd), __ldg(b + fnd + 1)), 2.f);
+                }
+            }
+        }
+        FT_WAIT()
+        hidden_epilogue64(trow, bias + WL::br0, BufA, t);
+        FT_SYNC_ISSUE(gemm_kk(tmem, aA, kRows, wb + WL::r1, kHid, kHid, kHid, false))
+        FT_WAIT()
+        hidden_epilogue64(trow, bias + WL::br1, BufB, t);
+        FT_SYNC_ISSUE(gemm_kk(tmem, aB, kRows, wb + WL::r2, kRgbOut, kRgbOut, kHid, false))
+        FT_WAIT()
+        {
+            float u[16];
+            tmem_ld16_nowait(trow, u);
+            tmem_wait_ld();
+            float c3[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) c3[i] = warp_sum(w * sigmoid_f(u[i] + bias[WL::br2 + i]));
+            if (lane == 0) { red[warp * 72 + 66] = c3[0]; red[warp * 72 + 67] = c3[1]; red[warp * 72 + 68] = c3[2]; }
+        }
+        fence_before();
+        bar_sync(barid, 128);          // red[] complete; every thread is done with the accumulator and the tiles
+        if (t < rpt * 3) {
+            const int qq = t / 3, c = t - qq * 3;
+            const int64_t rr = tile * rpt + qq;
+            if (rr < a.N) {
+                float sum = 0.f;
+                for (int k = 0; k < wpr; ++k) sum += red[(qq * wpr + k) * 72 + 66 + c];
+                a.rgb_out[rr * 3 + c] = sum;
+            }
+        }
+        bar_sync(barid, 128);          // red[] consumed before the next tile overwrites it
+    }
+#undef FT_SYNC_ISSUE
+#undef FT_WAIT
+    if (a.tminmax) {
+        tmin = warp_min(tmin);
+        tmax = warp_max(tmax);
+        if (lane == 0 && tmin <= tmax) {
+            atomic_min_float(a.tminmax, tmin);
+            atomic_max_float(a.tminmax + 1, tmax);
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (tid < 32) tmem_dealloc(*tmem_slot, 256);
+}
+
+template <int K0>
+static int launch_field_fwd(const FieldArgs& a, cudaStream_t stream) {
+    constexpr size_t smem = FwdSmem<K0>::total;
+    static_assert(smem <= 227 * 1024, "field_fwd: shared memory");
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(field_fwd_kernel<K0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess) {
+            set_error("field_level_fwd: cannot reserve %zu bytes of shared memory", smem);
+            return 2;
+        }
+        configured = true;
+    }
+    const int rpt = kRows / a.S;
+    const int64_t ntiles = (a.N + rpt - 1) / rpt;
+    const int64_t pairs = (ntiles + kGroups - 1) / kGroups;
+    const int grid = (int)(pairs < kNumSMs ? pairs : kNumSMs);
+    field_fwd_kernel<K0><<<grid, kFwdThreads, smem, stream>>>(a);
+    return check_launch("field_level_fwd");
+}
+
+}  // namespace ftc5
+}  // namespace ps
+
+using namespace ps;
+using namespace ps::ftc5;
+
+int ps_field_check_common(const ps_field_net* net, int L, int F, int64_t N, int S, const char* what);
+
+extern "C" int ps_field_level_fwd(const ps_field_net* net, const float* feat_lm, int L, int F, const uint8_t* sel,
+                                  const float* eu_bins, const float* dirs, const float* app, int64_t N, int S,
+                                  float threshold, float* weights, float* rgb_out, float* acc, float* depth_exp,
+                                  float* depth_thr, float* sem_out, float* tminmax, void* stream) {
+    if (N == 0) return 0;
+    if (int e = ps_field_check_common(net, L, F, N, S, "field_level_fwd")) return e;
+    PS_REQUIRE(feat_lm && eu_bins && dirs && weights && rgb_out && acc && depth_exp && depth_thr && sem_out,
+               "field_level_fwd: null pointer");
+    PS_REQUIRE(net->app_dim == 0 || app != nullptr, "field_level_fwd: appearance is null");
+    FieldArgs a{};
+    for (int l = 0; l < kLayers; ++l) { a.net.W[l] = net->W[l]; a.net.B[l] = net->B[l]; }
+    a.net.in_dim = L * F;
+    a.net.app_dim = net->app_dim;
+    a.feat = feat_lm; a.L = L; a.F = F; a.sel = sel; a.eu = eu_bins; a.dirs = dirs; a.app = app; a.N = N; a.S = S;
+    a.thr = threshold;
+    a.weights = weights; a.rgb_out = rgb_out; a.acc = acc; a.dexp = depth_exp; a.dthr = depth_thr; a.sem_out = sem_out;
+    a.tminmax = tminmax;
+    if (L * F <= 32) return launch_field_fwd<32>(a, (cudaStream_t)stream);
+    return launch_field_fwd<48>(a, (cudaStream_t)stream);
+}
+
+int ps_field_check_common(const ps_field_net* net, int L, int F, int64_t N, int S, const char* what) {
+    PS_REQUIRE(net != nullptr, "%s: net is null", what);
+    PS_REQUIRE(F == 2 || F == 4, "%s: features_per_level %d not in {2,4}", what, F);
+    PS_REQUIRE(L >= 1 && L * F <= 48, "%s: L*F = %d exceeds 48", what, L * F);
+    PS_REQUIRE(S >= 32 && S <= 128 && S % 32 == 0, "%s: samples per ray %d must be 32, 64, 96 or 128", what, S);
+    PS_REQUIRE(N > 0 && N * (int64_t)S < (1ll << 31), "%s: too many points", what);
+    PS_REQUIRE(net->app_dim >= 0 && net->app_dim <= 16, "%s: appearance dim %d exceeds 16", what, net->app_dim);
+    for (int l = 0; l < kLayers; ++l) PS_REQUIRE(net->W[l] != nullptr, "%s: weight %d is null", what, l);
+    return 0;
+}

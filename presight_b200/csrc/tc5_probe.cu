@@ -1,0 +1,79 @@
+// Self-test of the tcgen05 operand conventions of tc5.cuh (K-major / MN-major descriptors over one chunk-major
+// tile, M = 128 padding rows, accumulation across GEMM calls).  Test-only entry point, one CTA.
+#include "tc5.cuh"
+
+namespace ps {
+namespace tc5 {
+
+// X [128 x 64], Y [128 x 64], W [64 x 64] fp32 -> C1 = X W^T, C2 = X W, C3 = 2 X^T Y  (all [.. x 64] fp32)
+__global__ void __launch_bounds__(128) tc5_probe_kernel(const float* __restrict__ X, const float* __restrict__ Y,
+                                                        const float* __restrict__ W, float* __restrict__ C1,
+                                                        float* __restrict__ C2, float* __restrict__ C3) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* Xs = smem;                       // 16 KB
+    unsigned char* Ys = Xs + cm_bytes(128, 64);     // 16 KB (also the "garbage" behind X for the M = 128 wgrad)
+    unsigned char* Ws = Ys + cm_bytes(128, 64);     // 8 KB
+    uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(Ws + cm_bytes(64, 64));
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar_ptr + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int c0 = 0; c0 < 64; c0 += 8) {
+        float v[8], u[8];
+        for (int i = 0; i < 8; ++i) { v[i] = X[tid * 64 + c0 + i]; u[i] = Y[tid * 64 + c0 + i]; }
+        store_chunk(Xs, 128, tid, c0, v);
+        store_chunk(Ys, 128, tid, c0, u);
+    }
+    load_weight_cm(W, 64, 64, 64, 64, Ws, nullptr, tid, 128);
+    const uint32_t bar = smem_u32(bar_ptr);
+    if (warp == 0) tmem_alloc(slot, 256);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *slot;
+    if (tid == 0) {
+        gemm_kk(tmem, smem_u32(Xs), 128, smem_u32(Ws), 64, 64, 64, false);
+        gemm_dgrad(tmem + 64, smem_u32(Xs), 128, smem_u32(Ws), 64, 64, 64, false);
+        gemm_wgrad(tmem + 128, smem_u32(Xs), smem_u32(Ys), 64, false);
+        gemm_wgrad(tmem + 128, smem_u32(Xs), smem_u32(Ys), 64, true);
+        umma_commit(bar);
+    }
+    mbar_wait(bar, 0);
+    fence_after();
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    float* outs[3] = {C1, C2, C3};
+    for (int m = 0; m < 3; ++m)
+        for (int c = 0; c < 64; c += 32) {
+            float v[32];
+            tmem_ld32_nowait(trow + 64 * m + c, v);
+            tmem_wait_ld();
+            for (int i = 0; i < 32; ++i) outs[m][tid * 64 + c + i] = v[i];
+        }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace tc5
+}  // namespace ps
+
+extern "C" int ps_tc5_probe(const float* X, const float* Y, const float* W, float* C1, float* C2, float* C3,
+                            void* stream) {
+    using namespace ps;
+    PS_REQUIRE(X && Y && W && C1 && C2 && C3, "tc5_probe: null pointer");
+    const size_t smem = tc5::cm_bytes(128, 64) * 2 + tc5::cm_bytes(64, 64) + 64;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(tc5::tc5_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess) {
+            set_error("tc5_probe: cannot reserve %zu bytes of shared memory", smem);
+            return 2;
+        }
+        configured = true;
+    }
+    tc5::tc5_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(X, Y, W, C1, C2, C3);
+    return check_launch("tc5_probe");
+}

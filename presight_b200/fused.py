@@ -260,6 +260,58 @@ class _FieldLevel(torch.autograd.Function):
                 *dWb, *dbb, *grads_sem, *dWr, *dbr)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# tcgen05 field level: base + semantic + colour networks and the compositing in ONE kernel per direction
+# (csrc/field_tc5_fwd.cu / field_tc5_bwd.cu).  bf16 parity class only.
+# ---------------------------------------------------------------------------------------------------------------
+def tc5_field_supported(grid: GridMeta, base: MlpMeta, sem: Optional[MlpMeta], rgb: MlpMeta, geo_dim: int, prec,
+                        S: int, A: int) -> bool:
+    """The fused kernels implement exactly the reference field's architecture (ingp_field.py:118-161)."""
+    return (prec == ops.PREC_BF16 and sem is not None and grid.F in (2, 4) and grid.L * grid.F <= 48
+            and S in (32, 64, 96, 128) and geo_dim == 15 and 0 <= A <= 16
+            and base.dims == (grid.L * grid.F, 64, 80) and sem.dims == (64, 64, 64, 64)
+            and rgb.dims == (16 + 15 + A, 64, 64, 3) and rgb.out_act == ops.ACT_SIGMOID
+            and base.out_act == ops.ACT_NONE and sem.out_act == ops.ACT_NONE)
+
+
+def _hash_fwd_lm(x01, table, g: GridMeta):
+    P = x01.shape[0]
+    out = torch.empty(P * g.L * g.F, device=x01.device, dtype=torch.float32)
+    with ops._probe(f"hash_fwd_L{g.L}F{g.F}T{g.log2_T}"):
+        call("ps_hash_fwd_lm", ptr(x01), P, ptr(table), host_floats(g.scalings), g.L, g.F, g.log2_T, ptr(out), stream())
+    return out
+
+
+def _hash_bwd_lm(x01, dfeat, table, g: GridMeta):
+    dtable = torch.zeros_like(table)
+    with ops._probe(f"hash_bwd_L{g.L}F{g.F}T{g.log2_T}"):
+        call("ps_hash_bwd_lm", ptr(x01), x01.shape[0], None, host_floats(g.scalings), g.L, g.F, g.log2_T, ptr(dfeat),
+             ptr(dtable), None, stream())
+    return dtable
+
+
+def tc5_field_forward(o, d, eu, app_c, table, aabb, contract, grid: GridMeta, ws, bs, A, threshold):
+    """-> (x01, sel, feat, w [N,S], rgb [N,3], acc [N,1], dexp [N,1], dthr [N,1], sem [N,64], tmm [2])."""
+    from ._lib import host_field_net
+    import ctypes as C
+    N, S = eu.shape[0], eu.shape[1] - 1
+    dev = eu.device
+    x01, sel = _ray_points(o, d, eu, aabb, contract)
+    feat = _hash_fwd_lm(x01, table, grid)
+    w = torch.empty(N, S, device=dev, dtype=torch.float32)
+    rgb_out = torch.empty(N, 3, device=dev, dtype=torch.float32)
+    acc = torch.empty(N, 1, device=dev, dtype=torch.float32)
+    dexp = torch.empty(N, 1, device=dev, dtype=torch.float32)
+    dthr = torch.empty(N, 1, device=dev, dtype=torch.float32)
+    sem_out = torch.empty(N, 64, device=dev, dtype=torch.float32)
+    tmm = torch.tensor([float("inf"), float("-inf")], device=dev, dtype=torch.float32)
+    net = host_field_net(ws, bs, A)
+    with ops._probe("field_level_fwd"):
+        call("ps_field_level_fwd", C.byref(net), ptr(feat), grid.L, grid.F, ptr(sel), ptr(eu), ptr(d), ptr(app_c), N, S,
+             float(threshold), ptr(w), ptr(rgb_out), ptr(acc), ptr(dexp), ptr(dthr), ptr(sem_out), ptr(tmm), stream())
+    return x01, sel, feat, w, rgb_out, acc, dexp, dthr, sem_out, tmm
+
+
 def field_level(origins, dirs, eu_bins, app, table, aabb, contract, grid: GridMeta, base: MlpMeta,
                 sem: Optional[MlpMeta], rgb: MlpMeta, geo_dim: int, prec, threshold, base_params, sem_params,
                 rgb_params):

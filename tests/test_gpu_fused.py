@@ -225,3 +225,59 @@ def test_fused_prior_query_matches_modular_and_oracle():
     # empty query
     m0, f0 = model.query_priors(torch.zeros(0, 3, device=DEV))
     assert m0.shape == (0,) and f0.shape == (0, 64)
+
+
+# ------------------------------------------------------------------------------------------ tcgen05 field level
+def _tc5_case(n, S, A=16, L=16, F=2, seed=0):
+    """Random field of the reference architecture + rays; returns everything both paths need."""
+    from presight_b200 import fused, ops
+    g = torch.Generator().manual_seed(seed)
+    log2T = 12
+    scal = O.hash_scalings(L, 16, 512).tolist()
+    table = ((torch.rand(L << log2T, F, generator=g) * 2 - 1) * 0.5).to(DEV)
+    dims = {"base": (L * F, 64, 80), "sem": (64, 64, 64, 64), "rgb": (31 + A, 64, 64, 3)}
+    nets = {}
+    for k, dd in dims.items():
+        ws = [(torch.randn(dd[i + 1], dd[i], generator=g) / dd[i] ** 0.5).to(DEV).requires_grad_(True) for i in range(len(dd) - 1)]
+        bs = [(torch.randn(dd[i + 1], generator=g) * 0.1).to(DEV).requires_grad_(True) for i in range(len(dd) - 1)]
+        nets[k] = (ws, bs)
+    o = ((torch.rand(n, 3, generator=g) - 0.5) * torch.tensor([1.0, 1.0, 0.1])).to(DEV)
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).to(DEV)
+    eu = (torch.rand(n, S + 1, generator=g) * 0.08 + 0.002).cumsum(-1).to(DEV)
+    app = torch.randn(n, A, generator=g).to(DEV).requires_grad_(True) if A else None
+    grid = fused.GridMeta(tuple(scal), log2T, F)
+    metas = (fused.MlpMeta(dims["base"], ops.ACT_NONE), fused.MlpMeta(dims["sem"], ops.ACT_NONE),
+             fused.MlpMeta(dims["rgb"], ops.ACT_SIGMOID))
+    aabb = [-1.0, -1.0, -0.5, 1.0, 1.0, 0.5]
+    return dict(o=o, d=d, eu=eu, app=app, table=table.requires_grad_(True), grid=grid, metas=metas, nets=nets,
+                aabb=aabb, A=A)
+
+
+@pytest.mark.parametrize("n,S,A,L,F", [(1000, 64, 16, 16, 2), (333, 32, 16, 10, 4), (130, 128, 7, 16, 2),
+                                       (65, 96, 0, 6, 2), (1, 64, 16, 16, 2)])
+def test_tc5_field_forward_matches_modular(n, S, A, L, F):
+    """ps_field_level_fwd (tcgen05, one kernel) vs the chain of stand-alone bf16 kernels on the same inputs."""
+    from presight_b200 import fused, ops
+    c = _tc5_case(n, S, A, L, F)
+    base, sem, rgb = c["metas"]
+    assert fused.tc5_field_supported(c["grid"], base, sem, rgb, 15, ops.PREC_BF16, S, A)
+    with torch.no_grad():
+        ws = [*c["nets"]["base"][0], *c["nets"]["sem"][0], *c["nets"]["rgb"][0]]
+        bs = [*c["nets"]["base"][1], *c["nets"]["sem"][1], *c["nets"]["rgb"][1]]
+        got = fused.tc5_field_forward(c["o"], c["d"], c["eu"], None if c["app"] is None else c["app"].detach(),
+                                      c["table"].detach(), c["aabb"], True, c["grid"], [w.detach() for w in ws],
+                                      [b.detach() for b in bs], A, 0.5)
+        _, _, _, w, rgb_o, acc, dexp, dthr, sem_o, tmm = got
+        want = fused._FieldLevel.apply(c["o"], c["d"], c["eu"], c["app"], c["table"], c["aabb"], True, c["grid"], base,
+                                       sem, rgb, 15, ops.PREC_BF16, 0.5, *c["nets"]["base"][0], *c["nets"]["base"][1],
+                                       *c["nets"]["sem"][0], *c["nets"]["sem"][1], *c["nets"]["rgb"][0],
+                                       *c["nets"]["rgb"][1])
+    ww, wrgb, wacc, wdexp, wdthr, wsem, wtmm = want
+    assert_close(w, ww[..., 0], 3e-3, "weights")
+    assert_close(rgb_o, wrgb, 3e-3, "rgb")
+    assert_close(acc, wacc, 3e-3, "accumulation")
+    assert_close(dexp, wdexp, 3e-3, "expected depth")
+    assert_close(sem_o, wsem, 3e-3, "semantics")
+    assert torch.equal(tmm, wtmm)
+    # the threshold depth is an index decision: identical unless the cumulative weight sits on the threshold
+    assert float((dthr != wdthr).float().mean()) < 0.02

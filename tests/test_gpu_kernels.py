@@ -437,3 +437,19 @@ def test_interlevel_loss_kernel_random(ops):
         got.backward()
         assert_close(got.cpu(), want, 1e-5, f"loss {N}x{S}x{Sp}")
         assert_close(wg.grad.cpu(), we.grad, TOL32, f"grad {N}x{S}x{Sp}")
+
+
+def test_tcgen05_operand_conventions(ops):
+    """K-major / MN-major UMMA descriptors over one chunk-major tile (csrc/tc5.cuh): forward, input-gradient and
+    weight-gradient GEMM forms against fp32 matmuls of the bf16-rounded operands."""
+    from presight_b200._lib import call, ptr, stream
+    g = torch.Generator().manual_seed(3)
+    X, Y, W = torch.randn(128, 64, generator=g), torch.randn(128, 64, generator=g), torch.randn(64, 64, generator=g)
+    Xd, Yd, Wd = X.to(DEV), Y.to(DEV), W.to(DEV)
+    C = [torch.zeros(128, 64, device=DEV) for _ in range(3)]
+    call("ps_tc5_probe", ptr(Xd), ptr(Yd), ptr(Wd), ptr(C[0]), ptr(C[1]), ptr(C[2]), stream())
+    torch.cuda.synchronize()
+    Xb, Yb, Wb = (t.bfloat16().float() for t in (X, Y, W))
+    assert_close(C[0].cpu(), Xb @ Wb.T, 1e-5, "X W^T (K-major)")
+    assert_close(C[1].cpu(), Xb @ Wb, 1e-5, "X W (MN-major B)")
+    assert_close(C[2].cpu()[:64], 2.0 * (Xb.T @ Yb), 1e-5, "2 X^T Y (MN-major A and B, accumulated)")
