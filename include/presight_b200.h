@@ -238,6 +238,15 @@ int ps_field_level_fwd(const ps_field_net* net, const float* feat_lm, int L, int
                        float* weights, float* rgb_out, float* acc, float* depth_exp, float* depth_thr, float* sem_out,
                        float* tminmax, void* stream);
 
+/* Backward of ps_field_level_fwd (recomputes the forward on chip).  acc / depth_exp: the forward's outputs (needed only
+ * with d_depth_exp).  Upstream gradients (each nullable): d_weights [N,S], d_rgb_out [N,3], d_acc [N], d_depth_exp [N],
+ * d_sem_out [N,64].  Outputs: dfeat_lm [L][P][F] written; dapp [N,A] (nullable) and net->dW / net->dB accumulated into
+ * caller-zeroed buffers. */
+int ps_field_level_bwd(const ps_field_net* net, const float* feat_lm, int L, int F, const uint8_t* sel,
+                       const float* eu_bins, const float* dirs, const float* app, int64_t N, int S, const float* acc,
+                       const float* depth_exp, const float* d_weights, const float* d_rgb_out, const float* d_acc,
+                       const float* d_depth_exp, const float* d_sem_out, float* dfeat_lm, float* dapp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

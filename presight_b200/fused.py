@@ -13,6 +13,7 @@ written straight into the matching windows of one `dh` buffer (the appearance gr
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -23,6 +24,8 @@ from . import ops
 from ._lib import call, host_floats, host_ints, host_ptrs, host_segments, ptr, stream
 
 _f32c = ops._f32c
+# PS_TC5_FIELD=0 keeps the final level on the chain of stand-alone kernels (hash / 3 MLPs / compositing)
+USE_TC5_FIELD = os.environ.get("PS_TC5_FIELD", "1") == "1"
 
 
 @dataclass(frozen=True)
@@ -312,11 +315,63 @@ def tc5_field_forward(o, d, eu, app_c, table, aabb, contract, grid: GridMeta, ws
     return x01, sel, feat, w, rgb_out, acc, dexp, dthr, sem_out, tmm
 
 
+class _FieldLevelTc5(torch.autograd.Function):
+    """Final level on the fused tcgen05 kernels: ray_points -> hash gather -> ONE field+compositing kernel; backward =
+    ONE kernel (recompute + all gradients) -> hash scatter.  Saved for backward: bins, unit-cube points, selector and
+    the hash features only."""
+
+    @staticmethod
+    def forward(ctx, origins, dirs, eu_bins, app, table, aabb, contract, grid: GridMeta, threshold, *params):
+        o, d, eu = _f32c(origins.detach()), _f32c(dirs.detach()), _f32c(eu_bins.detach())
+        N, S = eu.shape[0], eu.shape[1] - 1
+        ws = [p.detach() for p in params[:8]]
+        bs = [p.detach() for p in params[8:]]
+        A = 0 if app is None else app.shape[1]
+        app_c = None if app is None else _f32c(app.detach())
+        x01, sel, feat, w, rgb_out, acc, dexp, dthr, sem_out, tmm = tc5_field_forward(
+            o, d, eu, app_c, table.detach(), aabb, contract, grid, ws, bs, A, threshold)
+        saved = [eu, d, x01, sel, feat, acc, dexp, table]
+        if app_c is not None:
+            saved.append(app_c)
+        ctx.save_for_backward(*saved, *params)
+        ctx.meta = (grid, N, S, A, len(saved), app is not None and app.requires_grad)
+        ctx.mark_non_differentiable(dthr, tmm)
+        return w.view(N, S, 1), rgb_out, acc, dexp, dthr, sem_out, tmm
+
+    @staticmethod
+    def backward(ctx, dw, drgb, dacc, ddexp, _dthr, dsem, _dtmm):
+        import ctypes as C
+        from ._lib import host_field_net
+        grid, N, S, A, n_saved, app_grad = ctx.meta
+        saved = list(ctx.saved_tensors)
+        params = saved[n_saved:]
+        eu, d, x01, sel, feat, acc, dexp, table = saved[:8]
+        app_c = saved[8] if A else None
+        ws = [p.detach() for p in params[:8]]
+        bs = [p.detach() for p in params[8:]]
+        dW = [torch.zeros_like(w) for w in ws]
+        dB = [torch.zeros_like(b) for b in bs]
+        dfeat = torch.empty_like(feat)
+        dapp = torch.zeros(N, A, device=eu.device, dtype=torch.float32) if (A and app_grad) else None
+        net = host_field_net(ws, bs, A, dW, dB)
+        with ops._probe("field_level_bwd"):
+            call("ps_field_level_bwd", C.byref(net), ptr(feat), grid.L, grid.F, ptr(sel), ptr(eu), ptr(d), ptr(app_c), N,
+                 S, ptr(acc), ptr(dexp), ptr(_f32c(dw).view(N, S)), ptr(_f32c(drgb)), ptr(_f32c(dacc)),
+                 ptr(_f32c(ddexp)), ptr(_f32c(dsem)), ptr(dfeat), ptr(dapp), stream())
+        dtable = _hash_bwd_lm(x01, dfeat, table, grid)
+        return (None, None, None, dapp, dtable, None, None, None, None, *dW, *dB)
+
+
 def field_level(origins, dirs, eu_bins, app, table, aabb, contract, grid: GridMeta, base: MlpMeta,
                 sem: Optional[MlpMeta], rgb: MlpMeta, geo_dim: int, prec, threshold, base_params, sem_params,
                 rgb_params):
     """-> (weights [N,S,1], rgb [N,3], acc [N,1], depth_expected_unclipped [N,1], depth_threshold [N,1],
     semantics [N,C], tminmax [2]).  *_params = (weights list, biases list)."""
+    A = 0 if app is None else app.shape[1]
+    if USE_TC5_FIELD and tc5_field_supported(grid, base, sem, rgb, geo_dim, prec, eu_bins.shape[1] - 1, A):
+        ws = [*base_params[0], *sem_params[0], *rgb_params[0]]
+        bs = [*base_params[1], *sem_params[1], *rgb_params[1]]
+        return _FieldLevelTc5.apply(origins, dirs, eu_bins, app, table, aabb, contract, grid, threshold, *ws, *bs)
     flat = [*base_params[0], *base_params[1]]
     if sem is not None:
         flat += [*sem_params[0], *sem_params[1]]

@@ -281,3 +281,38 @@ def test_tc5_field_forward_matches_modular(n, S, A, L, F):
     assert torch.equal(tmm, wtmm)
     # the threshold depth is an index decision: identical unless the cumulative weight sits on the threshold
     assert float((dthr != wdthr).float().mean()) < 0.02
+
+
+@pytest.mark.parametrize("n,S,A,L,F", [(700, 64, 16, 16, 2), (333, 32, 16, 10, 4), (130, 128, 7, 16, 2),
+                                       (65, 96, 0, 6, 2), (20000, 64, 16, 16, 2)])
+def test_tc5_field_backward_matches_modular(n, S, A, L, F):
+    """ps_field_level_bwd (one tcgen05 kernel: recompute + dgrad + wgrad + compositing backward) vs the chain of
+    stand-alone bf16 kernels: same loss, same inputs, every gradient."""
+    from presight_b200 import fused, ops
+    c = _tc5_case(n, S, A, L, F, seed=1)
+    base, sem, rgb = c["metas"]
+    g = torch.Generator().manual_seed(7)
+    tgt = {k: v.to(DEV) for k, v in dict(rgb=torch.rand(n, 3, generator=g), sem=torch.rand(n, 64, generator=g),
+                                         gw=torch.randn(n, S, 1, generator=g) * 0.05).items()}
+    ws = [*c["nets"]["base"][0], *c["nets"]["sem"][0], *c["nets"]["rgb"][0]]
+    bs = [*c["nets"]["base"][1], *c["nets"]["sem"][1], *c["nets"]["rgb"][1]]
+    leaves = [c["table"], *ws, *bs] + ([c["app"]] if A else [])
+
+    def loss_of(out):
+        w, rgb_o, acc, dexp, _, sem_o, _ = out
+        return ((rgb_o - tgt["rgb"]) ** 2).mean() + 0.5 * ((sem_o - tgt["sem"]) ** 2).mean() + 0.1 * dexp.mean() \
+            + 0.01 * acc.mean() + (w * tgt["gw"]).sum() / n
+
+    out_t = fused._FieldLevelTc5.apply(c["o"], c["d"], c["eu"], c["app"], c["table"], c["aabb"], True, c["grid"], 0.5,
+                                       *ws, *bs)
+    g_t = torch.autograd.grad(loss_of(out_t), leaves)
+    out_m = fused._FieldLevel.apply(c["o"], c["d"], c["eu"], c["app"], c["table"], c["aabb"], True, c["grid"], base, sem,
+                                    rgb, 15, ops.PREC_BF16, 0.5, *c["nets"]["base"][0], *c["nets"]["base"][1],
+                                    *c["nets"]["sem"][0], *c["nets"]["sem"][1], *c["nets"]["rgb"][0],
+                                    *c["nets"]["rgb"][1])
+    g_m = torch.autograd.grad(loss_of(out_m), leaves)
+    names = ["table"] + [f"W{i}" for i in range(8)] + [f"b{i}" for i in range(8)] + (["app"] if A else [])
+    for name, a, b in zip(names, g_t, g_m):
+        assert torch.isfinite(a).all(), name
+        e = rel_l2(a, b)
+        assert e < 2e-2, f"{name}: rel-L2 {e:.3e}"
