@@ -247,6 +247,37 @@ int ps_field_level_bwd(const ps_field_net* net, const float* feat_lm, int L, int
                        const float* depth_exp, const float* d_weights, const float* d_rgb_out, const float* d_acc,
                        const float* d_depth_exp, const float* d_sem_out, float* dfeat_lm, float* dapp, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Fused proposal level (bf16 parity class).  One forward kernel replaces, per proposal level of
+ * ProposalNetworkSampler.generate_ray_samples (model_components/ray_samplers.py:600-609),
+ * Frustums.get_positions + PropNetDensityField.density_fn (fields/PreSight/prop_density_field.py:129-153: contraction,
+ * selector, hash encoding, 2-layer MLP, trunc_exp) + RaySamples.get_weights (cameras/rays.py:128-150); one backward
+ * kernel produces the hash-table and MLP gradients from d_weights.  Supported: 2-layer MLP with hidden width 16 or 64,
+ * L*F <= 16 with F in {1,2}, S in {32,64,96,128}.
+ */
+typedef struct {
+    const float* W0; /* [hidden, L*F] */
+    const float* b0; /* [hidden] */
+    const float* W1; /* [1, hidden] */
+    const float* b1; /* [1] */
+    float* dW0;      /* backward only: accumulated into caller-zeroed buffers */
+    float* db0;
+    float* dW1;
+    float* db1;
+    int hidden;
+} ps_prop_net;
+/* row stride (in bf16 elements) of the feature buffer exchanged between the two kernels: 8 or 16 */
+int ps_prop_level_feat_stride(int L, int F);
+/* origins/dirs [N,3], eu_bins [N,S+1], aabb_host[6], table [L*T,F] -> weights [N,S]; feat_bf16 (nullable)
+ * [N*S, stride] bf16 hash features saved for the backward. */
+int ps_prop_level_fwd(const ps_prop_net* net, const float* origins, const float* dirs, const float* eu_bins, int64_t N,
+                      int S, const float* aabb_host, int contract, const float* table, const float* scalings_host,
+                      int L, int F, int log2_T, float* weights, void* feat_bf16, void* stream);
+/* d_weights [N,S] -> dtable [L*T,F] and net->dW0/db0/dW1/db1, all accumulated. */
+int ps_prop_level_bwd(const ps_prop_net* net, const float* origins, const float* dirs, const float* eu_bins, int64_t N,
+                      int S, const float* aabb_host, int contract, const float* scalings_host, int L, int F, int log2_T,
+                      const void* feat_bf16, const float* d_weights, float* dtable, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,9 @@ SIGNATURES = {
     "ps_tc5_probe": [_p, _p, _p, _p, _p, _p, _p],
     "ps_field_level_fwd": [_p, _p, _i, _i, _p, _p, _p, _p, _i64, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p],
     "ps_field_level_bwd": [_p, _p, _i, _i, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "ps_prop_level_feat_stride": [_i, _i],
+    "ps_prop_level_fwd": [_p, _p, _p, _p, _i64, _i, _fp, _i, _p, _fp, _i, _i, _i, _p, _p, _p],
+    "ps_prop_level_bwd": [_p, _p, _p, _p, _i64, _i, _fp, _i, _fp, _i, _i, _i, _p, _p, _p, _p],
 }
 _RESTYPES = {"ps_last_error": C.c_char_p, "ps_abi_version": C.c_int, "ps_launch_count": C.c_int64}
 
@@ -161,6 +164,21 @@ def host_field_net(weights, biases, app_dim, dweights=None, dbiases=None):
         net.dW[i] = None if dweights is None else ptr(dweights[i])
         net.dB[i] = None if dbiases is None else ptr(dbiases[i])
     net.app_dim = int(app_dim)
+    return net
+
+
+class PropNet(C.Structure):
+    """ps_prop_net of include/presight_b200.h."""
+    _fields_ = [("W0", C.c_void_p), ("b0", C.c_void_p), ("W1", C.c_void_p), ("b1", C.c_void_p), ("dW0", C.c_void_p),
+                ("db0", C.c_void_p), ("dW1", C.c_void_p), ("db1", C.c_void_p), ("hidden", C.c_int)]
+
+
+def host_prop_net(ws, bs, dws=None, dbs=None):
+    net = PropNet()
+    net.W0, net.b0, net.W1, net.b1 = ptr(ws[0]), ptr(bs[0]), ptr(ws[1]), ptr(bs[1])
+    if dws is not None:
+        net.dW0, net.db0, net.dW1, net.db1 = ptr(dws[0]), ptr(dbs[0]), ptr(dws[1]), ptr(dbs[1])
+    net.hidden = int(ws[0].shape[0])
     return net
 
 

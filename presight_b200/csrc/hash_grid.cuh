@@ -136,4 +136,93 @@ __device__ __forceinline__ void scatter_row(float* __restrict__ level_grad, uint
     }
 }
 
+// scatter the (already weighted) gradient of the two x-corners of one (y,z) pair; `live_*` is false when the
+// corner's interpolation weight was exactly zero for every contributing sample (ceil == floor), in which case the
+// atomic is skipped
+template <int F>
+__device__ __forceinline__ void scatter_xpair(float* __restrict__ lg, uint32_t r_hi, uint32_t r_lo,
+                                              const float (&v_hi)[F], const float (&v_lo)[F], bool live_hi,
+                                              bool live_lo) {
+    if constexpr (F <= 2) {
+        if ((r_hi ^ r_lo) == 1u && live_hi && live_lo) {
+            // rows r and r^1: one aligned slot of 2F floats
+            const uint32_t base = r_hi & ~1u;
+            const bool hi_first = !(r_hi & 1u);
+            if constexpr (F == 1)
+                red_add_v2(lg + base, hi_first ? v_hi[0] : v_lo[0], hi_first ? v_lo[0] : v_hi[0]);
+            else
+                red_add_v4(lg + (size_t)base * 2, hi_first ? v_hi[0] : v_lo[0], hi_first ? v_hi[1] : v_lo[1],
+                           hi_first ? v_lo[0] : v_hi[0], hi_first ? v_lo[1] : v_hi[1]);
+            return;
+        }
+    }
+    if (live_hi) scatter_row<F>(lg, r_hi, v_hi, 1.f);
+    if (live_lo) scatter_row<F>(lg, r_lo, v_lo, 1.f);
+}
+
+// Segmented warp reduction: lanes of one segment (consecutive lanes, first lane flagged in `heads`) are summed
+// into the segment's head lane.
+__device__ __forceinline__ float seg_reduce(float v, uint32_t heads, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float other = __shfl_down_sync(0xffffffffu, v, o);
+        // add lane+o only if no segment starts in (lane, lane+o]
+        const bool same = (lane + o < 32) && ((((heads >> lane) >> 1) & ((1u << o) - 1u)) == 0u);
+        if (same) v += other;
+    }
+    return v;
+}
+
+
+// Scatter-add one level's feature gradient `g[F]` of this lane's point into the level's gradient table `lg`
+// (all 32 lanes must call; `valid` = this lane carries a real point).
+//  * warp pre-aggregation: consecutive samples of a ray that fall into the same grid cell hit the same 8 rows; they are
+//    summed inside the warp and the first lane of each run issues the atomics.  The cell is identified by its floor
+//    coordinates plus the three "exact integer" flags (ceil = floor + !exact);
+//  * x-pair merge (see scatter_xpair).
+template <int F>
+__device__ __forceinline__ void scatter_level_preagg(float* __restrict__ lg, const Corner8& c, float px, float py,
+                                                     float pz, float scale, const float (&g)[F], bool valid, int lane) {
+    float w[8];
+    corner_weights(c.ox, c.oy, c.oz, w);
+    // weighted per-corner gradients and "weight was non-zero" flags
+    float v[8][F];
+    uint32_t live = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (w[k] != 0.f && valid) live |= 1u << k;
+#pragma unroll
+        for (int f = 0; f < F; ++f) v[k][f] = valid ? g[f] * w[k] : 0.f;
+    }
+    const int kx = (int)floorf(__fmul_rn(px, scale)), ky = (int)floorf(__fmul_rn(py, scale)),
+              kz = (int)floorf(__fmul_rn(pz, scale));
+    const int kf = (c.ox == 0.f ? 1 : 0) | (c.oy == 0.f ? 2 : 0) | (c.oz == 0.f ? 4 : 0) | (valid ? 0 : 8);
+    // (shuffles executed unconditionally by all 32 lanes, compared afterwards)
+    const int nx = __shfl_up_sync(0xffffffffu, kx, 1), ny = __shfl_up_sync(0xffffffffu, ky, 1),
+              nz = __shfl_up_sync(0xffffffffu, kz, 1), nf = __shfl_up_sync(0xffffffffu, kf, 1);
+    const bool same_prev = lane > 0 && nx == kx && ny == ky && nz == kz && nf == kf;
+    const uint32_t heads = __ballot_sync(0xffffffffu, !same_prev);
+    bool issue = valid;
+    if (heads != 0xffffffffu) {   // warp-uniform: at least one run of length > 1
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int f = 0; f < F; ++f) v[k][f] = seg_reduce(v[k][f], heads, lane);
+        // a corner is live for the run if it was live for any member
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t other = __shfl_down_sync(0xffffffffu, live, o);
+            if ((lane + o < 32) && ((((heads >> lane) >> 1) & ((1u << o) - 1u)) == 0u)) live |= other;
+        }
+        issue = valid && !same_prev;
+    }
+    if (issue) {
+        // (y,z) corner pairs in reference order: {x-ceil, x-floor} = {h0,h3}, {h1,h2}, {h4,h7}, {h5,h6}
+        scatter_xpair<F>(lg, c.row[0], c.row[3], v[0], v[3], live & 1u, live & 8u);
+        scatter_xpair<F>(lg, c.row[1], c.row[2], v[1], v[2], live & 2u, live & 4u);
+        scatter_xpair<F>(lg, c.row[4], c.row[7], v[4], v[7], live & 16u, live & 128u);
+        scatter_xpair<F>(lg, c.row[5], c.row[6], v[5], v[6], live & 32u, live & 64u);
+    }
+}
+
 }  // namespace ps

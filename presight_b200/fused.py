@@ -26,6 +26,7 @@ from ._lib import call, host_floats, host_ints, host_ptrs, host_segments, ptr, s
 _f32c = ops._f32c
 # PS_TC5_FIELD=0 keeps the final level on the chain of stand-alone kernels (hash / 3 MLPs / compositing)
 USE_TC5_FIELD = os.environ.get("PS_TC5_FIELD", "1") == "1"
+USE_TC5_PROP = os.environ.get("PS_TC5_PROP", "1") == "1"
 
 
 @dataclass(frozen=True)
@@ -149,8 +150,56 @@ class _PropLevel(torch.autograd.Function):
         return (None, None, None, dtable, None, None, None, None, None, *dW, *db)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# tcgen05 proposal level: positions + hash gather + MLP + weights in ONE kernel per direction (csrc/prop_tc5.cu)
+# ---------------------------------------------------------------------------------------------------------------
+def tc5_prop_supported(grid: GridMeta, net: MlpMeta, prec, S: int) -> bool:
+    return (prec == ops.PREC_BF16 and grid.F in (1, 2) and grid.L * grid.F <= 16 and S in (32, 64, 96, 128)
+            and net.n_layers == 2 and net.dims[1] in (16, 64) and net.dims[2] == 1 and net.out_act == ops.ACT_NONE)
+
+
+class _PropLevelTc5(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, origins, dirs, eu_bins, table, aabb, contract, grid: GridMeta, w0, b0, w1, b1):
+        import ctypes as C
+        from ._lib import host_prop_net, load
+        o, d, eu = _f32c(origins.detach()), _f32c(dirs.detach()), _f32c(eu_bins.detach())
+        N, S = eu.shape[0], eu.shape[1] - 1
+        need_grad = any(ctx.needs_input_grad)
+        stride = int(load().ps_prop_level_feat_stride(grid.L, grid.F))
+        feat = torch.empty(N * S, stride, device=eu.device, dtype=torch.bfloat16) if need_grad else None
+        w = torch.empty(N, S, device=eu.device, dtype=torch.float32)
+        net = host_prop_net([w0.detach(), w1.detach()], [b0.detach(), b1.detach()])
+        with ops._probe(f"prop_level_fwd_S{S}"):
+            call("ps_prop_level_fwd", C.byref(net), ptr(o), ptr(d), ptr(eu), N, S, host_floats(aabb), 1 if contract else 0,
+                 ptr(table.detach()), host_floats(grid.scalings), grid.L, grid.F, grid.log2_T, ptr(w), ptr(feat), stream())
+        if need_grad:
+            ctx.save_for_backward(o, d, eu, feat, table, w0, b0, w1, b1)
+        ctx.meta = (grid, tuple(aabb), contract, N, S)
+        return w.view(N, S, 1)
+
+    @staticmethod
+    def backward(ctx, dw):
+        import ctypes as C
+        from ._lib import host_prop_net
+        grid, aabb, contract, N, S = ctx.meta
+        o, d, eu, feat, table, w0, b0, w1, b1 = ctx.saved_tensors
+        ws, bs = [w0.detach(), w1.detach()], [b0.detach(), b1.detach()]
+        dws, dbs = [torch.zeros_like(t) for t in ws], [torch.zeros_like(t) for t in bs]
+        dtable = torch.zeros_like(table)
+        net = host_prop_net(ws, bs, dws, dbs)
+        with ops._probe(f"prop_level_bwd_S{S}"):
+            call("ps_prop_level_bwd", C.byref(net), ptr(o), ptr(d), ptr(eu), N, S, host_floats(aabb), 1 if contract else 0,
+                 host_floats(grid.scalings), grid.L, grid.F, grid.log2_T, ptr(feat), ptr(_f32c(dw).view(N, S)),
+                 ptr(dtable), stream())
+        return (None, None, None, dtable, None, None, None, dws[0], dbs[0], dws[1], dbs[1])
+
+
 def prop_level_weights(origins, dirs, eu_bins, table, aabb, contract, grid: GridMeta, net: MlpMeta, prec,
                        weights: Sequence[Tensor], biases: Sequence[Tensor]) -> Tensor:
+    if USE_TC5_PROP and tc5_prop_supported(grid, net, prec, eu_bins.shape[1] - 1) and all(b is not None for b in biases):
+        return _PropLevelTc5.apply(origins, dirs, eu_bins, table, aabb, contract, grid, weights[0], biases[0], weights[1],
+                                   biases[1])
     return _PropLevel.apply(origins, dirs, eu_bins, table, aabb, contract, grid, net, prec, *weights, *biases)
 
 

@@ -316,3 +316,41 @@ def test_tc5_field_backward_matches_modular(n, S, A, L, F):
         assert torch.isfinite(a).all(), name
         e = rel_l2(a, b)
         assert e < 2e-2, f"{name}: rel-L2 {e:.3e}"
+
+
+# ------------------------------------------------------------------------------------------ tcgen05 proposal level
+@pytest.mark.parametrize("n,S,L,F,H,log2T", [(900, 128, 8, 1, 64, 14), (901, 64, 8, 1, 64, 14), (333, 32, 5, 2, 16, 12),
+                                            (70, 96, 8, 2, 64, 12), (1, 64, 8, 1, 16, 10), (30000, 64, 8, 1, 64, 20)])
+def test_tc5_prop_level_matches_modular(n, S, L, F, H, log2T):
+    """ps_prop_level_fwd / _bwd (one kernel each) vs the chain ray_points -> hash -> mma.sync MLP -> compositing."""
+    from presight_b200 import fused, ops
+    g = torch.Generator().manual_seed(n + S)
+    scal = tuple(O.hash_scalings(L, 16, 1024).tolist())
+    table = ((torch.rand(L << log2T, F, generator=g) * 2 - 1) * 2.0).to(DEV).requires_grad_(True)
+    dims = (L * F, H, 1)
+    ws = [(torch.randn(dims[i + 1], dims[i], generator=g) / dims[i] ** 0.5).to(DEV).requires_grad_(True) for i in range(2)]
+    bs = [(torch.randn(dims[i + 1], generator=g) * 0.1).to(DEV).requires_grad_(True) for i in range(2)]
+    o = ((torch.rand(n, 3, generator=g) - 0.5) * torch.tensor([1.0, 1.0, 0.1])).to(DEV)
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).to(DEV)
+    eu = (torch.rand(n, S + 1, generator=g) * 0.05 + 0.001).cumsum(-1).to(DEV)
+    gw = (torch.randn(n, S, 1, generator=g) * 0.1).to(DEV)
+    grid = fused.GridMeta(scal, log2T, F)
+    meta = fused.MlpMeta(dims, ops.ACT_NONE)
+    aabb = [-1.0, -1.0, -0.5, 1.0, 1.0, 0.5]
+    assert fused.tc5_prop_supported(grid, meta, ops.PREC_BF16, S)
+    leaves = [table, *ws, *bs]
+    w_t = fused._PropLevelTc5.apply(o, d, eu, table, aabb, True, grid, ws[0], bs[0], ws[1], bs[1])
+    g_t = torch.autograd.grad((w_t * gw).sum(), leaves)
+    w_m = fused._PropLevel.apply(o, d, eu, table, aabb, True, grid, meta, ops.PREC_BF16, *ws, *bs)
+    g_m = torch.autograd.grad((w_m * gw).sum(), leaves)
+    assert_close(w_t, w_m, 3e-3, "weights")
+    for name, a, b in zip(["table", "W0", "W1", "b0", "b1"], g_t, g_m):
+        assert torch.isfinite(a).all(), name
+        e = rel_l2(a, b)
+        # b1 is ONE number, the sum of all d_raw (heavy cancellation): the stand-alone kernel sums bf16-rounded values,
+        # the fused one fp32 values, so they differ by the rounding noise of that sum rather than by 1e-2 of its value
+        assert e < (1e-1 if name == "b1" else 2e-2), f"{name}: rel-L2 {e:.3e}"
+    # no-grad forward (eval / non-update steps) takes the same kernel without saving features
+    with torch.no_grad():
+        w_n = fused._PropLevelTc5.apply(o, d, eu, table, aabb, True, grid, ws[0], bs[0], ws[1], bs[1])
+    assert torch.equal(w_n, w_t)
