@@ -83,7 +83,9 @@ def test_fused_matches_modular(impl):
         m.train()
     out_f = fused_model(bundle(), jitters=jit)
     out_m = modular(bundle(), jitters=jit)
-    tol = 1e-5 if impl == "b200+fp32" else 1e-4          # same kernels, same inputs: differences are only fp32 order
+    # fp32: same kernels, same inputs, differences are only fp32 summation order.  bf16: the fused levels run the
+    # tcgen05 kernels, the modular path the mma.sync ones — same parity class, values on a bf16 rounding boundary flip
+    tol = 1e-5 if impl == "b200+fp32" else 3e-3
     for k in ("rgb", "accumulation", "expected_depth", "semantics", "depth"):
         assert_close(out_f[k], out_m[k], tol, k)
     for i in range(3):
