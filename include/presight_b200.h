@@ -210,8 +210,10 @@ int ps_interlevel_loss(const float* c, const float* w, const float* t_env, const
 /* Self-test of the tcgen05 operand conventions used by the fused kernels (csrc/tc5.cuh): one CTA computes, from
  * X [128,64], Y [128,64], W [64,64] (fp32, rounded to bf16 on chip), C1 = X W^T (K-major operands), C2 = X W
  * (MN-major B: the input-gradient form) and C3 = 2 X^T Y (MN-major A and B, reduction over rows, accumulated over two
- * calls: the weight-gradient form; rows 64..127 of C3 are padding).  All outputs [128,64] fp32. */
-int ps_tc5_probe(const float* X, const float* Y, const float* W, float* C1, float* C2, float* C3, void* stream);
+ * calls: the weight-gradient form; rows 64..127 of C3 are padding), all [128,64] fp32, and C4 [128,16] whose column 3
+ * holds the column sums of X (bias-gradient form: one-hot B operand with a zero K stride). */
+int ps_tc5_probe(const float* X, const float* Y, const float* W, float* C1, float* C2, float* C3, float* C4,
+                 void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Fused field level on tcgen05 tensor cores (bf16 parity class).  One kernel evaluates, per 128-point tile,

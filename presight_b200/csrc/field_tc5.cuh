@@ -70,7 +70,12 @@ struct FieldArgs {
     const float* d_sem;    // [N, 64] nullable
 };
 
-// shared-memory weight tiles (bf16 chunk-major, rows = out features)
+// shared-memory weight tiles (bf16 chunk-major, rows = out features).  Every layer also has a 16-column "bias tile"
+// [N x 16]: column 0 = bf16(b), column 1 = bf16(b - bf16(b)) — one extra K step of the forward GEMM against a constant
+// A operand whose first two columns are 1 adds the bias (to ~2^-17 relative) on the tensor core, so no epilogue touches
+// it.  `ones`: that constant A operand as one 128-byte core-matrix block {1,1,0,..} x 8 rows + a zero block (the
+// descriptor's row-group stride is 0, so all 128 rows alias the block).  `onehot`: per layer l a pair of blocks selecting
+// column 3 + l of a 16-column accumulator — the B operand of the bias-gradient GEMM dB_l = dZ_l^T 1 (zero K stride).
 template <int K0>
 struct WLayout {
     static constexpr uint32_t b0 = 0;
@@ -81,12 +86,31 @@ struct WLayout {
     static constexpr uint32_t r0 = s2 + cm_bytes(kSem, kHid);
     static constexpr uint32_t r1 = r0 + cm_bytes(kHid, kRgbIn);
     static constexpr uint32_t r2 = r1 + cm_bytes(kHid, kHid);
-    static constexpr uint32_t bias = r2 + cm_bytes(kRgbOut, kHid);           // fp32 biases
-    // bias offsets (floats)
-    static constexpr int bb0 = 0, bb1 = 64, bs0 = 144, bs1 = 208, bs2 = 272, br0 = 336, br1 = 400, br2 = 464;
-    static constexpr int n_bias = 480;
-    static constexpr uint32_t end = bias + n_bias * 4;
+    static constexpr uint32_t bt0 = r2 + cm_bytes(kRgbOut, kHid);            // bias tiles, layer order B0..R2
+    static constexpr uint32_t ones = bt0 + 480 * 32;                          // 256 B
+    static constexpr uint32_t onehot = ones + 256;                            // 8 x 256 B
+    static constexpr uint32_t end = onehot + 8 * 256;
+    __host__ __device__ static constexpr int rows(int l) {
+        return l == B1 ? kBaseOut : (l == R2 ? kRgbOut : kHid);
+    }
+    __host__ __device__ static constexpr uint32_t bt(int l) {
+        uint32_t off = bt0;
+        for (int i = 0; i < l; ++i) off += rows(i) * 32;
+        return off;
+    }
 };
+
+// D[128 x N] = 1 * bias^T : the first K step of every forward GEMM (accumulate = false)
+__device__ __forceinline__ void gemm_bias(uint32_t tmem_d, uint32_t ones_addr, uint32_t bias_tile, int b_rows, int N) {
+    umma_bf16(tmem_d, make_desc(ones_addr, 128, 0), make_desc(bias_tile, b_rows * 16, 128), make_idesc(N, 0, 0), 0u);
+}
+// dB (column 3 + l of the 16-column accumulator at tmem_d) += column sums of the dZ tile at dz_addr
+__device__ __forceinline__ void gemm_dbias(uint32_t tmem_d, uint32_t dz_addr, uint32_t onehot_addr, int l, bool accumulate) {
+    const uint32_t idesc = make_idesc(16, 1, 1);
+    const uint64_t db = make_desc(onehot_addr + l * 256, 0, 128);
+    for (int kk = 0; kk < kRows / 16; ++kk)
+        umma_bf16(tmem_d, make_desc(dz_addr + kk * 256, 128, kRows * 16), db, idesc, (accumulate || kk > 0) ? 1u : 0u);
+}
 
 template <int K0>
 __device__ __forceinline__ void load_all_weights(const FieldNet& net, unsigned char* wbase, int tid, int nthreads) {
@@ -108,13 +132,30 @@ __device__ __forceinline__ void load_all_weights(const FieldNet& net, unsigned c
     load_weight_cm(net.W[R0], kHid, 16 + kGeo + net.app_dim, kHid, kRgbIn, wbase + WL::r0, kmap, tid, nthreads);
     load_weight_cm(net.W[R1], kHid, kHid, kHid, kHid, wbase + WL::r1, nullptr, tid, nthreads);
     load_weight_cm(net.W[R2], 3, kHid, kRgbOut, kHid, wbase + WL::r2, nullptr, tid, nthreads);
-    float* bias = reinterpret_cast<float*>(wbase + WL::bias);
-    const int off[kLayers] = {WL::bb0, WL::bb1, WL::bs0, WL::bs1, WL::bs2, WL::br0, WL::br1, WL::br2};
     const int nreal[kLayers] = {kHid, kBaseOut, kHid, kHid, kSem, kHid, kHid, 3};
-    const int npad[kLayers] = {kHid, kBaseOut, kHid, kHid, kSem, kHid, kHid, kRgbOut};
-    for (int l = 0; l < kLayers; ++l)
-        for (int i = tid; i < npad[l]; i += nthreads)
-            bias[off[l] + i] = (i < nreal[l] && net.B[l]) ? __ldg(net.B[l] + i) : 0.f;
+    for (int l = 0; l < kLayers; ++l) {
+        const int N = WL::rows(l);
+        unsigned char* bt = wbase + WL::bt(l);
+        for (int i = tid; i < N * 16; i += nthreads) {
+            const int n = i >> 4, k = i & 15;
+            float v = 0.f;
+            if (k < 2 && n < nreal[l] && net.B[l]) {
+                const float b = __ldg(net.B[l] + n);
+                const float hi = __bfloat162float(__float2bfloat16_rn(b));
+                v = k == 0 ? hi : b - hi;
+            }
+            *reinterpret_cast<__nv_bfloat16*>(bt + cm_off(N, n, k)) = __float2bfloat16_rn(v);
+        }
+    }
+    // constant blocks: element e of a 128-byte block = row e / 8, column e % 8
+    for (int i = tid; i < 128; i += nthreads) {
+        reinterpret_cast<__nv_bfloat16*>(wbase + WL::ones)[i] = __float2bfloat16_rn((i < 64 && (i & 7) < 2) ? 1.f : 0.f);
+    }
+    for (int i = tid; i < 8 * 128; i += nthreads) {
+        const int l = i >> 7, e = i & 127, col = 3 + l;               // block 0: columns 0..7, block 1: columns 8..15
+        const int blk = e >> 6, c = (e & 7) + 8 * blk;
+        reinterpret_cast<__nv_bfloat16*>(wbase + WL::onehot)[i] = __float2bfloat16_rn(c == col ? 1.f : 0.f);
+    }
 }
 
 // stage this row's hash features (level-major [L][P][F] fp32) as bf16 into the first K0 columns of `tile`

@@ -15,7 +15,8 @@
 // tc5.cuh and serve all three forms without a transpose.  The weight-gradient GEMM of a layer is issued behind its
 // input-gradient GEMM and is not waited for: it overlaps the next epilogue; the two gradient tiles alternate so a
 // tile is rewritten only after the GEMMs reading it have completed (in-order tensor pipe).
-// Bias gradients: butterfly warp reduction of the fp32 dZ rows, one register per layer and thread.
+// Biases: the forward adds them as one more K step against a constant operand; their gradients dB_l = dZ_l^T 1 are eight
+// tiny GEMMs against one-hot operands that all land in spare columns (3 + l) of one 16-column TMEM accumulator.
 #include "field_tc5.cuh"
 
 namespace ps {
@@ -60,17 +61,17 @@ struct BwdTmem {
     static_assert(end <= 512, "TMEM budget");
 };
 
-// 32 accumulator columns -> +bias, ReLU (mask of the positive ones) -> bf16 -> tile columns [c0, c0 + 32)
-__device__ __forceinline__ uint32_t relu_epilogue32(uint32_t trow, int c0, const float* bias, unsigned char* tile, int r) {
+// 32 accumulator columns (bias included by the GEMM) -> ReLU (mask of the positive ones) -> bf16 -> tile columns
+// [c0, c0 + 32)
+__device__ __forceinline__ uint32_t relu_epilogue32(uint32_t trow, int c0, unsigned char* tile, int r) {
     float v[32];
     tmem_ld32_nowait(trow + c0, v);
     tmem_wait_ld();
     uint32_t mask = 0;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-        const float x = v[i] + bias[c0 + i];
-        if (x > 0.f) mask |= 1u << i;
-        v[i] = fmaxf(x, 0.f);
+        if (v[i] > 0.f) mask |= 1u << i;
+        v[i] = fmaxf(v[i], 0.f);
     }
 #pragma unroll
     for (int i = 0; i < 32; i += 8) store_chunk(tile, kRows, r, c0 + i, v + i);
@@ -98,16 +99,14 @@ __device__ __forceinline__ float column_sums32(const float (&v)[32], int lane) {
     return t[0];
 }
 
-// input-gradient epilogue of a hidden layer: 32 accumulator columns -> ReLU mask -> (bias-gradient sums) -> bf16 dZ
-__device__ __forceinline__ void dgrad_epilogue32(uint32_t trow, int c0, uint32_t mask, unsigned char* dz_tile, int r,
-                                                 int lane, float& db) {
+// input-gradient epilogue of a hidden layer: 32 accumulator columns -> ReLU mask -> bf16 dZ
+__device__ __forceinline__ void dgrad_epilogue32(uint32_t trow, int c0, uint32_t mask, unsigned char* dz_tile, int r) {
     float v[32];
     tmem_ld32_nowait(trow + c0, v);
     tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < 32; ++i)
         if (!((mask >> i) & 1u)) v[i] = 0.f;
-    db += column_sums32(v, lane);
 #pragma unroll
     for (int i = 0; i < 32; i += 8) store_chunk(dz_tile, kRows, r, c0 + i, v + i);
 }
@@ -120,7 +119,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, half = tid >> 7, r = tid & 127, warp = r >> 5, lane = tid & 31;
     unsigned char* wbase = smem;
-    const float* bias = reinterpret_cast<const float*>(smem + WL::bias);
     unsigned char* DZb = smem + SM::dzb;
     unsigned char* DZa = smem + SM::dza;
     unsigned char* A2 = smem + SM::a2;
@@ -137,6 +135,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::bars + 16);
 
     load_all_weights<K0>(a.net, wbase, tid, kBwdThreads);
+    // The bias-gradient GEMMs of all layers share one accumulator and read their dZ operand with M = 128: rows past a
+    // layer's width come from whatever lies behind its tile.  Finite stale values there are harmless (they meet the
+    // zeros of the one-hot operand), NaN / Inf bit patterns are not (NaN * 0), so no tile may ever hold uninitialised
+    // shared memory.
+    for (uint32_t i = SM::dzb + tid * 16; i < SM::rayc; i += kBwdThreads * 16)
+        *reinterpret_cast<uint4*>(smem + i) = make_uint4(0u, 0u, 0u, 0u);
     if (tid < 32) tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
         mbar_init(smem_u32(bar_ptr), 1);
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
     const uint32_t tmem = *tmem_slot;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     const uint32_t bar = smem_u32(bar_ptr);
-    const uint32_t wb = smem_u32(wbase);
+    const uint32_t wb = smem_u32(wbase), ones = wb + WL::ones, oneh = wb + WL::onehot;
     const uint32_t aDZa = smem_u32(DZa), aDZb = smem_u32(DZb), aA1 = smem_u32(A1), aA2 = smem_u32(A2),
                    aX0 = smem_u32(X0), aH1 = smem_u32(H1), aH = smem_u32(Ht), aSH = smem_u32(SHAPPt);
     constexpr uint32_t CH = kRows * 16;     // bytes per 8-column chunk of a 128-row tile
@@ -160,9 +164,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
     const int64_t P = a.N * S;
     const int64_t ntiles = (a.N + rpt - 1) / rpt;
     const int A = a.net.app_dim;
-    // bias-gradient partial sums (lane l <-> one column of this thread's column block)
-    float db_b0 = 0.f, db_b1a = 0.f, db_b1b = 0.f, db_s0 = 0.f, db_s1 = 0.f, db_s2 = 0.f, db_r0 = 0.f, db_r1 = 0.f,
-          db_r2 = 0.f;
     bool first = true;
 
 #define FB_SYNC_ISSUE(...)     \
@@ -211,10 +212,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
         }
         const float* rc = rayc + (q < rpt ? q : 0) * 72;
         // ---- base network, forward --------------------------------------------------------------------------
-        FB_SYNC_ISSUE(gemm_kk(tmem + TM::acc, aX0, kRows, wb + WL::b0, kHid, kHid, K0, false); umma_commit(bar))
+        FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(B0), kHid, kHid);
+                      gemm_kk(tmem + TM::acc, aX0, kRows, wb + WL::b0, kHid, kHid, K0, true); umma_commit(bar))
         FB_WAIT()
-        const uint32_t m_b0 = relu_epilogue32(trow + TM::acc, 32 * half, bias + WL::bb0, H1, r);
-        FB_SYNC_ISSUE(gemm_kk(tmem + TM::acc, aH1, kRows, wb + WL::b1, kBaseOut, kBaseOut, kHid, false); umma_commit(bar))
+        const uint32_t m_b0 = relu_epilogue32(trow + TM::acc, 32 * half, H1, r);
+        FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(B1), kBaseOut, kBaseOut);
+                      gemm_kk(tmem + TM::acc, aH1, kRows, wb + WL::b1, kBaseOut, kBaseOut, kHid, true); umma_commit(bar))
         FB_WAIT()
         {
             // half 0: columns 0..47 (raw density, geo, first 32 semantic inputs); half 1: columns 48..79
@@ -222,8 +225,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
             const int c0 = half == 0 ? 0 : 48;
             tmem_ld32_nowait(trow + TM::acc + c0, v);
             tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += bias[WL::bb1 + c0 + i];
             if (half == 0) raws[r] = v[0];
 #pragma unroll
             for (int i = 0; i < 32; i += 8) store_chunk(Ht, kRows, r, c0 + i, v + i);
@@ -231,14 +232,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
                 float u[16];
                 tmem_ld16_nowait(trow + TM::acc + 32, u);
                 tmem_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) u[i] += bias[WL::bb1 + 32 + i];
                 store_chunk(Ht, kRows, r, 32, u);
                 store_chunk(Ht, kRows, r, 40, u + 8);
             }
         }
         // ---- colour head, forward ---------------------------------------------------------------------------
-        FB_SYNC_ISSUE(gemm_kk(tmem + TM::acc, aSH, kRows, wb + WL::r0, kHid, kHid, 16, false);
+        FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(R0), kHid, kHid);
+                      gemm_kk(tmem + TM::acc, aSH, kRows, wb + WL::r0, kHid, kHid, 16, true);
                       gemm_kk(tmem + TM::acc, aH, kRows, wb + WL::r0 + 2 * kHid * 16, kHid, kHid, 16, true);
                       gemm_kk(tmem + TM::acc, aSH + 2 * CH, kRows, wb + WL::r0 + 4 * kHid * 16, kHid, kHid, 16, true);
                       umma_commit(bar))
@@ -250,8 +250,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
         const double dd_incl = warp_scan_incl((double)dd, lane);
         if (lane == 31) tails[warp * 2] = dd_incl;
         FB_WAIT()
-        const uint32_t m_r0 = relu_epilogue32(trow + TM::acc, 32 * half, bias + WL::br0, A1, r);
-        FB_SYNC_ISSUE(gemm_kk(tmem + TM::acc, aA1, kRows, wb + WL::r1, kHid, kHid, kHid, false); umma_commit(bar))
+        const uint32_t m_r0 = relu_epilogue32(trow + TM::acc, 32 * half, A1, r);
+        FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(R1), kHid, kHid);
+                      gemm_kk(tmem + TM::acc, aA1, kRows, wb + WL::r1, kHid, kHid, kHid, true); umma_commit(bar))
         const int w_first = (warp / wpr) * wpr;
         float w, T;
         bool finite;
@@ -270,8 +271,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
         }
         const float tm = __fdiv_rn(__fadd_rn(t0, t1), 2.f);
         FB_WAIT()
-        const uint32_t m_r1 = relu_epilogue32(trow + TM::acc, 32 * half, bias + WL::br1, A2, r);
-        FB_SYNC_ISSUE(gemm_kk(tmem + TM::acc, aA2, kRows, wb + WL::r2, kRgbOut, kRgbOut, kHid, false); umma_commit(bar))
+        const uint32_t m_r1 = relu_epilogue32(trow + TM::acc, 32 * half, A2, r);
+        FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(R2), kRgbOut, kRgbOut);
+                      gemm_kk(tmem + TM::acc, aA2, kRows, wb + WL::r2, kRgbOut, kRgbOut, kHid, true); umma_commit(bar))
         FB_WAIT()
         // ---- colour head, backward --------------------------------------------------------------------------
         if (half == 0) {
@@ -284,27 +286,29 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
             for (int i = 0; i < 32; ++i) dz[i] = 0.f;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                const float y = sigmoid_f(u[i] + bias[WL::br2 + i]);
+                const float y = sigmoid_f(u[i]);
                 dot += y * rc[64 + i];
                 dz[i] = w * rc[64 + i] * y * (1.f - y);
             }
             dots[2 * 128 + r] = dot;
-            db_r2 += column_sums32(dz, lane);
             store_chunk(DZa, kRows, r, 0, dz);
             store_chunk(DZa, kRows, r, 8, dz + 8);
         }
         FB_SYNC_ISSUE(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::r2, kRgbOut, kHid, 16, false); umma_commit(bar);
-                      gemm_wgrad(tmem + TM::r2, aA2, aDZa, 16, acc_dw))
+                      gemm_wgrad(tmem + TM::r2, aA2, aDZa, 16, acc_dw);
+                      gemm_dbias(tmem + TM::r2, aDZa, oneh, R2, true))
         FB_WAIT()
-        dgrad_epilogue32(trow + TM::acc, 32 * half, m_r1, DZb, r, lane, db_r1);
+        dgrad_epilogue32(trow + TM::acc, 32 * half, m_r1, DZb, r);
         FB_SYNC_ISSUE(gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::r1, kHid, kHid, kHid, false); umma_commit(bar);
-                      gemm_wgrad(tmem + TM::r1, aDZb, aA1, kHid, acc_dw))
+                      gemm_wgrad(tmem + TM::r1, aDZb, aA1, kHid, acc_dw);
+                      gemm_dbias(tmem + TM::r2, aDZb, oneh, R1, true))
         FB_WAIT()
-        dgrad_epilogue32(trow + TM::acc, 32 * half, m_r0, DZa, r, lane, db_r0);
+        dgrad_epilogue32(trow + TM::acc, 32 * half, m_r0, DZa, r);
         FB_SYNC_ISSUE(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::r0, kHid, kRgbIn, kHid, false); umma_commit(bar);
                       gemm_wgrad(tmem + TM::r0, aDZa, aSH, 16, acc_dw);
                       gemm_wgrad(tmem + TM::r0 + 16, aDZa, aH, 16, acc_dw);
-                      gemm_wgrad(tmem + TM::r0 + 32, aDZa, aSH + 2 * CH, 16, acc_dw))
+                      gemm_wgrad(tmem + TM::r0 + 32, aDZa, aSH + 2 * CH, 16, acc_dw);
+                      gemm_dbias(tmem + TM::r2, aDZa, oneh, R0, true))
         FB_WAIT()
         float d_h01[16];   // half 0: gradient of h[0:16] from the colour head (column 0 is zero by construction)
         {
@@ -329,13 +333,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
             }
         }
         // ---- semantic head, forward -------------------------------------------------------------------------
-        FB_SYNC_ISSUE(gemm_kk(tmem + TM::acc, aH + 2 * CH, kRows, wb + WL::s0, kHid, kHid, kSem, false); umma_commit(bar))
+        FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(S0), kHid, kHid);
+                      gemm_kk(tmem + TM::acc, aH + 2 * CH, kRows, wb + WL::s0, kHid, kHid, kSem, true); umma_commit(bar))
         FB_WAIT()
-        const uint32_t m_s0 = relu_epilogue32(trow + TM::acc, 32 * half, bias + WL::bs0, A1, r);
-        FB_SYNC_ISSUE(gemm_kk(tmem + TM::acc, aA1, kRows, wb + WL::s1, kHid, kHid, kHid, false); umma_commit(bar))
+        const uint32_t m_s0 = relu_epilogue32(trow + TM::acc, 32 * half, A1, r);
+        FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(S1), kHid, kHid);
+                      gemm_kk(tmem + TM::acc, aA1, kRows, wb + WL::s1, kHid, kHid, kHid, true); umma_commit(bar))
         FB_WAIT()
-        const uint32_t m_s1 = relu_epilogue32(trow + TM::acc, 32 * half, bias + WL::bs1, A2, r);
-        FB_SYNC_ISSUE(gemm_kk(tmem + TM::acc, aA2, kRows, wb + WL::s2, kSem, kSem, kHid, false); umma_commit(bar))
+        const uint32_t m_s1 = relu_epilogue32(trow + TM::acc, 32 * half, A2, r);
+        FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(S2), kSem, kSem);
+                      gemm_kk(tmem + TM::acc, aA2, kRows, wb + WL::s2, kSem, kSem, kHid, true); umma_commit(bar))
         FB_WAIT()
         // ---- semantic head, backward ------------------------------------------------------------------------
         {
@@ -346,25 +353,26 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const float gs = rc[32 * half + i];
-                dot += (v[i] + bias[WL::bs2 + 32 * half + i]) * gs;
+                dot += v[i] * gs;
                 v[i] = w * gs;
             }
             dots[half * 128 + r] = dot;
-            db_s2 += column_sums32(v, lane);
 #pragma unroll
             for (int i = 0; i < 32; i += 8) store_chunk(DZb, kRows, r, 32 * half + i, v + i);
         }
         FB_SYNC_ISSUE(gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::s2, kSem, kHid, kSem, false); umma_commit(bar);
-                      gemm_wgrad(tmem + TM::s2, aDZb, aA2, kHid, acc_dw))
+                      gemm_wgrad(tmem + TM::s2, aDZb, aA2, kHid, acc_dw);
+                      gemm_dbias(tmem + TM::r2, aDZb, oneh, S2, true))
         // compositing backward, pass 1 (the barrier above published dots[]): total gradient on this weight
         float g = gw_in + rc[67] + rc[68] * (tm - rc[69]) * rc[70] + dots[r] + dots[128 + r] + dots[256 + r];
         if (!finite) g = 0.f;
         const double gw_incl = warp_scan_incl((double)g * (double)w, lane);
         if (lane == 31) tails[warp * 2 + 1] = gw_incl;
         FB_WAIT()
-        dgrad_epilogue32(trow + TM::acc, 32 * half, m_s1, DZa, r, lane, db_s1);
+        dgrad_epilogue32(trow + TM::acc, 32 * half, m_s1, DZa, r);
         FB_SYNC_ISSUE(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::s1, kHid, kHid, kHid, false); umma_commit(bar);
-                      gemm_wgrad(tmem + TM::s1, aDZa, aA1, kHid, acc_dw))
+                      gemm_wgrad(tmem + TM::s1, aDZa, aA1, kHid, acc_dw);
+                      gemm_dbias(tmem + TM::r2, aDZa, oneh, S1, true))
         // pass 2: d sigma_i = delta_i * (g_i T_{i+1} - sum_{k>i} g_k w_k); d raw = d sigma * sel * exp(clamp(raw))
         float d_raw;
         {
@@ -378,9 +386,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
             d_raw = valid ? d_sigma * selv * expf(fminf(fmaxf(raw, -15.f), 15.f)) : 0.f;
         }
         FB_WAIT()
-        dgrad_epilogue32(trow + TM::acc, 32 * half, m_s0, DZb, r, lane, db_s0);
+        dgrad_epilogue32(trow + TM::acc, 32 * half, m_s0, DZb, r);
         FB_SYNC_ISSUE(gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::s0, kHid, kSem, kHid, false); umma_commit(bar);
-                      gemm_wgrad(tmem + TM::s0, aDZb, aH + 2 * CH, kSem, acc_dw))
+                      gemm_wgrad(tmem + TM::s0, aDZb, aH + 2 * CH, kSem, acc_dw);
+                      gemm_dbias(tmem + TM::r2, aDZb, oneh, S0, true))
         FB_WAIT()
         // ---- base network, backward: dH = [d raw | colour head (15) | semantic head (64)] ----------------------
         {
@@ -391,8 +400,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = 0.f;
             }
-            if (half == 0) db_b1b += column_sums32(v, lane);      // columns 16..47
-            else db_b1a += column_sums32(v, lane);                // columns 48..79
 #pragma unroll
             for (int i = 0; i < 32; i += 8) store_chunk(DZa, kRows, r, 16 + 32 * half + i, v + i);
             if (half == 0) {
@@ -400,17 +407,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
 #pragma unroll
                 for (int i = 0; i < 32; ++i) u[i] = (i < 16 && valid) ? d_h01[i] : 0.f;
                 u[0] = d_raw;
-                db_b1a += column_sums32(u, lane);                 // columns 0..15 (lanes 16..31 receive zero)
                 store_chunk(DZa, kRows, r, 0, u);
                 store_chunk(DZa, kRows, r, 8, u + 8);
             }
         }
         FB_SYNC_ISSUE(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::b1, kBaseOut, kHid, kBaseOut, false); umma_commit(bar);
-                      gemm_wgrad(tmem + TM::b1, aDZa, aH1, kHid, acc_dw))
+                      gemm_wgrad(tmem + TM::b1, aDZa, aH1, kHid, acc_dw);
+                      gemm_dbias(tmem + TM::r2, aDZa, oneh, B1, true))
         FB_WAIT()
-        dgrad_epilogue32(trow + TM::acc, 32 * half, m_b0, DZb, r, lane, db_b0);
+        dgrad_epilogue32(trow + TM::acc, 32 * half, m_b0, DZb, r);
         // last layer: the weight-gradient GEMM goes first so the final wait also covers it (X0 is restaged next tile)
         FB_SYNC_ISSUE(gemm_wgrad(tmem + TM::b0, aDZb, aX0, K0, acc_dw);
+                      gemm_dbias(tmem + TM::r2, aDZb, oneh, B0, true);
                       gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::b0, kHid, K0, kHid, false); umma_commit(bar))
         FB_WAIT()
         // ---- hash-feature gradient (level-major [L][P][F]) ---------------------------------------------------
@@ -448,25 +456,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
 #undef FB_SYNC_ISSUE
 #undef FB_WAIT
 
-    // ---- flush: bias gradients (registers) and weight gradients (TMEM) -> global atomics ------------------------
-    {
-        // column owned by this lane in a 32-column block: 32 * half + lane (b1: see the dH epilogue)
-        float* const* dB = a.net.dB;
-        const int c = 32 * half + lane;
-        atomicAdd(dB[B0] + c, db_b0);
-        atomicAdd(dB[S0] + c, db_s0);
-        atomicAdd(dB[S1] + c, db_s1);
-        atomicAdd(dB[S2] + c, db_s2);
-        atomicAdd(dB[R0] + c, db_r0);
-        atomicAdd(dB[R1] + c, db_r1);
-        if (half == 0) {
-            if (lane < 3) atomicAdd(dB[R2] + lane, db_r2);
-            if (lane < 16) atomicAdd(dB[B1] + lane, db_b1a);
-            atomicAdd(dB[B1] + 16 + lane, db_b1b);
-        } else {
-            atomicAdd(dB[B1] + 48 + lane, db_b1a);
-        }
-    }
+    // ---- flush: weight and bias gradients (TMEM) -> global atomics ---------------------------------------------------
     if (!first) {
         fence_after();
         // region: TMEM column offset, rows (out features), 16-column blocks, global pointer, real row length, column map
@@ -505,6 +495,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
         flush(TM::r0, kHid, kRgbIn, a.net.dW[R0], 16 + kGeo + A, 1);
         flush(TM::r1, kHid, kHid, a.net.dW[R1], kHid, 0);
         flush(TM::r2, kHid, kRgbOut, a.net.dW[R2], kHid, 2);
+        // bias gradients: column 3 + l of the r2 region, row = output unit
+        if (half == 0) {
+            float u[16];
+            tmem_ld16_nowait(trow + TM::r2, u);
+            tmem_wait_ld();
+            const int n = warp * 32 + lane;
+            const int nreal[kLayers] = {kHid, kBaseOut, kHid, kHid, kSem, kHid, kHid, 3};
+#pragma unroll
+            for (int l = 0; l < kLayers; ++l)
+                if (n < nreal[l] && a.net.dB[l]) atomicAdd(a.net.dB[l] + n, u[3 + l]);
+        }
     }
     fence_before();
     __syncthreads();

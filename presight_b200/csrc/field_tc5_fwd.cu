@@ -5,7 +5,7 @@
 //
 // CTA = 256 threads = two independent groups of 128; a group owns one 128-point tile at a time (128 / S rays) with
 // one thread per point (row).  All eight layers run on tcgen05.mma (bf16 x bf16 -> fp32 in TMEM, M = 128); the
-// epilogues (bias, ReLU, bf16 re-pack into the next layer's A tile) are thread-per-row, so everything that is "per
+// epilogues (ReLU, bf16 re-pack into the next layer's A tile; the bias is one more K step of the GEMM) are thread-per-row, so everything that is "per
 // sample" — density, weights, the dot products of compositing — is plain per-thread code.  While one group waits for
 // its MMA the other runs its epilogue; the weights (54 KB bf16) are staged once per CTA and shared by both groups.
 #include "field_tc5.cuh"
@@ -33,15 +33,15 @@ struct FwdSmem {
     static constexpr uint32_t total = bars + 32;
 };
 
-// epilogue of a hidden layer: accumulator row -> +bias, ReLU -> bf16 -> columns [0, 64) of `tile`
-__device__ __forceinline__ void hidden_epilogue64(uint32_t trow, const float* bias, unsigned char* tile, int r) {
+// epilogue of a hidden layer: accumulator row (bias already added by the GEMM) -> ReLU -> bf16 -> columns [0, 64)
+__device__ __forceinline__ void hidden_epilogue64(uint32_t trow, unsigned char* tile, int r) {
 #pragma unroll
     for (int c = 0; c < 64; c += 32) {
         float v[32];
         tmem_ld32_nowait(trow + c, v);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[c + i], 0.f);
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
 #pragma unroll
         for (int i = 0; i < 32; i += 8) store_chunk(tile, kRows, r, c + i, v + i);
     }
@@ -75,7 +75,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, g = tid >> 7, t = tid & 127, warp = t >> 5, lane = tid & 31;
     unsigned char* wbase = smem;
-    const float* bias = reinterpret_cast<const float*>(smem + WL::bias);
     unsigned char* gs = smem + SM::groups + g * SM::group_bytes;
     unsigned char* Ht = gs + SM::h;
     unsigned char* SHAPPt = gs + SM::shapp;
@@ -101,7 +100,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
     const uint32_t tmem = *tmem_slot + g * 128;                        // this group's 80-column accumulator
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     const uint32_t bar = smem_u32(bar_ptr + g);
-    const uint32_t wb = smem_u32(wbase);
+    const uint32_t wb = smem_u32(wbase), ones = wb + WL::ones;
     const uint32_t aH = smem_u32(Ht), aSH = smem_u32(SHAPPt), aA = smem_u32(BufA), aB = smem_u32(BufB);
     const int barid = 1 + g;
     uint32_t phase = 0;
@@ -144,37 +143,34 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
             selv = a.sel ? (float)a.sel[p] : 1.f;
         }
         // ---- base network ------------------------------------------------------------------------------
-        FT_SYNC_ISSUE(gemm_kk(tmem, aA, kRows, wb + WL::b0, kHid, kHid, K0, false))
+        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(B0), kHid, kHid);
+                      gemm_kk(tmem, aA, kRows, wb + WL::b0, kHid, kHid, K0, true))
         FT_WAIT()
-        hidden_epilogue64(trow, bias + WL::bb0, BufB, t);
-        FT_SYNC_ISSUE(gemm_kk(tmem, aB, kRows, wb + WL::b1, kBaseOut, kBaseOut, kHid, false))
+        hidden_epilogue64(trow, BufB, t);
+        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(B1), kBaseOut, kBaseOut);
+                      gemm_kk(tmem, aB, kRows, wb + WL::b1, kBaseOut, kBaseOut, kHid, true))
         FT_WAIT()
         float raw;
         {
             float v[32];
             tmem_ld32_nowait(trow, v);
             tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += bias[WL::bb1 + i];
             raw = v[0];
 #pragma unroll
             for (int i = 0; i < 32; i += 8) store_chunk(Ht, kRows, t, i, v + i);
             tmem_ld32_nowait(trow + 32, v);
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += bias[WL::bb1 + 32 + i];
-#pragma unroll
             for (int i = 0; i < 32; i += 8) store_chunk(Ht, kRows, t, 32 + i, v + i);
             float u[16];
             tmem_ld16_nowait(trow + 64, u);
             tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) u[i] += bias[WL::bb1 + 64 + i];
             store_chunk(Ht, kRows, t, 64, u);
             store_chunk(Ht, kRows, t, 72, u + 8);
         }
         // semantic head layer 0 reads h[16:80] = chunks 2..9 of the H tile
-        FT_SYNC_ISSUE(gemm_kk(tmem, aH + 2 * kRows * 16, kRows, wb + WL::s0, kHid, kHid, kSem, false))
+        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(S0), kHid, kHid);
+                      gemm_kk(tmem, aH + 2 * kRows * 16, kRows, wb + WL::s0, kHid, kHid, kSem, true))
         // ---- weights of this ray (overlaps the MMA): rays.py:138-148 -------------------------------------
         const float density = valid ? expf(raw) * selv : 0.f;
         const float dd = __fmul_rn(__fsub_rn(t1, t0), density);
@@ -207,8 +203,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
         if (lane == 0) { red[warp * 72 + 64] = acc_w; red[warp * 72 + 65] = dnum_w; }
         // ---- semantic head -------------------------------------------------------------------------------
         FT_WAIT()
-        hidden_epilogue64(trow, bias + WL::bs0, BufA, t);
-        FT_SYNC_ISSUE(gemm_kk(tmem, aA, kRows, wb + WL::s1, kHid, kHid, kHid, false))
+        hidden_epilogue64(trow, BufA, t);
+        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(S1), kHid, kHid);
+                      gemm_kk(tmem, aA, kRows, wb + WL::s1, kHid, kHid, kHid, true))
         {   // (after the barrier inside FT_SYNC_ISSUE the weight tails of all warps are visible)
             double wc = 0.0;
             for (int k = w_first; k < warp; ++k) wc += tails[k * 2 + 1];
@@ -216,8 +213,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
             if (lane == 0) foundw[warp] = hit ? (warp - w_first) * 32 + __ffs(hit) - 1 : 0x7fffffff;
         }
         FT_WAIT()
-        hidden_epilogue64(trow, bias + WL::bs1, BufB, t);
-        FT_SYNC_ISSUE(gemm_kk(tmem, aB, kRows, wb + WL::s2, kSem, kSem, kHid, false))
+        hidden_epilogue64(trow, BufB, t);
+        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(S2), kSem, kSem);
+                      gemm_kk(tmem, aB, kRows, wb + WL::s2, kSem, kSem, kHid, true))
         FT_WAIT()
         {
             float v[64];
@@ -225,13 +223,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
             tmem_ld32_nowait(trow + 32, *reinterpret_cast<float(*)[32]>(v + 32));
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] = w * (v[i] + bias[WL::bs2 + i]);
+            for (int i = 0; i < 64; ++i) v[i] *= w;
             warp_transpose_reduce<64>(v, lane);
             red[warp * 72 + 2 * lane] = v[0];
             red[warp * 72 + 2 * lane + 1] = v[1];
         }
         // ---- colour head: [sh | h[0:16] | app] ------------------------------------------------------------
-        FT_SYNC_ISSUE(gemm_kk(tmem, aSH, kRows, wb + WL::r0, kHid, kHid, 16, false);
+        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(R0), kHid, kHid);
+                      gemm_kk(tmem, aSH, kRows, wb + WL::r0, kHid, kHid, 16, true);
                       gemm_kk(tmem, aH, kRows, wb + WL::r0 + 2 * kHid * 16, kHid, kHid, 16, true);
                       gemm_kk(tmem, aSH + 2 * kRows * 16, kRows, wb + WL::r0 + 4 * kHid * 16, kHid, kHid, 16, true))
         // per-ray semantics / accumulation / depths (the barrier above published red[] and foundw[])
@@ -259,11 +258,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
             }
         }
         FT_WAIT()
-        hidden_epilogue64(trow, bias + WL::br0, BufA, t);
-        FT_SYNC_ISSUE(gemm_kk(tmem, aA, kRows, wb + WL::r1, kHid, kHid, kHid, false))
+        hidden_epilogue64(trow, BufA, t);
+        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(R1), kHid, kHid);
+                      gemm_kk(tmem, aA, kRows, wb + WL::r1, kHid, kHid, kHid, true))
         FT_WAIT()
-        hidden_epilogue64(trow, bias + WL::br1, BufB, t);
-        FT_SYNC_ISSUE(gemm_kk(tmem, aB, kRows, wb + WL::r2, kRgbOut, kRgbOut, kHid, false))
+        hidden_epilogue64(trow, BufB, t);
+        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(R2), kRgbOut, kRgbOut);
+                      gemm_kk(tmem, aB, kRows, wb + WL::r2, kRgbOut, kRgbOut, kHid, true))
         FT_WAIT()
         {
             float u[16];
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
             tmem_wait_ld();
             float c3[3];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) c3[i] = warp_sum(w * sigmoid_f(u[i] + bias[WL::br2 + i]));
+            for (int i = 0; i < 3; ++i) c3[i] = warp_sum(w * sigmoid_f(u[i]));
             if (lane == 0) { red[warp * 72 + 66] = c3[0]; red[warp * 72 + 67] = c3[1]; red[warp * 72 + 68] = c3[2]; }
         }
         fence_before();

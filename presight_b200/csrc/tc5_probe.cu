@@ -5,15 +5,18 @@
 namespace ps {
 namespace tc5 {
 
-// X [128 x 64], Y [128 x 64], W [64 x 64] fp32 -> C1 = X W^T, C2 = X W, C3 = 2 X^T Y  (all [.. x 64] fp32)
+// X [128 x 64], Y [128 x 64], W [64 x 64] fp32 -> C1 = X W^T, C2 = X W, C3 = 2 X^T Y  (all [.. x 64] fp32),
+// C4 [128 x 16]: column 3 = column sums of X (rows 0..63), other columns zero
 __global__ void __launch_bounds__(128) tc5_probe_kernel(const float* __restrict__ X, const float* __restrict__ Y,
                                                         const float* __restrict__ W, float* __restrict__ C1,
-                                                        float* __restrict__ C2, float* __restrict__ C3) {
+                                                        float* __restrict__ C2, float* __restrict__ C3,
+                                                        float* __restrict__ C4) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* Xs = smem;                       // 16 KB
     unsigned char* Ys = Xs + cm_bytes(128, 64);     // 16 KB (also the "garbage" behind X for the M = 128 wgrad)
     unsigned char* Ws = Ys + cm_bytes(128, 64);     // 8 KB
-    uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(Ws + cm_bytes(64, 64));
+    unsigned char* Oh = Ws + cm_bytes(64, 64);     // 256 B: one-hot block (column 3) + zero block
+    uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(Oh + 256);
     uint32_t* slot = reinterpret_cast<uint32_t*>(bar_ptr + 1);
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int c0 = 0; c0 < 64; c0 += 8) {
@@ -23,6 +26,7 @@ __global__ void __launch_bounds__(128) tc5_probe_kernel(const float* __restrict_
         store_chunk(Ys, 128, tid, c0, u);
     }
     load_weight_cm(W, 64, 64, 64, 64, Ws, nullptr, tid, 128);
+    if (tid < 128) reinterpret_cast<__nv_bfloat16*>(Oh)[tid] = __float2bfloat16_rn((tid < 64 && (tid & 7) == 3) ? 1.f : 0.f);
     const uint32_t bar = smem_u32(bar_ptr);
     if (warp == 0) tmem_alloc(slot, 256);
     if (tid == 0) {
@@ -39,11 +43,22 @@ __global__ void __launch_bounds__(128) tc5_probe_kernel(const float* __restrict_
         gemm_dgrad(tmem + 64, smem_u32(Xs), 128, smem_u32(Ws), 64, 64, 64, false);
         gemm_wgrad(tmem + 128, smem_u32(Xs), smem_u32(Ys), 64, false);
         gemm_wgrad(tmem + 128, smem_u32(Xs), smem_u32(Ys), 64, true);
+        // column sums of X through a one-hot B operand whose K stride (LBO) is zero: every 8-row group of the
+        // reduction re-reads the same 128-byte block {0,0,0,1,0,0,0,0} x 8; the second 8-column chunk is a zero block
+        for (int kk = 0; kk < 8; ++kk)
+            umma_bf16(tmem + 192, make_desc(smem_u32(Xs) + kk * 256, 128, 128 * 16), make_desc(smem_u32(Oh), 0, 128),
+                      make_idesc(16, 1, 1), kk > 0 ? 1u : 0u);
         umma_commit(bar);
     }
     mbar_wait(bar, 0);
     fence_after();
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    {
+        float v[16];
+        tmem_ld16_nowait(trow + 192, v);
+        tmem_wait_ld();
+        for (int i = 0; i < 16; ++i) C4[tid * 16 + i] = v[i];
+    }
     float* outs[3] = {C1, C2, C3};
     for (int m = 0; m < 3; ++m)
         for (int c = 0; c < 64; c += 32) {
@@ -61,10 +76,10 @@ __global__ void __launch_bounds__(128) tc5_probe_kernel(const float* __restrict_
 }  // namespace ps
 
 extern "C" int ps_tc5_probe(const float* X, const float* Y, const float* W, float* C1, float* C2, float* C3,
-                            void* stream) {
+                            float* C4, void* stream) {
     using namespace ps;
-    PS_REQUIRE(X && Y && W && C1 && C2 && C3, "tc5_probe: null pointer");
-    const size_t smem = tc5::cm_bytes(128, 64) * 2 + tc5::cm_bytes(64, 64) + 64;
+    PS_REQUIRE(X && Y && W && C1 && C2 && C3 && C4, "tc5_probe: null pointer");
+    const size_t smem = tc5::cm_bytes(128, 64) * 2 + tc5::cm_bytes(64, 64) + 256 + 64;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(tc5::tc5_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
@@ -74,6 +89,6 @@ extern "C" int ps_tc5_probe(const float* X, const float* Y, const float* W, floa
         }
         configured = true;
     }
-    tc5::tc5_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(X, Y, W, C1, C2, C3);
+    tc5::tc5_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(X, Y, W, C1, C2, C3, C4);
     return check_launch("tc5_probe");
 }

@@ -447,9 +447,13 @@ def test_tcgen05_operand_conventions(ops):
     X, Y, W = torch.randn(128, 64, generator=g), torch.randn(128, 64, generator=g), torch.randn(64, 64, generator=g)
     Xd, Yd, Wd = X.to(DEV), Y.to(DEV), W.to(DEV)
     C = [torch.zeros(128, 64, device=DEV) for _ in range(3)]
-    call("ps_tc5_probe", ptr(Xd), ptr(Yd), ptr(Wd), ptr(C[0]), ptr(C[1]), ptr(C[2]), stream())
+    C4 = torch.full((128, 16), -1.0, device=DEV)
+    call("ps_tc5_probe", ptr(Xd), ptr(Yd), ptr(Wd), ptr(C[0]), ptr(C[1]), ptr(C[2]), ptr(C4), stream())
     torch.cuda.synchronize()
     Xb, Yb, Wb = (t.bfloat16().float() for t in (X, Y, W))
     assert_close(C[0].cpu(), Xb @ Wb.T, 1e-5, "X W^T (K-major)")
     assert_close(C[1].cpu(), Xb @ Wb, 1e-5, "X W (MN-major B)")
     assert_close(C[2].cpu()[:64], 2.0 * (Xb.T @ Yb), 1e-5, "2 X^T Y (MN-major A and B, accumulated)")
+    want4 = torch.zeros(64, 16)
+    want4[:, 3] = Xb.sum(0)
+    assert_close(C4.cpu()[:64], want4, 1e-5, "column sums through a one-hot operand with zero K stride")

@@ -17,6 +17,8 @@ def scalings(L, lo, hi):
 
 def timeit(fn, iters):
     fn(); torch.cuda.synchronize()
+    if iters <= 0:
+        return float("nan")
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(iters): fn()
