@@ -27,6 +27,7 @@ _f32c = ops._f32c
 # PS_TC5_FIELD=0 keeps the final level on the chain of stand-alone kernels (hash / 3 MLPs / compositing)
 USE_TC5_FIELD = os.environ.get("PS_TC5_FIELD", "1") == "1"
 USE_TC5_PROP = os.environ.get("PS_TC5_PROP", "1") == "1"
+OVERLAP_PROP_BWD = os.environ.get("PS_OVERLAP_PROP_BWD", "1") == "1"
 
 
 @dataclass(frozen=True)
@@ -185,13 +186,31 @@ class _PropLevelTc5(torch.autograd.Function):
         grid, aabb, contract, N, S = ctx.meta
         o, d, eu, feat, table, w0, b0, w1, b1 = ctx.saved_tensors
         ws, bs = [w0.detach(), w1.detach()], [b0.detach(), b1.detach()]
-        dws, dbs = [torch.zeros_like(t) for t in ws], [torch.zeros_like(t) for t in bs]
-        dtable = torch.zeros_like(table)
-        net = host_prop_net(ws, bs, dws, dbs)
-        with ops._probe(f"prop_level_bwd_S{S}"):
-            call("ps_prop_level_bwd", C.byref(net), ptr(o), ptr(d), ptr(eu), N, S, host_floats(aabb), 1 if contract else 0,
-                 host_floats(grid.scalings), grid.L, grid.F, grid.log2_T, ptr(feat), ptr(_f32c(dw).view(N, S)),
-                 ptr(dtable), stream())
+        main = torch.cuda.current_stream()
+        # The proposal levels' gradients depend only on the interlevel loss, not on the final level's backward: when
+        # the producer of `dw` published its completion event, run this backward on a side stream so that it overlaps
+        # the field kernels / main hash scatter already queued on the main stream.
+        ev_in = ops.pop_grad_event(dw) if OVERLAP_PROP_BWD else None
+        run_on = ops.side_stream(eu.device) if ev_in is not None else main
+        with torch.cuda.stream(run_on):
+            if ev_in is not None:
+                run_on.wait_event(ev_in)
+            dwc = _f32c(dw).view(N, S)
+            dws, dbs = [torch.zeros_like(t) for t in ws], [torch.zeros_like(t) for t in bs]
+            dtable = torch.zeros_like(table)
+            net = host_prop_net(ws, bs, dws, dbs)
+            with ops._probe(f"prop_level_bwd_S{S}"):
+                call("ps_prop_level_bwd", C.byref(net), ptr(o), ptr(d), ptr(eu), N, S, host_floats(aabb),
+                     1 if contract else 0, host_floats(grid.scalings), grid.L, grid.F, grid.log2_T, ptr(feat), ptr(dwc),
+                     ptr(dtable), run_on.cuda_stream)
+            if ev_in is not None:
+                done = torch.cuda.Event()
+                done.record(run_on)
+                for t in (dtable, *dws, *dbs):
+                    t.record_stream(main)
+                dw.record_stream(run_on)
+        if ev_in is not None:
+            main.wait_event(done)
         return (None, None, None, dtable, None, None, None, dws[0], dbs[0], dws[1], dbs[1])
 
 

@@ -41,7 +41,7 @@ def interlevel_loss(weights_list: List[Tensor], sp_bins_list: List[Tensor]) -> T
         if w.is_cuda:
             # one kernel per proposal level: loss and d loss / d proposal weights (csrc/losses.cu)
             from . import ops
-            loss = loss + ops.interlevel_loss_level(c, w, sdist, weights[..., 0])
+            loss = loss + ops.interlevel_loss_level(c, w, sdist, weights)     # [N,Sp,1]: no slicing node in between
         else:
             loss = loss + torch.mean(lossfun_outer(c, w, sdist, weights[..., 0]))
     return loss

@@ -403,6 +403,34 @@ def composite(eu_bins: Tensor, density: Tensor, rgb: Optional[Tensor], sem: Opti
 # --------------------------------------------------------------------------------------------------
 # loss stack: proposal (interlevel) loss
 # --------------------------------------------------------------------------------------------------
+# Cross-stream hand-off of gradients: a producer may publish "this gradient tensor is complete at event E" so that a
+# consumer running its backward on a side stream (presight_b200/fused.py: the proposal levels' backward overlaps the
+# final level's hash scatter) waits for E instead of for everything queued on the main stream.
+_GRAD_EVENTS = {}
+
+
+def publish_grad_event(t: Tensor) -> None:
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    if len(_GRAD_EVENTS) > 64:
+        _GRAD_EVENTS.clear()
+    _GRAD_EVENTS[t.data_ptr()] = ev
+
+
+def pop_grad_event(t: Tensor):
+    return _GRAD_EVENTS.pop(t.data_ptr(), None)
+
+
+_SIDE_STREAMS = {}
+
+
+def side_stream(device) -> "torch.cuda.Stream":
+    key = torch.device(device).index
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 class _InterlevelLoss(torch.autograd.Function):
     """mean(lossfun_outer(c, w, t_env, w_env)) (model_components/losses.py:80-126) with the gradient w.r.t. the
     proposal weights produced in the same kernel; c and w are constants (the reference detaches them)."""
@@ -410,7 +438,7 @@ class _InterlevelLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, c, w, t_env, w_env):
         c, w, t_env, we = _f32c(c.detach()), _f32c(w.detach()), _f32c(t_env.detach()), _f32c(w_env.detach())
-        N, S = w.shape
+        N, S = w.shape[0], w.shape[1]
         Sp = we.shape[1]
         loss = torch.zeros(1, device=w.device, dtype=torch.float32)
         need = ctx.needs_input_grad[3]
@@ -425,11 +453,14 @@ class _InterlevelLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (grad,) = ctx.saved_tensors
-        return None, None, None, grad * (g * ctx.scale)
+        out = grad * (g * ctx.scale)
+        publish_grad_event(out)
+        return None, None, None, out
 
 
 def interlevel_loss_level(c: Tensor, w: Tensor, t_env: Tensor, w_env: Tensor) -> Tensor:
-    """One proposal level's term of interlevel_loss: c [N,S+1], w [N,S], t_env [N,Sp+1], w_env [N,Sp] -> scalar."""
+    """One proposal level's term of interlevel_loss: c [N,S+1], w [N,S], t_env [N,Sp+1], w_env [N,Sp] or [N,Sp,1]
+    (the gradient comes back in w_env's shape) -> scalar."""
     return _InterlevelLoss.apply(c, w, t_env, w_env)
 
 
