@@ -28,6 +28,7 @@ _f32c = ops._f32c
 USE_TC5_FIELD = os.environ.get("PS_TC5_FIELD", "1") == "1"
 USE_TC5_PROP = os.environ.get("PS_TC5_PROP", "1") == "1"
 OVERLAP_PROP_BWD = os.environ.get("PS_OVERLAP_PROP_BWD", "1") == "1"
+FIELD_CHUNKS = max(1, int(os.environ.get("PS_FIELD_CHUNKS", "3")))
 
 
 @dataclass(frozen=True)
@@ -191,7 +192,7 @@ class _PropLevelTc5(torch.autograd.Function):
         # the producer of `dw` published its completion event, run this backward on a side stream so that it overlaps
         # the field kernels / main hash scatter already queued on the main stream.
         ev_in = ops.pop_grad_event(dw) if OVERLAP_PROP_BWD else None
-        run_on = ops.side_stream(eu.device) if ev_in is not None else main
+        run_on = ops.side_stream(eu.device, 1) if ev_in is not None else main
         with torch.cuda.stream(run_on):
             if ev_in is not None:
                 run_on.wait_event(ev_in)
@@ -383,26 +384,63 @@ def tc5_field_forward(o, d, eu, app_c, table, aabb, contract, grid: GridMeta, ws
     return x01, sel, feat, w, rgb_out, acc, dexp, dthr, sem_out, tmm
 
 
+def _chunk_bounds(N: int, S: int) -> List[Tuple[int, int]]:
+    """Ray ranges of the software pipeline between the hash kernels and the field kernels: FIELD_CHUNKS equal slices
+    (multiples of 128 rays) for large batches, one slice otherwise."""
+    k = FIELD_CHUNKS if N * S >= (1 << 21) else 1
+    step = ((N + k - 1) // k + 127) // 128 * 128
+    return [(c0, min(c0 + step, N)) for c0 in range(0, N, step)]
+
+
 class _FieldLevelTc5(torch.autograd.Function):
     """Final level on the fused tcgen05 kernels: ray_points -> hash gather -> ONE field+compositing kernel; backward =
     ONE kernel (recompute + all gradients) -> hash scatter.  Saved for backward: bins, unit-cube points, selector and
-    the hash features only."""
+    the hash features only.
+
+    The hash kernels (bound by L2 gather / atomic throughput, few registers, no shared memory) and the field kernels
+    (bound by the latency of their GEMM -> epilogue chain, one CTA per SM) use disjoint resources, so the batch is cut
+    into ray slices and in the backward the two kernel families run as a two-stage pipeline on two streams: the scatter
+    of slice c overlaps the field backward of slice c+1 (tools/overlap_probe.py: 2.66 ms -> 2.01 ms for 32k rays)."""
 
     @staticmethod
     def forward(ctx, origins, dirs, eu_bins, app, table, aabb, contract, grid: GridMeta, threshold, *params):
+        import ctypes as C
+        from ._lib import host_field_net
         o, d, eu = _f32c(origins.detach()), _f32c(dirs.detach()), _f32c(eu_bins.detach())
         N, S = eu.shape[0], eu.shape[1] - 1
+        dev = eu.device
         ws = [p.detach() for p in params[:8]]
         bs = [p.detach() for p in params[8:]]
         A = 0 if app is None else app.shape[1]
         app_c = None if app is None else _f32c(app.detach())
-        x01, sel, feat, w, rgb_out, acc, dexp, dthr, sem_out, tmm = tc5_field_forward(
-            o, d, eu, app_c, table.detach(), aabb, contract, grid, ws, bs, A, threshold)
-        saved = [eu, d, x01, sel, feat, acc, dexp, table]
+        tab = table.detach()
+        x01, sel = _ray_points(o, d, eu, aabb, contract)
+        w = torch.empty(N, S, device=dev, dtype=torch.float32)
+        rgb_out = torch.empty(N, 3, device=dev, dtype=torch.float32)
+        acc = torch.empty(N, 1, device=dev, dtype=torch.float32)
+        dexp = torch.empty(N, 1, device=dev, dtype=torch.float32)
+        dthr = torch.empty(N, 1, device=dev, dtype=torch.float32)
+        sem_out = torch.empty(N, 64, device=dev, dtype=torch.float32)
+        tmm = torch.tensor([float("inf"), float("-inf")], device=dev, dtype=torch.float32)
+        net = host_field_net(ws, bs, A)
+        bounds = _chunk_bounds(N, S)
+        feats = []
+        for (c0, c1) in bounds:
+            # (forward: the gather wants the L1 carve-out, the field kernel the shared-memory one — the two do not
+            # co-run, measured with tools/overlap_probe.py — so the slices simply alternate on one stream)
+            f = _hash_fwd_lm(x01[c0 * S:c1 * S], tab, grid)
+            feats.append(f)
+            with ops._probe("field_level_fwd"):
+                call("ps_field_level_fwd", C.byref(net), ptr(f), grid.L, grid.F, ptr(sel[c0 * S:c1 * S]),
+                     ptr(eu[c0:c1]), ptr(d[c0:c1]), None if app_c is None else ptr(app_c[c0:c1]), c1 - c0, S,
+                     float(threshold), ptr(w[c0:c1]), ptr(rgb_out[c0:c1]), ptr(acc[c0:c1]), ptr(dexp[c0:c1]),
+                     ptr(dthr[c0:c1]), ptr(sem_out[c0:c1]), ptr(tmm), stream())
+        saved = [eu, d, x01, sel, acc, dexp, table]
         if app_c is not None:
             saved.append(app_c)
-        ctx.save_for_backward(*saved, *params)
-        ctx.meta = (grid, N, S, A, len(saved), app is not None and app.requires_grad)
+        ctx.n_fixed = len(saved)
+        ctx.save_for_backward(*saved, *feats, *params)
+        ctx.meta = (grid, N, S, A, bounds, app is not None and app.requires_grad)
         ctx.mark_non_differentiable(dthr, tmm)
         return w.view(N, S, 1), rgb_out, acc, dexp, dthr, sem_out, tmm
 
@@ -410,23 +448,46 @@ class _FieldLevelTc5(torch.autograd.Function):
     def backward(ctx, dw, drgb, dacc, ddexp, _dthr, dsem, _dtmm):
         import ctypes as C
         from ._lib import host_field_net
-        grid, N, S, A, n_saved, app_grad = ctx.meta
+        grid, N, S, A, bounds, app_grad = ctx.meta
         saved = list(ctx.saved_tensors)
-        params = saved[n_saved:]
-        eu, d, x01, sel, feat, acc, dexp, table = saved[:8]
-        app_c = saved[8] if A else None
+        nf, nc = ctx.n_fixed, len(bounds)
+        eu, d, x01, sel, acc, dexp, table = saved[:7]
+        app_c = saved[7] if A else None
+        feats = saved[nf:nf + nc]
+        params = saved[nf + nc:]
+        dev = eu.device
         ws = [p.detach() for p in params[:8]]
         bs = [p.detach() for p in params[8:]]
         dW = [torch.zeros_like(w) for w in ws]
         dB = [torch.zeros_like(b) for b in bs]
-        dfeat = torch.empty_like(feat)
-        dapp = torch.zeros(N, A, device=eu.device, dtype=torch.float32) if (A and app_grad) else None
+        dapp = torch.zeros(N, A, device=dev, dtype=torch.float32) if (A and app_grad) else None
         net = host_field_net(ws, bs, A, dW, dB)
-        with ops._probe("field_level_bwd"):
-            call("ps_field_level_bwd", C.byref(net), ptr(feat), grid.L, grid.F, ptr(sel), ptr(eu), ptr(d), ptr(app_c), N,
-                 S, ptr(acc), ptr(dexp), ptr(_f32c(dw).view(N, S)), ptr(_f32c(drgb)), ptr(_f32c(dacc)),
-                 ptr(_f32c(ddexp)), ptr(_f32c(dsem)), ptr(dfeat), ptr(dapp), stream())
-        dtable = _hash_bwd_lm(x01, dfeat, table, grid)
+        dwc, drgbc, daccc, ddexpc, dsemc = (_f32c(dw).view(N, S), _f32c(drgb), _f32c(dacc), _f32c(ddexp), _f32c(dsem))
+        main = torch.cuda.current_stream()
+        piped = nc > 1
+        side = ops.side_stream(dev, 0) if piped else main
+        with torch.cuda.stream(side):
+            dtable = torch.zeros_like(table)          # (the 512 MiB memset runs under the first field slice)
+        for i, (c0, c1) in enumerate(bounds):
+            dfeat = torch.empty_like(feats[i])
+            with ops._probe("field_level_bwd"):
+                call("ps_field_level_bwd", C.byref(net), ptr(feats[i]), grid.L, grid.F, ptr(sel[c0 * S:c1 * S]),
+                     ptr(eu[c0:c1]), ptr(d[c0:c1]), None if app_c is None else ptr(app_c[c0:c1]), c1 - c0, S,
+                     ptr(acc[c0:c1]), ptr(dexp[c0:c1]), ptr(dwc[c0:c1]), ptr(drgbc[c0:c1]), ptr(daccc[c0:c1]),
+                     ptr(ddexpc[c0:c1]), ptr(dsemc[c0:c1]), ptr(dfeat), None if dapp is None else ptr(dapp[c0:c1]),
+                     stream())
+            if piped:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                dfeat.record_stream(side)
+            with torch.cuda.stream(side):
+                with ops._probe(f"hash_bwd_L{grid.L}F{grid.F}T{grid.log2_T}"):
+                    call("ps_hash_bwd_lm", ptr(x01[c0 * S:c1 * S]), (c1 - c0) * S, None, host_floats(grid.scalings), grid.L,
+                         grid.F, grid.log2_T, ptr(dfeat), ptr(dtable), None, side.cuda_stream)
+        if piped:
+            dtable.record_stream(main)
+            main.wait_stream(side)
         return (None, None, None, dapp, dtable, None, None, None, None, *dW, *dB)
 
 

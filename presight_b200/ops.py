@@ -424,8 +424,8 @@ def pop_grad_event(t: Tensor):
 _SIDE_STREAMS = {}
 
 
-def side_stream(device) -> "torch.cuda.Stream":
-    key = torch.device(device).index
+def side_stream(device, idx: int = 0) -> "torch.cuda.Stream":
+    key = (torch.device(device).index, idx)
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
     return _SIDE_STREAMS[key]
