@@ -267,6 +267,10 @@ def main() -> None:
     launches0 = ops.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_host0 = time.perf_counter()
+    run_step(resident)                               # one more warm-up step, timed on the HOST with an empty launch queue:
+    t_host = time.perf_counter() - t_host0          # the Python / launch cost of a step (the GPU must exceed it to stay busy)
+    barrier()
     ev0.record()
     for _ in range(args.steps):
         run_step(resident)
@@ -323,7 +327,7 @@ def main() -> None:
                        "l2": "inputs larger than L2 (576 MiB of hash tables + grads re-zeroed every step)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": t_e2e / args.steps * 1e3},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": t_host * 1e3,
             "clocks": clock_info,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
