@@ -197,7 +197,8 @@ class _PropLevelTc5(torch.autograd.Function):
             if ev_in is not None:
                 run_on.wait_event(ev_in)
             dwc = _f32c(dw).view(N, S)
-            dws, dbs = [torch.zeros_like(t) for t in ws], [torch.zeros_like(t) for t in bs]
+            zs = _zeros_like_many([*ws, *bs])
+            dws, dbs = zs[:2], zs[2:]
             dtable = torch.zeros_like(table)
             net = host_prop_net(ws, bs, dws, dbs)
             with ops._probe(f"prop_level_bwd_S{S}"):
@@ -384,6 +385,17 @@ def tc5_field_forward(o, d, eu, app_c, table, aabb, contract, grid: GridMeta, ws
     return x01, sel, feat, w, rgb_out, acc, dexp, dthr, sem_out, tmm
 
 
+def _zeros_like_many(tensors: Sequence[Tensor]) -> List[Tensor]:
+    """Zero-filled buffers shaped like `tensors`, carved out of ONE allocation (one fill kernel instead of one each)."""
+    sizes = [((t.numel() + 3) // 4) * 4 for t in tensors]          # keep every view 16-byte aligned
+    flat = torch.zeros(sum(sizes), device=tensors[0].device, dtype=torch.float32)
+    out, off = [], 0
+    for t, n in zip(tensors, sizes):
+        out.append(flat[off:off + t.numel()].view(t.shape))
+        off += n
+    return out
+
+
 def _chunk_bounds(N: int, S: int) -> List[Tuple[int, int]]:
     """Ray ranges of the software pipeline between the hash kernels and the field kernels: FIELD_CHUNKS equal slices
     (multiples of 128 rays) for large batches, one slice otherwise."""
@@ -442,6 +454,7 @@ class _FieldLevelTc5(torch.autograd.Function):
         ctx.save_for_backward(*saved, *feats, *params)
         ctx.meta = (grid, N, S, A, bounds, app is not None and app.requires_grad)
         ctx.mark_non_differentiable(dthr, tmm)
+        ctx.set_materialize_grads(False)
         return w.view(N, S, 1), rgb_out, acc, dexp, dthr, sem_out, tmm
 
     @staticmethod
@@ -458,11 +471,20 @@ class _FieldLevelTc5(torch.autograd.Function):
         dev = eu.device
         ws = [p.detach() for p in params[:8]]
         bs = [p.detach() for p in params[8:]]
-        dW = [torch.zeros_like(w) for w in ws]
-        dB = [torch.zeros_like(b) for b in bs]
+        zs = _zeros_like_many([*ws, *bs])
+        dW, dB = zs[:8], zs[8:]
         dapp = torch.zeros(N, A, device=dev, dtype=torch.float32) if (A and app_grad) else None
         net = host_field_net(ws, bs, A, dW, dB)
-        dwc, drgbc, daccc, ddexpc, dsemc = (_f32c(dw).view(N, S), _f32c(drgb), _f32c(dacc), _f32c(ddexp), _f32c(dsem))
+
+        def opt(t, shape=None):      # upstream gradients that autograd did not produce stay NULL (set_materialize_grads)
+            if t is None:
+                return None
+            t = _f32c(t)
+            return t if shape is None else t.view(shape)
+        dwc, drgbc, daccc, ddexpc, dsemc = opt(dw, (N, S)), opt(drgb), opt(dacc), opt(ddexp), opt(dsem)
+
+        def sl(t, c0, c1):
+            return None if t is None else ptr(t[c0:c1])
         main = torch.cuda.current_stream()
         piped = nc > 1
         side = ops.side_stream(dev, 0) if piped else main
@@ -473,9 +495,8 @@ class _FieldLevelTc5(torch.autograd.Function):
             with ops._probe("field_level_bwd"):
                 call("ps_field_level_bwd", C.byref(net), ptr(feats[i]), grid.L, grid.F, ptr(sel[c0 * S:c1 * S]),
                      ptr(eu[c0:c1]), ptr(d[c0:c1]), None if app_c is None else ptr(app_c[c0:c1]), c1 - c0, S,
-                     ptr(acc[c0:c1]), ptr(dexp[c0:c1]), ptr(dwc[c0:c1]), ptr(drgbc[c0:c1]), ptr(daccc[c0:c1]),
-                     ptr(ddexpc[c0:c1]), ptr(dsemc[c0:c1]), ptr(dfeat), None if dapp is None else ptr(dapp[c0:c1]),
-                     stream())
+                     ptr(acc[c0:c1]), ptr(dexp[c0:c1]), sl(dwc, c0, c1), sl(drgbc, c0, c1), sl(daccc, c0, c1),
+                     sl(ddexpc, c0, c1), sl(dsemc, c0, c1), ptr(dfeat), sl(dapp, c0, c1), stream())
             if piped:
                 ev = torch.cuda.Event()
                 ev.record(main)

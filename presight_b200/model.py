@@ -68,6 +68,24 @@ class NerfactoNuscMSModelConfig:
     eval_num_rays_per_chunk: int = 1 << 15
 
 
+class _EmbeddingLookup(torch.autograd.Function):
+    """weight[idx] whose backward is one index_add_ (atomics) instead of torch's sort + segmented reduction — the tables
+    here have a handful of rows (cameras, videos) and tens of thousands of lookups per step."""
+
+    @staticmethod
+    def forward(ctx, weight, idx):
+        ctx.save_for_backward(idx)
+        ctx.shape = weight.shape
+        return weight.index_select(0, idx.reshape(-1)).view(*idx.shape, weight.shape[1])
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        gw = torch.zeros(ctx.shape, device=g.device, dtype=g.dtype)
+        gw.index_add_(0, idx.reshape(-1), g.reshape(-1, ctx.shape[1]))
+        return gw, None
+
+
 class Embedding(nn.Module):
     """nerfstudio/field_components/embedding.py:24-55."""
 
@@ -80,6 +98,8 @@ class Embedding(nn.Module):
         return self.embedding.weight.mean(dim)
 
     def forward(self, in_tensor: Tensor) -> Tensor:
+        if in_tensor.is_cuda and self.embedding.weight.requires_grad and torch.is_grad_enabled():
+            return _EmbeddingLookup.apply(self.embedding.weight, in_tensor)
         return self.embedding(in_tensor)
 
 
