@@ -8,7 +8,8 @@ plus the gradient all-reduce for N > 1; the optimizer is excluded.
   value     device-resident inputs, CUDA-event timed, max over ranks
   e2e       the same step through the public model API with HOST (pinned) ray batches copied in every step and the
             loss read back every step
-  roofline  dominant kernel (main-grid hash scatter-add), algorithmic bytes / CUDA-event duration vs measured HBM peak
+  roofline  dominant memory kernel (main-grid hash scatter-add), algorithmic bytes / CUDA-event duration vs measured HBM
+            peak; the kernel runs once per ray slice of the final level, concurrently with the field backward
   cpu_baseline  the oracle port of the reference's torch path, timed on this box's host cores on a bounded sample
 `--impl reference` times that CPU path alone (the reference arm of the harness).
 """
@@ -330,7 +331,11 @@ def main() -> None:
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": t_host * 1e3,
             "clocks": clock_info,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                         "frac": (achieved / peak) if achieved else None,
+                         # dram__bytes_read + write of ONE slice launch (21 846 rays) from the ncu --set full capture
+                         # profiles/r1_final_kernels_ncu_summary.jsonl (475.2 MB + 192.1 MB); valid for the default C2 run
+                         "traffic": 667.3e6 if (args.config == "c2" and rays_per_rank == 65536) else None,
+                         "peak_source": peak_src,
                          "kernel_ms": k_ms, "launches_per_step": (n_launch / args.steps) if n_launch else None,
                          "algorithmic_bytes_per_launch": algo_bytes / max(1.0, n_launch / args.steps) if n_launch else None,
                          "algorithmic_bytes_per_step": algo_bytes,
