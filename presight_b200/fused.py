@@ -208,9 +208,10 @@ class _PropLevelTc5(torch.autograd.Function):
             if ev_in is not None:
                 done = torch.cuda.Event()
                 done.record(run_on)
-                for t in (dtable, *dws, *dbs):
-                    t.record_stream(main)
-                dw.record_stream(run_on)
+                if not torch.cuda.is_current_stream_capturing():
+                    for t in (dtable, *dws, *dbs):
+                        t.record_stream(main)
+                    dw.record_stream(run_on)
         if ev_in is not None:
             main.wait_event(done)
         return (None, None, None, dtable, None, None, None, dws[0], dbs[0], dws[1], dbs[1])
@@ -267,7 +268,7 @@ class _FieldLevel(torch.autograd.Function):
         dexp = torch.empty(N, 1, device=dev, dtype=torch.float32)
         dthr = torch.empty(N, 1, device=dev, dtype=torch.float32)
         sem_out = torch.empty(N, C, device=dev, dtype=torch.float32) if C else torch.empty(0, device=dev)
-        tmm = torch.tensor([float("inf"), float("-inf")], device=dev, dtype=torch.float32)
+        tmm = ops.new_tminmax(dev)
         with ops._probe("composite_fwd"):
             call("ps_composite_fwd", ptr(eu), ptr(density), ptr(rgb_s), ptr(sem_s), N, S, C, float(threshold), ptr(w),
                  ptr(rgb_out), ptr(acc), ptr(dexp), ptr(dthr), ptr(sem_out) if C else None, ptr(tmm), stream())
@@ -377,7 +378,7 @@ def tc5_field_forward(o, d, eu, app_c, table, aabb, contract, grid: GridMeta, ws
     dexp = torch.empty(N, 1, device=dev, dtype=torch.float32)
     dthr = torch.empty(N, 1, device=dev, dtype=torch.float32)
     sem_out = torch.empty(N, 64, device=dev, dtype=torch.float32)
-    tmm = torch.tensor([float("inf"), float("-inf")], device=dev, dtype=torch.float32)
+    tmm = ops.new_tminmax(dev)
     net = host_field_net(ws, bs, A)
     with ops._probe("field_level_fwd"):
         call("ps_field_level_fwd", C.byref(net), ptr(feat), grid.L, grid.F, ptr(sel), ptr(eu), ptr(d), ptr(app_c), N, S,
@@ -433,7 +434,7 @@ class _FieldLevelTc5(torch.autograd.Function):
         dexp = torch.empty(N, 1, device=dev, dtype=torch.float32)
         dthr = torch.empty(N, 1, device=dev, dtype=torch.float32)
         sem_out = torch.empty(N, 64, device=dev, dtype=torch.float32)
-        tmm = torch.tensor([float("inf"), float("-inf")], device=dev, dtype=torch.float32)
+        tmm = ops.new_tminmax(dev)
         net = host_field_net(ws, bs, A)
         bounds = _chunk_bounds(N, S)
         feats = []
@@ -488,6 +489,9 @@ class _FieldLevelTc5(torch.autograd.Function):
         main = torch.cuda.current_stream()
         piped = nc > 1
         side = ops.side_stream(dev, 0) if piped else main
+        capturing = torch.cuda.is_current_stream_capturing()
+        if piped:
+            side.wait_stream(main)                    # fork (also what makes the side stream part of a graph capture)
         with torch.cuda.stream(side):
             dtable = torch.zeros_like(table)          # (the 512 MiB memset runs under the first field slice)
         for i, (c0, c1) in enumerate(bounds):
@@ -501,13 +505,15 @@ class _FieldLevelTc5(torch.autograd.Function):
                 ev = torch.cuda.Event()
                 ev.record(main)
                 side.wait_event(ev)
-                dfeat.record_stream(side)
+                if not capturing:
+                    dfeat.record_stream(side)
             with torch.cuda.stream(side):
                 with ops._probe(f"hash_bwd_L{grid.L}F{grid.F}T{grid.log2_T}"):
                     call("ps_hash_bwd_lm", ptr(x01[c0 * S:c1 * S]), (c1 - c0) * S, None, host_floats(grid.scalings), grid.L,
                          grid.F, grid.log2_T, ptr(dfeat), ptr(dtable), None, side.cuda_stream)
         if piped:
-            dtable.record_stream(main)
+            if not capturing:
+                dtable.record_stream(main)
             main.wait_stream(side)
         return (None, None, None, dapp, dtable, None, None, None, None, *dW, *dB)
 

@@ -67,6 +67,13 @@ def _probe(name: str):
     return _ProbeCtx(PROBE, name)
 
 
+def new_tminmax(dev) -> Tensor:
+    """[+inf, -inf] built on the device (fill kernels only, so it can be captured into a CUDA graph)."""
+    t = torch.full((2,), float("inf"), device=dev, dtype=torch.float32)
+    t[1:].fill_(float("-inf"))
+    return t
+
+
 def _f32c(t: Tensor) -> Tensor:
     if t.dtype != torch.float32:
         t = t.float()
@@ -362,7 +369,7 @@ class _Composite(torch.autograd.Function):
         dexp = torch.empty(N, 1, device=dev, dtype=torch.float32)
         dthr = torch.empty(N, 1, device=dev, dtype=torch.float32)
         sem_out = torch.empty(N, C, device=dev, dtype=torch.float32) if m is not None else None
-        tmm = torch.tensor([float("inf"), float("-inf")], device=dev, dtype=torch.float32)
+        tmm = new_tminmax(dev)
         call("ps_composite_fwd", ptr(b), ptr(s), ptr(r), ptr(m), N, S, C, float(threshold), ptr(w), ptr(rgb_out),
              ptr(acc), ptr(dexp), ptr(dthr), ptr(sem_out), ptr(tmm), stream())
         ctx.save_for_backward(b, s, acc, dexp, *(t for t in (r, m) if t is not None))
