@@ -61,21 +61,13 @@ struct BwdTmem {
     static_assert(end <= 512, "TMEM budget");
 };
 
-// 32 accumulator columns (bias included by the GEMM) -> ReLU (mask of the positive ones) -> bf16 -> tile columns
-// [c0, c0 + 32)
-__device__ __forceinline__ uint32_t relu_epilogue32(uint32_t trow, int c0, unsigned char* tile, int r) {
+// 32 accumulator columns (bias included by the GEMM) -> ReLU -> bf16 -> tile columns [c0, c0 + 32)
+__device__ __forceinline__ void relu_epilogue32(uint32_t trow, int c0, unsigned char* tile, int r) {
     float v[32];
     tmem_ld32_nowait(trow + c0, v);
     tmem_wait_ld();
-    uint32_t mask = 0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        if (v[i] > 0.f) mask |= 1u << i;
-        v[i] = fmaxf(v[i], 0.f);
-    }
-#pragma unroll
-    for (int i = 0; i < 32; i += 8) store_chunk(tile, kRows, r, c0 + i, v + i);
-    return mask;
+    for (int i = 0; i < 32; i += 8) store_chunk_relu(tile, kRows, r, c0 + i, v + i);
 }
 
 // warp column sums of v[0..32): lane l receives the total of column l
@@ -99,16 +91,15 @@ __device__ __forceinline__ float column_sums32(const float (&v)[32], int lane) {
     return t[0];
 }
 
-// input-gradient epilogue of a hidden layer: 32 accumulator columns -> ReLU mask -> bf16 dZ
-__device__ __forceinline__ void dgrad_epilogue32(uint32_t trow, int c0, uint32_t mask, unsigned char* dz_tile, int r) {
+// input-gradient epilogue of a hidden layer: 32 accumulator columns, gated by the sign of the layer's forward
+// activation (read back from its tile) -> bf16 dZ
+__device__ __forceinline__ void dgrad_epilogue32(uint32_t trow, int c0, const unsigned char* act_tile, unsigned char* dz_tile,
+                                                 int r) {
     float v[32];
     tmem_ld32_nowait(trow + c0, v);
     tmem_wait_ld();
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-        if (!((mask >> i) & 1u)) v[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; i += 8) store_chunk(dz_tile, kRows, r, c0 + i, v + i);
+    for (int i = 0; i < 32; i += 8) store_chunk_relu_grad(dz_tile, act_tile, kRows, r, c0 + i, v + i);
 }
 
 template <int K0>
@@ -215,7 +206,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
         FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(B0), kHid, kHid);
                       gemm_kk(tmem + TM::acc, aX0, kRows, wb + WL::b0, kHid, kHid, K0, true); umma_commit(bar))
         FB_WAIT()
-        const uint32_t m_b0 = relu_epilogue32(trow + TM::acc, 32 * half, H1, r);
+        relu_epilogue32(trow + TM::acc, 32 * half, H1, r);
         FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(B1), kBaseOut, kBaseOut);
                       gemm_kk(tmem + TM::acc, aH1, kRows, wb + WL::b1, kBaseOut, kBaseOut, kHid, true); umma_commit(bar))
         FB_WAIT()
@@ -250,7 +241,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
         const double dd_incl = warp_scan_incl((double)dd, lane);
         if (lane == 31) tails[warp * 2] = dd_incl;
         FB_WAIT()
-        const uint32_t m_r0 = relu_epilogue32(trow + TM::acc, 32 * half, A1, r);
+        relu_epilogue32(trow + TM::acc, 32 * half, A1, r);
         FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(R1), kHid, kHid);
                       gemm_kk(tmem + TM::acc, aA1, kRows, wb + WL::r1, kHid, kHid, kHid, true); umma_commit(bar))
         const int w_first = (warp / wpr) * wpr;
@@ -271,7 +262,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
         }
         const float tm = __fdiv_rn(__fadd_rn(t0, t1), 2.f);
         FB_WAIT()
-        const uint32_t m_r1 = relu_epilogue32(trow + TM::acc, 32 * half, A2, r);
+        relu_epilogue32(trow + TM::acc, 32 * half, A2, r);
         FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(R2), kRgbOut, kRgbOut);
                       gemm_kk(tmem + TM::acc, aA2, kRows, wb + WL::r2, kRgbOut, kRgbOut, kHid, true); umma_commit(bar))
         FB_WAIT()
@@ -298,12 +289,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
                       gemm_wgrad(tmem + TM::r2, aA2, aDZa, 16, acc_dw);
                       gemm_dbias(tmem + TM::r2, aDZa, oneh, R2, true))
         FB_WAIT()
-        dgrad_epilogue32(trow + TM::acc, 32 * half, m_r1, DZb, r);
+        dgrad_epilogue32(trow + TM::acc, 32 * half, A2, DZb, r);
         FB_SYNC_ISSUE(gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::r1, kHid, kHid, kHid, false); umma_commit(bar);
                       gemm_wgrad(tmem + TM::r1, aDZb, aA1, kHid, acc_dw);
                       gemm_dbias(tmem + TM::r2, aDZb, oneh, R1, true))
         FB_WAIT()
-        dgrad_epilogue32(trow + TM::acc, 32 * half, m_r0, DZa, r);
+        dgrad_epilogue32(trow + TM::acc, 32 * half, A1, DZa, r);
         FB_SYNC_ISSUE(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::r0, kHid, kRgbIn, kHid, false); umma_commit(bar);
                       gemm_wgrad(tmem + TM::r0, aDZa, aSH, 16, acc_dw);
                       gemm_wgrad(tmem + TM::r0 + 16, aDZa, aH, 16, acc_dw);
@@ -336,11 +327,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
         FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(S0), kHid, kHid);
                       gemm_kk(tmem + TM::acc, aH + 2 * CH, kRows, wb + WL::s0, kHid, kHid, kSem, true); umma_commit(bar))
         FB_WAIT()
-        const uint32_t m_s0 = relu_epilogue32(trow + TM::acc, 32 * half, A1, r);
+        relu_epilogue32(trow + TM::acc, 32 * half, A1, r);
         FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(S1), kHid, kHid);
                       gemm_kk(tmem + TM::acc, aA1, kRows, wb + WL::s1, kHid, kHid, kHid, true); umma_commit(bar))
         FB_WAIT()
-        const uint32_t m_s1 = relu_epilogue32(trow + TM::acc, 32 * half, A2, r);
+        relu_epilogue32(trow + TM::acc, 32 * half, A2, r);
         FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(S2), kSem, kSem);
                       gemm_kk(tmem + TM::acc, aA2, kRows, wb + WL::s2, kSem, kSem, kHid, true); umma_commit(bar))
         FB_WAIT()
@@ -369,7 +360,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
         const double gw_incl = warp_scan_incl((double)g * (double)w, lane);
         if (lane == 31) tails[warp * 2 + 1] = gw_incl;
         FB_WAIT()
-        dgrad_epilogue32(trow + TM::acc, 32 * half, m_s1, DZa, r);
+        dgrad_epilogue32(trow + TM::acc, 32 * half, A2, DZa, r);
         FB_SYNC_ISSUE(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::s1, kHid, kHid, kHid, false); umma_commit(bar);
                       gemm_wgrad(tmem + TM::s1, aDZa, aA1, kHid, acc_dw);
                       gemm_dbias(tmem + TM::r2, aDZa, oneh, S1, true))
@@ -386,7 +377,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
             d_raw = valid ? d_sigma * selv * expf(fminf(fmaxf(raw, -15.f), 15.f)) : 0.f;
         }
         FB_WAIT()
-        dgrad_epilogue32(trow + TM::acc, 32 * half, m_s0, DZb, r);
+        dgrad_epilogue32(trow + TM::acc, 32 * half, A1, DZb, r);
         FB_SYNC_ISSUE(gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::s0, kHid, kSem, kHid, false); umma_commit(bar);
                       gemm_wgrad(tmem + TM::s0, aDZb, aH + 2 * CH, kSem, acc_dw);
                       gemm_dbias(tmem + TM::r2, aDZb, oneh, S0, true))
@@ -415,7 +406,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
                       gemm_wgrad(tmem + TM::b1, aDZa, aH1, kHid, acc_dw);
                       gemm_dbias(tmem + TM::r2, aDZa, oneh, B1, true))
         FB_WAIT()
-        dgrad_epilogue32(trow + TM::acc, 32 * half, m_b0, DZb, r);
+        dgrad_epilogue32(trow + TM::acc, 32 * half, H1, DZb, r);
         // last layer: the weight-gradient GEMM goes first so the final wait also covers it (X0 is restaged next tile)
         FB_SYNC_ISSUE(gemm_wgrad(tmem + TM::b0, aDZb, aX0, K0, acc_dw);
                       gemm_dbias(tmem + TM::r2, aDZb, oneh, B0, true);

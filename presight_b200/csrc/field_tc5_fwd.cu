@@ -41,9 +41,7 @@ __device__ __forceinline__ void hidden_epilogue64(uint32_t trow, unsigned char* 
         tmem_ld32_nowait(trow + c, v);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) store_chunk(tile, kRows, r, c + i, v + i);
+        for (int i = 0; i < 32; i += 8) store_chunk_relu(tile, kRows, r, c + i, v + i);
     }
 }
 

@@ -124,6 +124,38 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
     q.w = pack_bf16x2(v[6], v[7]);
     return q;
 }
+// packed epilogue arithmetic (two columns per instruction): ReLU on the bf16 pair, and "gradient through a ReLU" as a
+// multiply with hgt2(activation, 0) = {1.0, 0.0} — the activation pair is read back from the forward tile, so no mask
+// registers are carried from the forward pass.  Both give bit-identical results to the fp32 form followed by rounding.
+__device__ __forceinline__ uint32_t relu_pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __hmax2(__floats2bfloat162_rn(lo, hi), __floats2bfloat162_rn(0.f, 0.f));
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t relu_grad_pack_bf16x2(float lo, float hi, uint32_t act) {
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&act);
+    __nv_bfloat162 v = __hmul2(__floats2bfloat162_rn(lo, hi), __hgt2(a, __floats2bfloat162_rn(0.f, 0.f)));
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// ReLU + store of 8 consecutive columns
+__device__ __forceinline__ void store_chunk_relu(unsigned char* tile, int rows, int r, int c0, const float* v) {
+    uint4 q;
+    q.x = relu_pack_bf16x2(v[0], v[1]);
+    q.y = relu_pack_bf16x2(v[2], v[3]);
+    q.z = relu_pack_bf16x2(v[4], v[5]);
+    q.w = relu_pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(tile + cm_off(rows, r, c0)) = q;
+}
+// dz[c0..c0+8) = da * (act > 0), act read from the same position of the forward activation tile
+__device__ __forceinline__ void store_chunk_relu_grad(unsigned char* dz_tile, const unsigned char* act_tile, int rows, int r,
+                                                      int c0, const float* da) {
+    const uint4 a = *reinterpret_cast<const uint4*>(act_tile + cm_off(rows, r, c0));
+    uint4 q;
+    q.x = relu_grad_pack_bf16x2(da[0], da[1], a.x);
+    q.y = relu_grad_pack_bf16x2(da[2], da[3], a.y);
+    q.z = relu_grad_pack_bf16x2(da[4], da[5], a.z);
+    q.w = relu_grad_pack_bf16x2(da[6], da[7], a.w);
+    *reinterpret_cast<uint4*>(dz_tile + cm_off(rows, r, c0)) = q;
+}
 // store 8 consecutive columns [c0, c0+8) of row r of a chunk-major tile (c0 a multiple of 8)
 __device__ __forceinline__ void store_chunk(unsigned char* tile, int rows, int r, int c0, const float* v) {
     *reinterpret_cast<uint4*>(tile + cm_off(rows, r, c0)) = pack8(v);
