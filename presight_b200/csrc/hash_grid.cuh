@@ -136,16 +136,15 @@ __device__ __forceinline__ void scatter_row(float* __restrict__ level_grad, uint
     }
 }
 
-// scatter the (already weighted) gradient of the two x-corners of one (y,z) pair; `live_*` is false when the
-// corner's interpolation weight was exactly zero for every contributing sample (ceil == floor), in which case the
-// atomic is skipped
+// scatter the (already weighted) gradient of the two x-corners of one (y,z) pair.  The hash multiplies x by 1, so for an
+// even floor coordinate the two corners are rows r and r^1 — one aligned slot of 2F floats, ONE vector reduction.
+// (Corners whose interpolation weight is exactly zero — ceil == floor — contribute an exact 0.0, which leaves the table
+// value unchanged, so they are not special-cased.)
 template <int F>
 __device__ __forceinline__ void scatter_xpair(float* __restrict__ lg, uint32_t r_hi, uint32_t r_lo,
-                                              const float (&v_hi)[F], const float (&v_lo)[F], bool live_hi,
-                                              bool live_lo) {
+                                              const float (&v_hi)[F], const float (&v_lo)[F]) {
     if constexpr (F <= 2) {
-        if ((r_hi ^ r_lo) == 1u && live_hi && live_lo) {
-            // rows r and r^1: one aligned slot of 2F floats
+        if ((r_hi ^ r_lo) == 1u) {
             const uint32_t base = r_hi & ~1u;
             const bool hi_first = !(r_hi & 1u);
             if constexpr (F == 1)
@@ -156,8 +155,8 @@ __device__ __forceinline__ void scatter_xpair(float* __restrict__ lg, uint32_t r
             return;
         }
     }
-    if (live_hi) scatter_row<F>(lg, r_hi, v_hi, 1.f);
-    if (live_lo) scatter_row<F>(lg, r_lo, v_lo, 1.f);
+    scatter_row<F>(lg, r_hi, v_hi, 1.f);
+    scatter_row<F>(lg, r_lo, v_lo, 1.f);
 }
 
 // Segmented warp reduction: lanes of one segment (consecutive lanes, first lane flagged in `heads`) are summed
@@ -185,15 +184,11 @@ __device__ __forceinline__ void scatter_level_preagg(float* __restrict__ lg, con
                                                      float pz, float scale, const float (&g)[F], bool valid, int lane) {
     float w[8];
     corner_weights(c.ox, c.oy, c.oz, w);
-    // weighted per-corner gradients and "weight was non-zero" flags
     float v[8][F];
-    uint32_t live = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        if (w[k] != 0.f && valid) live |= 1u << k;
+    for (int k = 0; k < 8; ++k)
 #pragma unroll
         for (int f = 0; f < F; ++f) v[k][f] = valid ? g[f] * w[k] : 0.f;
-    }
     const int kx = (int)floorf(__fmul_rn(px, scale)), ky = (int)floorf(__fmul_rn(py, scale)),
               kz = (int)floorf(__fmul_rn(pz, scale));
     const int kf = (c.ox == 0.f ? 1 : 0) | (c.oy == 0.f ? 2 : 0) | (c.oz == 0.f ? 4 : 0) | (valid ? 0 : 8);
@@ -208,20 +203,14 @@ __device__ __forceinline__ void scatter_level_preagg(float* __restrict__ lg, con
         for (int k = 0; k < 8; ++k)
 #pragma unroll
             for (int f = 0; f < F; ++f) v[k][f] = seg_reduce(v[k][f], heads, lane);
-        // a corner is live for the run if it was live for any member
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t other = __shfl_down_sync(0xffffffffu, live, o);
-            if ((lane + o < 32) && ((((heads >> lane) >> 1) & ((1u << o) - 1u)) == 0u)) live |= other;
-        }
         issue = valid && !same_prev;
     }
     if (issue) {
         // (y,z) corner pairs in reference order: {x-ceil, x-floor} = {h0,h3}, {h1,h2}, {h4,h7}, {h5,h6}
-        scatter_xpair<F>(lg, c.row[0], c.row[3], v[0], v[3], live & 1u, live & 8u);
-        scatter_xpair<F>(lg, c.row[1], c.row[2], v[1], v[2], live & 2u, live & 4u);
-        scatter_xpair<F>(lg, c.row[4], c.row[7], v[4], v[7], live & 16u, live & 128u);
-        scatter_xpair<F>(lg, c.row[5], c.row[6], v[5], v[6], live & 32u, live & 64u);
+        scatter_xpair<F>(lg, c.row[0], c.row[3], v[0], v[3]);
+        scatter_xpair<F>(lg, c.row[1], c.row[2], v[1], v[2]);
+        scatter_xpair<F>(lg, c.row[4], c.row[7], v[4], v[7]);
+        scatter_xpair<F>(lg, c.row[5], c.row[6], v[5], v[6]);
     }
 }
 
