@@ -4,7 +4,8 @@
 // 286-314, 332-383, models/PreSight/nerfacto_nusc_ms.py:497-530.
 //
 // CTA = 256 threads = two independent groups of 128; a group owns one 128-point tile at a time (128 / S rays) with
-// one thread per point (row).  All eight layers run on tcgen05.mma (bf16 x bf16 -> fp32 in TMEM, M = 128); the
+// one thread per point (row).  All eight layers run on tcgen05.mma (bf16 x bf16 -> fp32 in TMEM, M = 128) in five
+// GEMM -> epilogue phases per tile (base 0, base 1, then the colour and the semantic head side by side); the
 // epilogues (ReLU, bf16 re-pack into the next layer's A tile; the bias is one more K step of the GEMM) are thread-per-row, so everything that is "per
 // sample" — density, weights, the dot products of compositing — is plain per-thread code.  While one group waits for
 // its MMA the other runs its epilogue; the weights (54 KB bf16) are staged once per CTA and shared by both groups.
@@ -166,9 +167,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
             store_chunk(Ht, kRows, t, 64, u);
             store_chunk(Ht, kRows, t, 72, u + 8);
         }
-        // semantic head layer 0 reads h[16:80] = chunks 2..9 of the H tile
-        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(S0), kHid, kHid);
-                      gemm_kk(tmem, aH + 2 * kRows * 16, kRows, wb + WL::s0, kHid, kHid, kSem, true))
+        // ---- both heads, layer by layer in the same phases (independent chains, two accumulators): the colour head
+        // [sh | h[0:16] | app] -> columns 0..63, the semantic head h[16:80] (chunks 2..9 of the H tile) -> columns 64..127
+        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(R0), kHid, kHid);
+                      gemm_kk(tmem, aSH, kRows, wb + WL::r0, kHid, kHid, 16, true);
+                      gemm_kk(tmem, aH, kRows, wb + WL::r0 + 2 * kHid * 16, kHid, kHid, 16, true);
+                      gemm_kk(tmem, aSH + 2 * kRows * 16, kRows, wb + WL::r0 + 4 * kHid * 16, kHid, kHid, 16, true);
+                      gemm_bias(tmem + 64, ones, wb + WL::bt(S0), kHid, kHid);
+                      gemm_kk(tmem + 64, aH + 2 * kRows * 16, kRows, wb + WL::s0, kHid, kHid, kSem, true))
         // ---- weights of this ray (overlaps the MMA): rays.py:138-148 -------------------------------------
         const float density = valid ? expf(raw) * selv : 0.f;
         const float dd = __fmul_rn(__fsub_rn(t1, t0), density);
@@ -199,11 +205,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
         if (lane == 31) tails[warp * 2 + 1] = w_incl;
         const float acc_w = warp_sum(w), dnum_w = warp_sum(w * tm);
         if (lane == 0) { red[warp * 72 + 64] = acc_w; red[warp * 72 + 65] = dnum_w; }
-        // ---- semantic head -------------------------------------------------------------------------------
         FT_WAIT()
-        hidden_epilogue64(trow, BufA, t);
-        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(S1), kHid, kHid);
-                      gemm_kk(tmem, aA, kRows, wb + WL::s1, kHid, kHid, kHid, true))
+        hidden_epilogue64(trow, BufA, t);            // colour hidden 1   (X0 is dead: its GEMM completed long ago)
+        hidden_epilogue64(trow + 64, BufB, t);       // semantic hidden 1 (H1 likewise)
+        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(R1), kHid, kHid);
+                      gemm_kk(tmem, aA, kRows, wb + WL::r1, kHid, kHid, kHid, true);
+                      gemm_bias(tmem + 64, ones, wb + WL::bt(S1), kHid, kHid);
+                      gemm_kk(tmem + 64, aB, kRows, wb + WL::s1, kHid, kHid, kHid, true))
         {   // (after the barrier inside FT_SYNC_ISSUE the weight tails of all warps are visible)
             double wc = 0.0;
             for (int k = w_first; k < warp; ++k) wc += tails[k * 2 + 1];
@@ -211,27 +219,33 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
             if (lane == 0) foundw[warp] = hit ? (warp - w_first) * 32 + __ffs(hit) - 1 : 0x7fffffff;
         }
         FT_WAIT()
-        hidden_epilogue64(trow, BufB, t);
-        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(S2), kSem, kSem);
-                      gemm_kk(tmem, aB, kRows, wb + WL::s2, kSem, kSem, kHid, true))
+        hidden_epilogue64(trow, BufA, t);            // hidden 2 of both heads, in place: the GEMMs that read the tiles
+        hidden_epilogue64(trow + 64, BufB, t);       // have completed
+        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(R2), kRgbOut, kRgbOut);
+                      gemm_kk(tmem, aA, kRows, wb + WL::r2, kRgbOut, kRgbOut, kHid, true);
+                      gemm_bias(tmem + 64, ones, wb + WL::bt(S2), kSem, kSem);
+                      gemm_kk(tmem + 64, aB, kRows, wb + WL::s2, kSem, kSem, kHid, true))
         FT_WAIT()
         {
             float v[64];
-            tmem_ld32_nowait(trow, *reinterpret_cast<float(*)[32]>(v));
-            tmem_ld32_nowait(trow + 32, *reinterpret_cast<float(*)[32]>(v + 32));
+            tmem_ld32_nowait(trow + 64, *reinterpret_cast<float(*)[32]>(v));
+            tmem_ld32_nowait(trow + 96, *reinterpret_cast<float(*)[32]>(v + 32));
+            float u[16];
+            tmem_ld16_nowait(trow, u);
             tmem_wait_ld();
 #pragma unroll
             for (int i = 0; i < 64; ++i) v[i] *= w;
             warp_transpose_reduce<64>(v, lane);
             red[warp * 72 + 2 * lane] = v[0];
             red[warp * 72 + 2 * lane + 1] = v[1];
+            float c3[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) c3[i] = warp_sum(w * sigmoid_f(u[i]));
+            if (lane == 0) { red[warp * 72 + 66] = c3[0]; red[warp * 72 + 67] = c3[1]; red[warp * 72 + 68] = c3[2]; }
         }
-        // ---- colour head: [sh | h[0:16] | app] ------------------------------------------------------------
-        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(R0), kHid, kHid);
-                      gemm_kk(tmem, aSH, kRows, wb + WL::r0, kHid, kHid, 16, true);
-                      gemm_kk(tmem, aH, kRows, wb + WL::r0 + 2 * kHid * 16, kHid, kHid, 16, true);
-                      gemm_kk(tmem, aSH + 2 * kRows * 16, kRows, wb + WL::r0 + 4 * kHid * 16, kHid, kHid, 16, true))
-        // per-ray semantics / accumulation / depths (the barrier above published red[] and foundw[])
+        fence_before();
+        bar_sync(barid, 128);          // red[] / foundw[] complete; every thread is done with the accumulators and tiles
+        // per-ray semantics / colour / accumulation / depths
         for (int i = t; i < rpt * 64; i += 128) {
             const int qq = i >> 6, c = i & 63;
             const int64_t rr = tile * rpt + qq;
@@ -239,7 +253,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
                 float sum = 0.f;
                 for (int k = 0; k < wpr; ++k) sum += red[(qq * wpr + k) * 72 + c];
                 a.sem_out[rr * kSem + c] = sum;
-                if (c == 0) {
+                if (c < 3) {
+                    float col = 0.f;
+                    for (int k = 0; k < wpr; ++k) col += red[(qq * wpr + k) * 72 + 66 + c];
+                    a.rgb_out[rr * 3 + c] = col;
+                }
+                if (c == 3) {
                     float accv = 0.f, dn = 0.f;
                     int fnd = 0x7fffffff;
                     for (int k = 0; k < wpr; ++k) {
@@ -253,35 +272,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
                     const float* b = a.eu + rr * (S + 1);
                     a.dthr[rr] = __fdiv_rn(__fadd_rn(__ldg(b + fnd), __ldg(b + fnd + 1)), 2.f);
                 }
-            }
-        }
-        FT_WAIT()
-        hidden_epilogue64(trow, BufA, t);
-        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(R1), kHid, kHid);
-                      gemm_kk(tmem, aA, kRows, wb + WL::r1, kHid, kHid, kHid, true))
-        FT_WAIT()
-        hidden_epilogue64(trow, BufB, t);
-        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(R2), kRgbOut, kRgbOut);
-                      gemm_kk(tmem, aB, kRows, wb + WL::r2, kRgbOut, kRgbOut, kHid, true))
-        FT_WAIT()
-        {
-            float u[16];
-            tmem_ld16_nowait(trow, u);
-            tmem_wait_ld();
-            float c3[3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) c3[i] = warp_sum(w * sigmoid_f(u[i]));
-            if (lane == 0) { red[warp * 72 + 66] = c3[0]; red[warp * 72 + 67] = c3[1]; red[warp * 72 + 68] = c3[2]; }
-        }
-        fence_before();
-        bar_sync(barid, 128);          // red[] complete; every thread is done with the accumulator and the tiles
-        if (t < rpt * 3) {
-            const int qq = t / 3, c = t - qq * 3;
-            const int64_t rr = tile * rpt + qq;
-            if (rr < a.N) {
-                float sum = 0.f;
-                for (int k = 0; k < wpr; ++k) sum += red[(qq * wpr + k) * 72 + 66 + c];
-                a.rgb_out[rr * 3 + c] = sum;
             }
         }
         bar_sync(barid, 128);          // red[] consumed before the next tile overwrites it
