@@ -158,49 +158,94 @@ __device__ __forceinline__ void load_all_weights(const FieldNet& net, unsigned c
     }
 }
 
-// stage this row's hash features (level-major [L][P][F] fp32) as bf16 into the first K0 columns of `tile`
+// Per-point / per-ray inputs of one row, loaded into registers in ONE batch (all global loads are issued before the
+// first is consumed: staged separately, each group of loads would expose its own global-memory latency).
 template <int K0>
-__device__ __forceinline__ void stage_features(const FieldArgs& a, int64_t P, int64_t p, bool valid, unsigned char* tile,
-                                               int r) {
-    float v[K0];
+struct RowInputs {
+    float feat[K0];
+    float dir[3];
+    float app[16];
+    float t0, t1, selv, gw;
+};
+
+template <int K0>
+__device__ __forceinline__ void load_row_inputs(const FieldArgs& a, int64_t P, int64_t ray, int s, bool valid,
+                                                bool want_feat, bool want_ray, RowInputs<K0>& in) {
 #pragma unroll
-    for (int c = 0; c < K0; ++c) v[c] = 0.f;
-    if (valid) {
+    for (int c = 0; c < K0; ++c) in.feat[c] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) in.app[c] = 0.f;
+    in.dir[0] = in.dir[1] = in.dir[2] = 0.f;
+    in.t0 = in.t1 = in.selv = in.gw = 0.f;
+    if (!valid) return;
+    const int64_t p = ray * a.S + s;
+    if (want_feat) {
         if (a.F == 2) {
 #pragma unroll
             for (int l = 0; l < K0 / 2; ++l)
                 if (l < a.L) {
                     const float2 q = __ldg(reinterpret_cast<const float2*>(a.feat + ((int64_t)l * P + p) * 2));
-                    v[2 * l] = q.x;
-                    v[2 * l + 1] = q.y;
+                    in.feat[2 * l] = q.x;
+                    in.feat[2 * l + 1] = q.y;
                 }
         } else {  // F == 4
 #pragma unroll
             for (int l = 0; l < K0 / 4; ++l)
                 if (l < a.L) {
                     const float4 q = __ldg(reinterpret_cast<const float4*>(a.feat + ((int64_t)l * P + p) * 4));
-                    v[4 * l] = q.x; v[4 * l + 1] = q.y; v[4 * l + 2] = q.z; v[4 * l + 3] = q.w;
+                    in.feat[4 * l] = q.x; in.feat[4 * l + 1] = q.y; in.feat[4 * l + 2] = q.z; in.feat[4 * l + 3] = q.w;
                 }
         }
     }
+    if (want_ray) {
+        in.dir[0] = __ldg(a.dirs + 3 * ray);
+        in.dir[1] = __ldg(a.dirs + 3 * ray + 1);
+        in.dir[2] = __ldg(a.dirs + 3 * ray + 2);
+        if (a.app)
 #pragma unroll
-    for (int c = 0; c < K0; c += 8) store_chunk(tile, kRows, r, c, v + c);
+            for (int c = 0; c < 16; ++c)
+                if (c < a.net.app_dim) in.app[c] = __ldg(a.app + ray * a.net.app_dim + c);
+    }
+    in.t0 = __ldg(a.eu + ray * (a.S + 1) + s);
+    in.t1 = __ldg(a.eu + ray * (a.S + 1) + s + 1);
+    in.selv = a.sel ? (float)a.sel[p] : 1.f;
+    if (a.d_w) in.gw = __ldg(a.d_w + p);
 }
 
-// stage [sh16(direction) | appearance (zero padded to 16)] of this row's ray into the 32-column SHAPP tile
-__device__ __forceinline__ void stage_shapp(const FieldArgs& a, int64_t ray, bool valid, unsigned char* tile, int r) {
+// per-ray inputs only (view direction, appearance embedding)
+template <int K0>
+__device__ __forceinline__ void load_ray_inputs(const FieldArgs& a, int64_t ray, bool valid, RowInputs<K0>& in) {
+    if (!valid) return;
+    in.dir[0] = __ldg(a.dirs + 3 * ray);
+    in.dir[1] = __ldg(a.dirs + 3 * ray + 1);
+    in.dir[2] = __ldg(a.dirs + 3 * ray + 2);
+    if (a.app)
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+            if (c < a.net.app_dim) in.app[c] = __ldg(a.app + ray * a.net.app_dim + c);
+}
+
+// features -> bf16 -> the first K0 columns of `tile`
+template <int K0>
+__device__ __forceinline__ void stage_features(const RowInputs<K0>& in, unsigned char* tile, int r) {
+#pragma unroll
+    for (int c = 0; c < K0; c += 8) store_chunk(tile, kRows, r, c, in.feat + c);
+}
+
+// [sh16(direction) | appearance (zero padded to 16)] of this row's ray -> the 32-column SHAPP tile
+template <int K0>
+__device__ __forceinline__ void stage_shapp(const RowInputs<K0>& in, bool valid, unsigned char* tile, int r) {
     float v[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) v[c] = 0.f;
     if (valid) {
         float sh[16];
-        sh4_of_direction(__ldg(a.dirs + 3 * ray), __ldg(a.dirs + 3 * ray + 1), __ldg(a.dirs + 3 * ray + 2), sh);
+        sh4_of_direction(in.dir[0], in.dir[1], in.dir[2], sh);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] = sh[c];
-        if (a.app)
-#pragma unroll
-            for (int c = 0; c < 16; ++c)
-                if (c < a.net.app_dim) v[16 + c] = __ldg(a.app + ray * a.net.app_dim + c);
+        for (int c = 0; c < 16; ++c) {
+            v[c] = sh[c];
+            v[16 + c] = in.app[c];
+        }
     }
 #pragma unroll
     for (int c = 0; c < 32; c += 8) store_chunk(tile, kRows, r, c, v + c);

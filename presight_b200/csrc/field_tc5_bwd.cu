@@ -42,7 +42,7 @@ struct BwdSmem {
     static constexpr uint32_t dots = raw + 128 * 4;                      // float [3][128]: sem half 0, sem half 1, rgb
     static constexpr uint32_t tails = dots + 3 * 128 * 4;                // double [2 halves][4 warps][2]
     static constexpr uint32_t bars = tails + 2 * 4 * 2 * 8;              // mbarrier + tmem slot
-    static constexpr uint32_t total = bars + 32;
+    static constexpr uint32_t total = bars + 48;
 };
 
 // TMEM columns: working accumulator first, then the weight-gradient accumulators
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
     float* dots = reinterpret_cast<float*>(smem + SM::dots);
     double* tails = reinterpret_cast<double*>(smem + SM::tails) + half * 8;
     uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(smem + SM::bars);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::bars + 16);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::bars + 24);
 
     load_all_weights<K0>(a.net, wbase, tid, kBwdThreads);
     // The bias-gradient GEMMs of all layers share one accumulator and read their dZ operand with M = 128: rows past a
@@ -135,6 +135,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
     if (tid < 32) tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
         mbar_init(smem_u32(bar_ptr), 1);
+        mbar_init(smem_u32(bar_ptr + 1), 1);
+        mbar_init(smem_u32(bar_ptr + 2), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_async_smem();
@@ -143,12 +145,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
     fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    const uint32_t bar = smem_u32(bar_ptr);
+    const uint32_t bar = smem_u32(bar_ptr), barB0 = smem_u32(bar_ptr + 1), barB1 = smem_u32(bar_ptr + 2);
     const uint32_t wb = smem_u32(wbase), ones = wb + WL::ones, oneh = wb + WL::onehot;
     const uint32_t aDZa = smem_u32(DZa), aDZb = smem_u32(DZb), aA1 = smem_u32(A1), aA2 = smem_u32(A2),
                    aX0 = smem_u32(X0), aH1 = smem_u32(H1), aH = smem_u32(Ht), aSH = smem_u32(SHAPPt);
     constexpr uint32_t CH = kRows * 16;     // bytes per 8-column chunk of a 128-row tile
-    uint32_t phase = 0;
+    uint32_t phase = 0, phaseB0 = 0, phaseB1 = 0;
 
     const int S = a.S;
     const int rpt = kRows / S, rows_used = rpt * S, wpr = S / 32;
@@ -169,6 +171,32 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
     mbar_wait(bar, phase);  \
     phase ^= 1;             \
     fence_after();
+// Two issuing threads.  A single thread pays ~100 cycles per tcgen05.mma it issues, and a tile needs ~220 of them: the
+// forward / input-gradient GEMMs (whose results the epilogues wait for) are issued by thread 0, the weight- and
+// bias-gradient GEMMs (results needed only at the end of the kernel) by thread 128, each with its own commit barrier.
+// The B groups are waited one phase late, just before the tiles they read can be rewritten; they alternate between two
+// mbarriers (KB = 0, 1) so that a barrier never completes two phases before every thread has observed the first.
+#define FB_SYNC_ISSUE2(A_LIST, B_LIST, KB) \
+    fence_async_smem();                    \
+    fence_before();                        \
+    __syncthreads();                       \
+    if (tid == 0) {                        \
+        fence_after();                     \
+        A_LIST;                            \
+        umma_commit(bar);                  \
+    } else if (tid == 128) {               \
+        fence_after();                     \
+        B_LIST;                            \
+        umma_commit(KB ? barB1 : barB0);   \
+    }
+#define FB_WAIT_B(KB)                  \
+    if (KB) {                          \
+        mbar_wait(barB1, phaseB1);     \
+        phaseB1 ^= 1;                  \
+    } else {                           \
+        mbar_wait(barB0, phaseB0);     \
+        phaseB0 ^= 1;                  \
+    }
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const bool acc_dw = !first;
@@ -178,8 +206,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
         const bool valid = r < rows_used && ray < a.N;
         const int64_t p = ray * S + s;
         // ---- stage inputs ----------------------------------------------------------------------------------
-        if (half == 0) stage_features<K0>(a, P, p, valid, X0, r);
-        else stage_shapp(a, ray, valid, SHAPPt, r);
+        float t0, t1, selv, gw_in;
+        {
+            RowInputs<K0> in;
+            load_row_inputs<K0>(a, P, ray, s, valid, half == 0, half == 1, in);
+            if (half == 0) stage_features<K0>(in, X0, r);
+            else stage_shapp<K0>(in, valid, SHAPPt, r);
+            t0 = in.t0; t1 = in.t1; selv = in.selv; gw_in = in.gw;
+        }
         for (int i = tid; i < rpt * 72; i += kBwdThreads) {
             const int qq = i / 72, c = i - qq * 72;
             const int64_t rr = tile * rpt + qq;
@@ -193,13 +227,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
                 else if (c == 70) v = a.d_dexp ? 1.f / (__ldg(a.acc + rr) + 1e-10f) : 0.f;
             }
             rayc[i] = v;
-        }
-        float t0 = 0.f, t1 = 0.f, selv = 0.f, gw_in = 0.f;
-        if (valid) {
-            t0 = __ldg(a.eu + ray * (S + 1) + s);
-            t1 = __ldg(a.eu + ray * (S + 1) + s + 1);
-            selv = a.sel ? (float)a.sel[p] : 1.f;
-            gw_in = a.d_w ? __ldg(a.d_w + p) : 0.f;
         }
         const float* rc = rayc + (q < rpt ? q : 0) * 72;
         // ---- base network, forward --------------------------------------------------------------------------
@@ -285,22 +312,24 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
             store_chunk(DZa, kRows, r, 0, dz);
             store_chunk(DZa, kRows, r, 8, dz + 8);
         }
-        FB_SYNC_ISSUE(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::r2, kRgbOut, kHid, 16, false); umma_commit(bar);
-                      gemm_wgrad(tmem + TM::r2, aA2, aDZa, 16, acc_dw);
-                      gemm_dbias(tmem + TM::r2, aDZa, oneh, R2, true))
+        FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::r2, kRgbOut, kHid, 16, false),
+                       gemm_wgrad(tmem + TM::r2, aA2, aDZa, 16, acc_dw);
+                       gemm_dbias(tmem + TM::r2, aDZa, oneh, R2, true), 0)
         FB_WAIT()
         dgrad_epilogue32(trow + TM::acc, 32 * half, A2, DZb, r);
-        FB_SYNC_ISSUE(gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::r1, kHid, kHid, kHid, false); umma_commit(bar);
-                      gemm_wgrad(tmem + TM::r1, aDZb, aA1, kHid, acc_dw);
-                      gemm_dbias(tmem + TM::r2, aDZb, oneh, R1, true))
+        FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::r1, kHid, kHid, kHid, false),
+                       gemm_wgrad(tmem + TM::r1, aDZb, aA1, kHid, acc_dw);
+                       gemm_dbias(tmem + TM::r2, aDZb, oneh, R1, true), 1)
         FB_WAIT()
+        FB_WAIT_B(0)      // the r2 group (read DZa, A2) is complete: DZa may be rewritten
         dgrad_epilogue32(trow + TM::acc, 32 * half, A1, DZa, r);
-        FB_SYNC_ISSUE(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::r0, kHid, kRgbIn, kHid, false); umma_commit(bar);
-                      gemm_wgrad(tmem + TM::r0, aDZa, aSH, 16, acc_dw);
-                      gemm_wgrad(tmem + TM::r0 + 16, aDZa, aH, 16, acc_dw);
-                      gemm_wgrad(tmem + TM::r0 + 32, aDZa, aSH + 2 * CH, 16, acc_dw);
-                      gemm_dbias(tmem + TM::r2, aDZa, oneh, R0, true))
+        FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::r0, kHid, kRgbIn, kHid, false),
+                       gemm_wgrad(tmem + TM::r0, aDZa, aSH, 16, acc_dw);
+                       gemm_wgrad(tmem + TM::r0 + 16, aDZa, aH, 16, acc_dw);
+                       gemm_wgrad(tmem + TM::r0 + 32, aDZa, aSH + 2 * CH, 16, acc_dw);
+                       gemm_dbias(tmem + TM::r2, aDZa, oneh, R0, true), 0)
         FB_WAIT()
+        FB_WAIT_B(1)      // the r1 group (read DZb, A1) is complete
         float d_h01[16];   // half 0: gradient of h[0:16] from the colour head (column 0 is zero by construction)
         {
             float u[16];
@@ -327,6 +356,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
         FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(S0), kHid, kHid);
                       gemm_kk(tmem + TM::acc, aH + 2 * CH, kRows, wb + WL::s0, kHid, kHid, kSem, true); umma_commit(bar))
         FB_WAIT()
+        FB_WAIT_B(0)      // the r0 group (read DZa, SHAPP, H) is complete
         relu_epilogue32(trow + TM::acc, 32 * half, A1, r);
         FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(S1), kHid, kHid);
                       gemm_kk(tmem + TM::acc, aA1, kRows, wb + WL::s1, kHid, kHid, kHid, true); umma_commit(bar))
@@ -351,9 +381,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
 #pragma unroll
             for (int i = 0; i < 32; i += 8) store_chunk(DZb, kRows, r, 32 * half + i, v + i);
         }
-        FB_SYNC_ISSUE(gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::s2, kSem, kHid, kSem, false); umma_commit(bar);
-                      gemm_wgrad(tmem + TM::s2, aDZb, aA2, kHid, acc_dw);
-                      gemm_dbias(tmem + TM::r2, aDZb, oneh, S2, true))
+        FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::s2, kSem, kHid, kSem, false),
+                       gemm_wgrad(tmem + TM::s2, aDZb, aA2, kHid, acc_dw);
+                       gemm_dbias(tmem + TM::r2, aDZb, oneh, S2, true), 1)
         // compositing backward, pass 1 (the barrier above published dots[]): total gradient on this weight
         float g = gw_in + rc[67] + rc[68] * (tm - rc[69]) * rc[70] + dots[r] + dots[128 + r] + dots[256 + r];
         if (!finite) g = 0.f;
@@ -361,9 +391,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
         if (lane == 31) tails[warp * 2 + 1] = gw_incl;
         FB_WAIT()
         dgrad_epilogue32(trow + TM::acc, 32 * half, A2, DZa, r);
-        FB_SYNC_ISSUE(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::s1, kHid, kHid, kHid, false); umma_commit(bar);
-                      gemm_wgrad(tmem + TM::s1, aDZa, aA1, kHid, acc_dw);
-                      gemm_dbias(tmem + TM::r2, aDZa, oneh, S1, true))
+        FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::s1, kHid, kHid, kHid, false),
+                       gemm_wgrad(tmem + TM::s1, aDZa, aA1, kHid, acc_dw);
+                       gemm_dbias(tmem + TM::r2, aDZa, oneh, S1, true), 0)
         // pass 2: d sigma_i = delta_i * (g_i T_{i+1} - sum_{k>i} g_k w_k); d raw = d sigma * sel * exp(clamp(raw))
         float d_raw;
         {
@@ -377,11 +407,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
             d_raw = valid ? d_sigma * selv * expf(fminf(fmaxf(raw, -15.f), 15.f)) : 0.f;
         }
         FB_WAIT()
+        FB_WAIT_B(1)      // the s2 group (read DZb, A2) is complete: DZb may be rewritten
         dgrad_epilogue32(trow + TM::acc, 32 * half, A1, DZb, r);
-        FB_SYNC_ISSUE(gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::s0, kHid, kSem, kHid, false); umma_commit(bar);
-                      gemm_wgrad(tmem + TM::s0, aDZb, aH + 2 * CH, kSem, acc_dw);
-                      gemm_dbias(tmem + TM::r2, aDZb, oneh, S0, true))
+        FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::s0, kHid, kSem, kHid, false),
+                       gemm_wgrad(tmem + TM::s0, aDZb, aH + 2 * CH, kSem, acc_dw);
+                       gemm_dbias(tmem + TM::r2, aDZb, oneh, S0, true), 1)
         FB_WAIT()
+        FB_WAIT_B(0)      // the s1 group (read DZa, A1) is complete: DZa may take dH
         // ---- base network, backward: dH = [d raw | colour head (15) | semantic head (64)] ----------------------
         {
             float v[32];
@@ -402,16 +434,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
                 store_chunk(DZa, kRows, r, 8, u + 8);
             }
         }
-        FB_SYNC_ISSUE(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::b1, kBaseOut, kHid, kBaseOut, false); umma_commit(bar);
-                      gemm_wgrad(tmem + TM::b1, aDZa, aH1, kHid, acc_dw);
-                      gemm_dbias(tmem + TM::r2, aDZa, oneh, B1, true))
+        FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::b1, kBaseOut, kHid, kBaseOut, false),
+                       gemm_wgrad(tmem + TM::b1, aDZa, aH1, kHid, acc_dw);
+                       gemm_dbias(tmem + TM::r2, aDZa, oneh, B1, true), 0)
         FB_WAIT()
+        FB_WAIT_B(1)      // the s0 group (read DZb, H) is complete
         dgrad_epilogue32(trow + TM::acc, 32 * half, H1, DZb, r);
-        // last layer: the weight-gradient GEMM goes first so the final wait also covers it (X0 is restaged next tile)
-        FB_SYNC_ISSUE(gemm_wgrad(tmem + TM::b0, aDZb, aX0, K0, acc_dw);
-                      gemm_dbias(tmem + TM::r2, aDZb, oneh, B0, true);
-                      gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::b0, kHid, K0, kHid, false); umma_commit(bar))
+        FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::b0, kHid, K0, kHid, false),
+                       gemm_wgrad(tmem + TM::b0, aDZb, aX0, K0, acc_dw);
+                       gemm_dbias(tmem + TM::r2, aDZb, oneh, B0, true), 1)
         FB_WAIT()
+        FB_WAIT_B(0)      // the b1 group (read DZa, H1) ...
+        FB_WAIT_B(1)      // ... and the b0 group (read DZb, X0) are complete: every tile may be restaged
         // ---- hash-feature gradient (level-major [L][P][F]) ---------------------------------------------------
         if (a.dfeat) {
 #pragma unroll
@@ -445,7 +479,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
         __syncthreads();
     }
 #undef FB_SYNC_ISSUE
+#undef FB_SYNC_ISSUE2
 #undef FB_WAIT
+#undef FB_WAIT_B
 
     // ---- flush: weight and bias gradients (TMEM) -> global atomics ---------------------------------------------------
     if (!first) {

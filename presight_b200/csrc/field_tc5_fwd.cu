@@ -132,14 +132,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
         const int64_t ray = tile * rpt + q;
         const bool valid = t < rows_used && ray < a.N;
         const int64_t p = ray * S + s;
-        // ---- stage inputs -----------------------------------------------------------------------------
-        stage_features<K0>(a, P, p, valid, BufA, t);
-        stage_shapp(a, ray, valid, SHAPPt, t);
-        float t0 = 0.f, t1 = 0.f, selv = 0.f;
-        if (valid) {
-            t0 = __ldg(a.eu + ray * (S + 1) + s);
-            t1 = __ldg(a.eu + ray * (S + 1) + s + 1);
-            selv = a.sel ? (float)a.sel[p] : 1.f;
+        // ---- stage inputs (all global loads of the row in one batch) -----------------------------------
+        float t0, t1, selv;
+        {
+            RowInputs<K0> in;
+            load_row_inputs<K0>(a, P, ray, s, valid, true, true, in);
+            stage_features<K0>(in, BufA, t);
+            stage_shapp<K0>(in, valid, SHAPPt, t);
+            t0 = in.t0; t1 = in.t1; selv = in.selv;
         }
         // ---- base network ------------------------------------------------------------------------------
         FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(B0), kHid, kHid);

@@ -92,3 +92,61 @@ extern "C" int ps_tc5_probe(const float* X, const float* Y, const float* W, floa
     tc5::tc5_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(X, Y, W, C1, C2, C3, C4);
     return check_launch("tc5_probe");
 }
+
+// ---- timing probe: cycles per tcgen05.mma as a function of N and of the operand majorness (tools/mma_cost.py) --------
+namespace ps {
+namespace tc5 {
+__global__ void __launch_bounds__(128) mma_cost_kernel(int N, int mn_major, int n_mma, int same_acc, long long* out) {
+    extern __shared__ __align__(128) unsigned char smem[];      // 64 KB of zeros: operands
+    uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(smem + 65536);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar_ptr + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 65536 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    const uint32_t bar = smem_u32(bar_ptr);
+    if (warp == 0) tmem_alloc(slot, 512);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *slot;
+    if (tid == 0) {
+        const uint32_t a = smem_u32(smem), b = smem_u32(smem) + 32768;
+        const uint32_t idesc = make_idesc(N, mn_major, mn_major);
+        const long long t0 = clock64();
+        for (int i = 0; i < n_mma; ++i) {
+            const uint32_t d = tmem + (same_acc ? 0 : (i & 1) * 256);
+            if (mn_major)
+                umma_bf16(d, make_desc(a + (i & 7) * 256, 128, kRows * 16), make_desc(b + (i & 7) * 256, 128, kRows * 16), idesc, 1u);
+            else
+                umma_bf16(d, make_desc(a + (i & 3) * 4096, kRows * 16, 128), make_desc(b + (i & 3) * 4096, kRows * 16, 128), idesc, 1u);
+        }
+        const long long t1 = clock64();
+        umma_commit(bar);
+        mbar_wait(bar, 0);
+        const long long t2 = clock64();
+        out[0] = t1 - t0;
+        out[1] = t2 - t0;
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+}  // namespace tc5
+}  // namespace ps
+
+/* tools only (not declared in include/presight_b200.h) */
+extern "C" int ps_tc5_mma_cost(int N, int mn_major, int n_mma, int same_acc, long long* out, void* stream) {
+    using namespace ps;
+    const size_t smem = 65536 + 64;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(tc5::mma_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    tc5::mma_cost_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(N, mn_major, n_mma, same_acc, out);
+    return check_launch("tc5_mma_cost");
+}
