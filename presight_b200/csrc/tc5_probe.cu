@@ -96,7 +96,7 @@ extern "C" int ps_tc5_probe(const float* X, const float* Y, const float* W, floa
 // ---- timing probe: cycles per tcgen05.mma as a function of N and of the operand majorness (tools/mma_cost.py) --------
 namespace ps {
 namespace tc5 {
-__global__ void __launch_bounds__(128) mma_cost_kernel(int N, int mn_major, int n_mma, int same_acc, long long* out) {
+__global__ void __launch_bounds__(128) mma_cost_kernel(int N, int mn_major, int n_mma, int same_acc, int M, long long* out) {
     extern __shared__ __align__(128) unsigned char smem[];      // 64 KB of zeros: operands
     uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(smem + 65536);
     uint32_t* slot = reinterpret_cast<uint32_t*>(bar_ptr + 1);
@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(128) mma_cost_kernel(int N, int mn_major, int 
     const uint32_t tmem = *slot;
     if (tid == 0) {
         const uint32_t a = smem_u32(smem), b = smem_u32(smem) + 32768;
-        const uint32_t idesc = make_idesc(N, mn_major, mn_major);
+        // make_idesc encodes M = 128; patch the M field (bits 24..28 = M >> 4) for the M = 64 variant
+        const uint32_t idesc = (make_idesc(N, mn_major, mn_major) & ~(0x1Fu << 24)) | ((uint32_t)(M >> 4) << 24);
         const long long t0 = clock64();
         for (int i = 0; i < n_mma; ++i) {
             const uint32_t d = tmem + (same_acc ? 0 : (i & 1) * 256);
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(128) mma_cost_kernel(int N, int mn_major, int 
 }  // namespace ps
 
 /* tools only (not declared in include/presight_b200.h) */
-extern "C" int ps_tc5_mma_cost(int N, int mn_major, int n_mma, int same_acc, long long* out, void* stream) {
+extern "C" int ps_tc5_mma_cost(int N, int mn_major, int n_mma, int same_acc, int M, long long* out, void* stream) {
     using namespace ps;
     const size_t smem = 65536 + 64;
     static bool configured = false;
@@ -147,6 +148,6 @@ extern "C" int ps_tc5_mma_cost(int N, int mn_major, int n_mma, int same_acc, lon
         cudaFuncSetAttribute(tc5::mma_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
-    tc5::mma_cost_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(N, mn_major, n_mma, same_acc, out);
+    tc5::mma_cost_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(N, mn_major, n_mma, same_acc, M, out);
     return check_launch("tc5_mma_cost");
 }

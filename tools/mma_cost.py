@@ -6,15 +6,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from presight_b200 import _lib
 lib = _lib.load()
-lib.ps_tc5_mma_cost.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+lib.ps_tc5_mma_cost.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
 out = torch.zeros(2, dtype=torch.int64, device="cuda")
 n = 256
-for mn in (0, 1):
-    for same in (1, 0):
-        for N in (16, 32, 64, 80, 128, 256):
-            lib.ps_tc5_mma_cost(N, mn, n, same, out.data_ptr(), None)
+for M in (128, 64):
+    for mn in (0, 1):
+        for N in (16, 64, 128):
+            lib.ps_tc5_mma_cost(N, mn, n, 1, M, out.data_ptr(), None)
             torch.cuda.synchronize()
-            lib.ps_tc5_mma_cost(N, mn, n, same, out.data_ptr(), None)
+            lib.ps_tc5_mma_cost(N, mn, n, 1, M, out.data_ptr(), None)
             torch.cuda.synchronize()
             i, d = out.tolist()
-            print(f"{'MN' if mn else 'K '}-major same_acc={same} N={N:3d}: issue {i / n:6.1f} cyc/MMA, done {d / n:6.1f} cyc/MMA")
+            print(f"M={M:3d} {'MN' if mn else 'K '}-major N={N:3d}: issue {i / n:6.1f} cyc/MMA, done {d / n:6.1f} cyc/MMA")
