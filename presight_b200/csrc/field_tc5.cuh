@@ -74,8 +74,7 @@ struct FieldArgs {
 // [N x 16]: column 0 = bf16(b), column 1 = bf16(b - bf16(b)) — one extra K step of the forward GEMM against a constant
 // A operand whose first two columns are 1 adds the bias (to ~2^-17 relative) on the tensor core, so no epilogue touches
 // it.  `ones`: that constant A operand as one 128-byte core-matrix block {1,1,0,..} x 8 rows + a zero block (the
-// descriptor's row-group stride is 0, so all 128 rows alias the block).  `onehot`: per layer l a pair of blocks selecting
-// column 3 + l of a 16-column accumulator — the B operand of the bias-gradient GEMM dB_l = dZ_l^T 1 (zero K stride).
+// descriptor's row-group stride is 0, so all 128 rows alias the block).
 template <int K0>
 struct WLayout {
     static constexpr uint32_t b0 = 0;
@@ -88,8 +87,7 @@ struct WLayout {
     static constexpr uint32_t r2 = r1 + cm_bytes(kHid, kHid);
     static constexpr uint32_t bt0 = r2 + cm_bytes(kRgbOut, kHid);            // bias tiles, layer order B0..R2
     static constexpr uint32_t ones = bt0 + 480 * 32;                          // 256 B
-    static constexpr uint32_t onehot = ones + 256;                            // 8 x 256 B
-    static constexpr uint32_t end = onehot + 8 * 256;
+    static constexpr uint32_t end = ones + 256;
     __host__ __device__ static constexpr int rows(int l) {
         return l == B1 ? kBaseOut : (l == R2 ? kRgbOut : kHid);
     }
@@ -103,13 +101,6 @@ struct WLayout {
 // D[128 x N] = 1 * bias^T : the first K step of every forward GEMM (accumulate = false)
 __device__ __forceinline__ void gemm_bias(uint32_t tmem_d, uint32_t ones_addr, uint32_t bias_tile, int b_rows, int N) {
     umma_bf16(tmem_d, make_desc(ones_addr, 128, 0), make_desc(bias_tile, b_rows * 16, 128), make_idesc(N, 0, 0), 0u);
-}
-// dB (column 3 + l of the 16-column accumulator at tmem_d) += column sums of the dZ tile at dz_addr
-__device__ __forceinline__ void gemm_dbias(uint32_t tmem_d, uint32_t dz_addr, uint32_t onehot_addr, int l, bool accumulate) {
-    const uint32_t idesc = make_idesc(16, 1, 1);
-    const uint64_t db = make_desc(onehot_addr + l * 256, 0, 128);
-    for (int kk = 0; kk < kRows / 16; ++kk)
-        umma_bf16(tmem_d, make_desc(dz_addr + kk * 256, 128, kRows * 16), db, idesc, (accumulate || kk > 0) ? 1u : 0u);
 }
 
 template <int K0>
@@ -150,11 +141,6 @@ __device__ __forceinline__ void load_all_weights(const FieldNet& net, unsigned c
     // constant blocks: element e of a 128-byte block = row e / 8, column e % 8
     for (int i = tid; i < 128; i += nthreads) {
         reinterpret_cast<__nv_bfloat16*>(wbase + WL::ones)[i] = __float2bfloat16_rn((i < 64 && (i & 7) < 2) ? 1.f : 0.f);
-    }
-    for (int i = tid; i < 8 * 128; i += nthreads) {
-        const int l = i >> 7, e = i & 127, col = 3 + l;               // block 0: columns 0..7, block 1: columns 8..15
-        const int blk = e >> 6, c = (e & 7) + 8 * blk;
-        reinterpret_cast<__nv_bfloat16*>(wbase + WL::onehot)[i] = __float2bfloat16_rn(c == col ? 1.f : 0.f);
     }
 }
 

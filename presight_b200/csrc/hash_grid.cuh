@@ -159,20 +159,6 @@ __device__ __forceinline__ void scatter_xpair(float* __restrict__ lg, uint32_t r
     scatter_row<F>(lg, r_lo, v_lo, 1.f);
 }
 
-// Segmented warp reduction: lanes of one segment (consecutive lanes, first lane flagged in `heads`) are summed
-// into the segment's head lane.
-__device__ __forceinline__ float seg_reduce(float v, uint32_t heads, int lane) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const float other = __shfl_down_sync(0xffffffffu, v, o);
-        // add lane+o only if no segment starts in (lane, lane+o]
-        const bool same = (lane + o < 32) && ((((heads >> lane) >> 1) & ((1u << o) - 1u)) == 0u);
-        if (same) v += other;
-    }
-    return v;
-}
-
-
 // Scatter-add one level's feature gradient `g[F]` of this lane's point into the level's gradient table `lg`
 // (all 32 lanes must call; `valid` = this lane carries a real point).
 //  * warp pre-aggregation: consecutive samples of a ray that fall into the same grid cell hit the same 8 rows; they are
@@ -199,10 +185,21 @@ __device__ __forceinline__ void scatter_level_preagg(float* __restrict__ lg, con
     const uint32_t heads = __ballot_sync(0xffffffffu, !same_prev);
     bool issue = valid;
     if (heads != 0xffffffffu) {   // warp-uniform: at least one run of length > 1
+        // Segmented reduction into each run's first lane (all 8F values per step).  Only the butterfly
+        // steps the warp's longest run needs are executed: beyond it no lane has a same-run partner, so the skipped
+        // steps would add nothing (fine levels mostly have runs of 2: one step instead of five).
+        const int head_pos = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+        const int max_pos = __reduce_max_sync(0xffffffffu, lane - head_pos);
+        for (int o = 1; o <= max_pos; o <<= 1) {
+            const bool same = (lane + o < 32) && ((((heads >> lane) >> 1) & ((1u << o) - 1u)) == 0u);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < 8; ++k)
 #pragma unroll
-            for (int f = 0; f < F; ++f) v[k][f] = seg_reduce(v[k][f], heads, lane);
+                for (int f = 0; f < F; ++f) {
+                    const float other = __shfl_down_sync(0xffffffffu, v[k][f], o);
+                    if (same) v[k][f] += other;
+                }
+        }
         issue = valid && !same_prev;
     }
     if (issue) {

@@ -208,11 +208,12 @@ class _PropLevelTc5(torch.autograd.Function):
             if ev_in is not None:
                 done = torch.cuda.Event()
                 done.record(run_on)
-                if not torch.cuda.is_current_stream_capturing():
-                    for t in (dtable, *dws, *dbs):
-                        t.record_stream(main)
-                    dw.record_stream(run_on)
         if ev_in is not None:
+            # Join before returning: everything later on the main stream is ordered behind the side-stream kernel, so
+            # `dw` (a main-stream block read on the side stream) may be freed by autograd right away, and the outputs
+            # (side-stream blocks) are only ever reused by a later backward on the same side stream, which first waits
+            # for a later main-stream event.  No Tensor.record_stream: its deferred frees make the caching allocator fall
+            # back to cudaMalloc (a device-wide sync) whenever the host runs several steps ahead of the GPU.
             main.wait_event(done)
         return (None, None, None, dtable, None, None, None, dws[0], dbs[0], dws[1], dbs[1])
 
@@ -489,13 +490,14 @@ class _FieldLevelTc5(torch.autograd.Function):
         main = torch.cuda.current_stream()
         piped = nc > 1
         side = ops.side_stream(dev, 0) if piped else main
-        capturing = torch.cuda.is_current_stream_capturing()
         if piped:
             side.wait_stream(main)                    # fork (also what makes the side stream part of a graph capture)
         with torch.cuda.stream(side):
             dtable = torch.zeros_like(table)          # (the 512 MiB memset runs under the first field slice)
+        keep = []            # main-stream buffers read on the side stream: alive until the join below
         for i, (c0, c1) in enumerate(bounds):
             dfeat = torch.empty_like(feats[i])
+            keep.append(dfeat)
             with ops._probe("field_level_bwd"):
                 call("ps_field_level_bwd", C.byref(net), ptr(feats[i]), grid.L, grid.F, ptr(sel[c0 * S:c1 * S]),
                      ptr(eu[c0:c1]), ptr(d[c0:c1]), None if app_c is None else ptr(app_c[c0:c1]), c1 - c0, S,
@@ -505,16 +507,13 @@ class _FieldLevelTc5(torch.autograd.Function):
                 ev = torch.cuda.Event()
                 ev.record(main)
                 side.wait_event(ev)
-                if not capturing:
-                    dfeat.record_stream(side)
             with torch.cuda.stream(side):
                 with ops._probe(f"hash_bwd_L{grid.L}F{grid.F}T{grid.log2_T}"):
                     call("ps_hash_bwd_lm", ptr(x01[c0 * S:c1 * S]), (c1 - c0) * S, None, host_floats(grid.scalings), grid.L,
                          grid.F, grid.log2_T, ptr(dfeat), ptr(dtable), None, side.cuda_stream)
         if piped:
-            if not capturing:
-                dtable.record_stream(main)
-            main.wait_stream(side)
+            main.wait_stream(side)   # join (see _PropLevelTc5.backward for why no record_stream is needed)
+        del keep
         return (None, None, None, dapp, dtable, None, None, None, None, *dW, *dB)
 
 

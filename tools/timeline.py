@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Kernel timeline of ONE train step (kineto / CUPTI through torch.profiler; nsys is not in the image):
+prints every GPU kernel / memset / memcpy of the last profiled step with its stream, start offset and duration, plus
+the idle gaps of the device (no kernel running on any stream).
+
+    python tools/timeline.py [--rays 65536] > gpurun_out/timeline.txt
+"""
+import argparse, json, os, sys, tempfile
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from presight_b200 import synthetic
+from presight_b200.cameras.rays import RayBundle
+from presight_b200.model import VIDEO_ID, NerfactoNuscMSModel
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--rays", type=int, default=65536)
+ap.add_argument("--config", default="c2")
+args = ap.parse_args()
+dev = torch.device("cuda", 0)
+cfg = bench.build_config(args.config, "b200")
+torch.manual_seed(42)
+host = synthetic.make_rays(args.rays, seed=42)
+model = NerfactoNuscMSModel(cfg, torch.zeros(1, 3), synthetic.tile_aabb(), host["n_cameras"], host["n_videos"]).to(dev).train()
+params = [p for p in model.parameters() if p.requires_grad]
+keys = ("origins", "directions", "camera_indices", "video_ids", "rgb", "features", "sky")
+b = {k: host[k].to(dev) for k in keys}
+
+
+def step():
+    for p in params:
+        p.grad = None
+    rb = RayBundle(origins=b["origins"], directions=b["directions"], camera_indices=b["camera_indices"],
+                   metadata={VIDEO_ID: b["video_ids"]})
+    model.proposal_sampler._step = 0
+    out = model(rb)
+    loss = bench.step_loss(model, out, b)
+    loss.backward()
+    return loss
+
+
+for _ in range(5):
+    step()
+torch.cuda.synchronize()
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    for _ in range(3):
+        with torch.profiler.record_function("PS_STEP"):
+            step()
+        torch.cuda.synchronize()
+path = os.path.join(tempfile.gettempdir(), "ps_trace.json")
+prof.export_chrome_trace(path)
+tr = json.load(open(path))["traceEvents"]
+steps = sorted([e for e in tr if e.get("name") == "PS_STEP" and e.get("ph") == "X" and e.get("cat") in ("user_annotation", "cpu_op")],
+               key=lambda e: e["ts"])
+t_lo = steps[-1]["ts"]
+gpu = sorted([e for e in tr if e.get("ph") == "X" and e.get("cat") in ("kernel", "gpu_memset", "gpu_memcpy") and e["ts"] >= t_lo],
+             key=lambda e: e["ts"])
+t0 = gpu[0]["ts"]
+print(f"# {len(gpu)} device activities; step host span {steps[-1]['dur'] / 1e3:.3f} ms; device span "
+      f"{(max(e['ts'] + e['dur'] for e in gpu) - t0) / 1e3:.3f} ms")
+print("# start_ms  dur_ms  stream  name")
+end_all, idle = t0, 0.0
+gaps = []
+for e in gpu:
+    if e["ts"] > end_all:
+        idle += e["ts"] - end_all
+        gaps.append((e["ts"] - end_all, (end_all - t0) / 1e3, e["name"][:60]))
+    end_all = max(end_all, e["ts"] + e["dur"])
+    print(f"{(e['ts'] - t0) / 1e3:8.3f} {e['dur'] / 1e3:7.3f}  s{e['args'].get('stream', '?'):<3} {e['name'][:90]}")
+print(f"# device idle inside the step: {idle / 1e3:.3f} ms in {len(gaps)} gaps; largest:")
+for g, at, nm in sorted(gaps, reverse=True)[:15]:
+    print(f"#   {g / 1e3:.3f} ms at {at:.3f} ms before {nm}")
