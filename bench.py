@@ -93,11 +93,8 @@ def workload_name(name: str) -> str:
 def step_loss(model, out, batch):
     """rgb MSE + sky BCE + semantic MSE + interlevel (nerfacto_nusc_ms.py:558-645, multipliers :167,:192,:145)."""
     from presight_b200 import losses
-    loss = torch.nn.functional.mse_loss(out["rgb"], batch["rgb"])
-    if model.config.use_sky_model:
-        loss = loss + 0.001 * losses.sky_loss(out["accumulation"].view(-1, 1), batch["sky"])
-    if model.config.use_semantics:
-        loss = loss + 0.5 * losses.semantic_loss(out["semantics"], batch["features"])
+    terms = losses.render_losses(out, batch, model.config.use_sky_model, model.config.use_semantics)   # one kernel
+    loss = terms[0] + 0.001 * terms[1] + 0.5 * terms[2]
     sp = [rs.sp_bins for rs in out["ray_samples_list"]]
     loss = loss + 1.0 * losses.interlevel_loss(out["weights_list"], sp)
     return loss
@@ -133,7 +130,6 @@ def oracle_model_from(model, cfg):
 def cpu_reference_step(omodel, emb, cfg, batch, n):
     """One fwd+bwd of the oracle port on `n` rays (torch CPU, all host threads)."""
     import oracle as O
-    from presight_b200 import losses
     o, d = batch["origins"][:n], batch["directions"][:n]
     parts = []
     if cfg.appearance_embed_dim > 0:
@@ -143,11 +139,11 @@ def cpu_reference_step(omodel, emb, cfg, batch, n):
     app = torch.cat(parts, dim=-1) if parts else None
     jit = [torch.rand(n, 1) for _ in range(len(cfg.num_proposal_samples_per_ray) + 1)]
     out = O.model_outputs(omodel, o, d, app, jit)
-    loss = torch.nn.functional.mse_loss(out["rgb"], batch["rgb"][:n])
+    loss = O.rgb_loss(batch["rgb"][:n], out["rgb"])
     if cfg.use_sky_model:
-        loss = loss + 0.001 * losses.sky_loss(out["accumulation"].view(-1, 1), batch["sky"][:n])
+        loss = loss + 0.001 * O.sky_loss(out["accumulation"].view(-1, 1), batch["sky"][:n].view(-1, 1))
     if cfg.use_semantics:
-        loss = loss + 0.5 * losses.semantic_loss(out["semantics"], batch["features"][:n])
+        loss = loss + 0.5 * O.semantic_loss(out["semantics"], batch["features"][:n])
     loss = loss + O.interlevel_loss(out["weights_list"], [b[0] for b in out["bins_list"]])
     params = [f.grid.table for f in omodel.fields] + [p.grid.table for lvl in omodel.props for p in lvl]
     for p in params:

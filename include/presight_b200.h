@@ -207,6 +207,29 @@ int ps_composite_bwd(const float* eu_bins, const float* density, const float* rg
 int ps_interlevel_loss(const float* c, const float* w, const float* t_env, const float* w_env, int64_t N, int S,
                        int Sp, float* loss_sum, float* grad_w_env, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Loss stack, per-ray tail of the step: model epilogue and rendered-output loss terms, one kernel each.
+ *
+ * ps_sky_blend_fwd replaces models/PreSight/nerfacto_nusc_ms.py:512-532:
+ *   acc = clamp(acc_raw, 0, 1); rgb = [clamp01 if clamp_rgb](rgb_f) + (1 - acc) * sky_rgb; sem = sem_f + (1 - acc) * sky_sem
+ *   rgb_f [N,3], acc_raw [N], sem_f [N,C] (nullable with sem), sky_rgb [N,3] / sky_sem [N,C] nullable (no blending).
+ * ps_sky_blend_bwd: upstream d_rgb [N,3] / d_acc [N] / d_sem [N,C] (each nullable = zero) ->
+ *   d_acc_raw [N] (written), d_sky_rgb [N,3], d_sky_sem [N,C] (written, nullable), d_rgb_f [N,3] (nullable: only needed
+ *   when clamp_rgb, otherwise it equals d_rgb; d_sem_f always equals d_sem).
+ * ps_render_losses replaces nn.MSELoss (nerfacto_nusc_ms.py:314,560-567), sky_loss and semantic_loss
+ *   (model_components/PreSight/losses.py:106-125): losses[3] += {mean (rgb-gt)^2, mean BCE(clip(acc,eps,1-eps), 1-sky),
+ *   mean (sem - clip(gt_sem,0,1))^2} (caller-zeroed; a term whose inputs are NULL is skipped) and
+ *   g_rgb [N,3], g_acc [N], g_sem [N,C] = d losses[i] / d input (written, nullable). */
+int ps_sky_blend_fwd(const float* rgb_f, const float* acc_raw, const float* sem_f, const float* sky_rgb,
+                     const float* sky_sem, int64_t N, int C, int clamp_rgb, float* rgb, float* acc, float* sem,
+                     void* stream);
+int ps_sky_blend_bwd(const float* rgb_f, const float* acc_raw, const float* sky_rgb, const float* sky_sem,
+                     const float* d_rgb, const float* d_acc, const float* d_sem, int64_t N, int C, int clamp_rgb,
+                     float* d_rgb_f, float* d_acc_raw, float* d_sky_rgb, float* d_sky_sem, void* stream);
+int ps_render_losses(const float* rgb, const float* gt_rgb, const float* acc, const float* sky_mask, const float* sem,
+                     const float* gt_sem, int64_t N, int C, float eps, float* losses, float* g_rgb, float* g_acc,
+                     float* g_sem, void* stream);
+
 /* Self-test of the tcgen05 operand conventions used by the fused kernels (csrc/tc5.cuh): one CTA computes, from
  * X [128,64], Y [128,64], W [64,64] (fp32, rounded to bf16 on chip), C1 = X W^T (K-major operands), C2 = X W
  * (MN-major B: the input-gradient form) and C3 = 2 X^T Y (MN-major A and B, reduction over rows, accumulated over two

@@ -33,7 +33,7 @@ __all__ = [
     "pdf_resample", "sample_positions", "get_weights", "render_rgb", "render_accumulation",
     "render_depth_expected", "render_depth_threshold", "proposal_sample", "model_outputs",
     "model_depth", "prior_query", "sky_outputs", "PRIME_Y", "PRIME_Z", "mlp_forward_bf16_emulated",
-    "loss_outer", "lossfun_outer", "interlevel_loss",
+    "loss_outer", "lossfun_outer", "interlevel_loss", "sky_blend", "rgb_loss", "sky_loss", "semantic_loss",
 ]
 
 PRIME_Y = 2654435761  # ENC:336
@@ -484,6 +484,41 @@ def interlevel_loss(weights_list: Sequence[Tensor], sp_bins_list: Sequence[Tenso
     for sdist, weights in zip(sp_bins_list[:-1], weights_list[:-1]):
         loss = loss + torch.mean(lossfun_outer(c, w, sdist, weights[..., 0]))
     return loss
+
+
+def sky_blend(rgb_f: Tensor, acc_raw: Tensor, sem_f: Optional[Tensor], sky_rgb: Optional[Tensor],
+              sky_sem: Optional[Tensor], training: bool = True):
+    """Model epilogue (models/PreSight/nerfacto_nusc_ms.py:512-532): clamp the accumulation, add the sky colour /
+    sky semantics behind the scene.  [N,3],[N,1],[N,C],[N,3],[N,C] -> (rgb, accumulation, semantics)."""
+    accumulation = torch.clamp(acc_raw, min=0.0, max=1.0)
+    rgb = rgb_f if training else torch.clamp(rgb_f, min=0.0, max=1.0)          # RN:221-229 (eval clamp)
+    if sky_rgb is not None:
+        rgb = rgb + (1.0 - accumulation) * sky_rgb
+    sem = sem_f
+    if sem_f is not None and sky_sem is not None:
+        sem = sem_f + (1.0 - accumulation) * sky_sem
+    return rgb, accumulation, sem
+
+
+def rgb_loss(gt_rgb: Tensor, pred_rgb: Tensor) -> Tensor:
+    """nn.MSELoss of models/PreSight/nerfacto_nusc_ms.py:314, 560-567."""
+    return torch.mean((pred_rgb - gt_rgb) ** 2)
+
+
+def sky_loss(accumulation: Tensor, sky_mask: Tensor, eps: float = 1e-7) -> Tensor:
+    """model_components/PreSight/losses.py:106-115: BCE of the clipped accumulation against 1 - sky_mask
+    (F.binary_cross_entropy clamps both logarithms at -100)."""
+    target = 1.0 - sky_mask
+    x = torch.clip(accumulation, min=eps, max=1 - eps)
+    loss = -(target * torch.clamp(torch.log(x), min=-100.0) + (1.0 - target) * torch.clamp(torch.log(1.0 - x), min=-100.0))
+    return loss.mean()
+
+
+def semantic_loss(pred: Tensor, target: Tensor, clip: bool = True) -> Tensor:
+    """model_components/PreSight/losses.py:117-125."""
+    if clip:
+        target = torch.clip(target, min=0.0, max=1.0)
+    return torch.mean((pred - target) ** 2)
 
 
 # --------------------------------------------------------------------------------------

@@ -136,7 +136,9 @@ class SkyFieldMS(nn.Module):
         """sky_field_ms.py:81-117 (routed by ray origin)."""
         origins = ray_samples.frustums.origins[:, 0, :]
         directions = ray_samples.frustums.directions[:, 0, :]
-        app = None if appearance_embedding is None else appearance_embedding[:, 0, :]
+        # reference layout [N,S,A] (sample 0 is used) or per-ray [N,A]
+        app = None if appearance_embedding is None else (
+            appearance_embedding if appearance_embedding.dim() == 2 else appearance_embedding[:, 0, :])
         res = _dispatch(origins.contiguous(), self.centroids, len(self.fields),
                         lambda i, o, d, a: self.fields[i].get_outputs(d, a), (directions, app))
         return {k: v.contiguous() for k, v in res.items()}

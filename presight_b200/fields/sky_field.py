@@ -44,6 +44,8 @@ class SkyField(nn.Module):
 
     def forward(self, ray_samples: RaySamples, appearance_embedding: Optional[Tensor]) -> Dict[str, Tensor]:
         directions = ray_samples.frustums.directions[:, 0, :].contiguous()
+        if appearance_embedding is not None and appearance_embedding.dim() == 3:   # [N,S,A] (reference) or [N,A]
+            appearance_embedding = appearance_embedding[:, 0, :]
         if appearance_embedding is not None:
-            appearance_embedding = appearance_embedding[:, 0, :].contiguous()
+            appearance_embedding = appearance_embedding.contiguous()
         return self.get_outputs(directions, appearance_embedding)

@@ -59,3 +59,14 @@ def semantic_loss(pred: Tensor, target: Tensor, clip: bool = True) -> Tensor:
     if clip:
         target = torch.clip(target, min=0.0, max=1.0)
     return F.mse_loss(pred, target, reduction="none").mean()
+
+
+def render_losses(outputs, batch, use_sky: bool = True, use_semantics: bool = True) -> Tensor:
+    """[rgb_loss, sky_loss, semantic_loss] of get_loss_dict (nerfacto_nusc_ms.py:558-576, 641-645) before their
+    multipliers: ONE kernel producing the three means and their gradients (`ps_render_losses`, CUDA tensors only).
+    batch keys: "rgb" [N,3], "sky" [N,1] (1 = sky), "features" [N,C]."""
+    from . import ops
+    rgb, acc = outputs["rgb"], outputs["accumulation"].view(-1, 1)
+    sem = outputs.get("semantics") if use_semantics else None
+    return ops.render_losses(rgb, batch["rgb"], acc if use_sky else None, batch["sky"].view(-1, 1) if use_sky else None,
+                             sem, batch["features"] if sem is not None else None)

@@ -195,7 +195,9 @@ class NerfactoNuscMSModel(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def _appearance(self, ray_samples: RaySamples) -> Optional[Tensor]:
-        """nerfacto_nusc_ms.py:456-490 -> [N,S,A] (expanded view) or None."""
+        """nerfacto_nusc_ms.py:456-490 -> per-ray embeddings [N,A] or None.  (The reference expands them to [N,S,A];
+        here only the un-fused field path does, so that autograd never materialises an [N,S,A] gradient — selecting
+        sample 0 of an expanded view costs a 268 MB zero-fill, an add and a reduction per step at C2 sizes.)"""
         c = self.config
         cam = ray_samples.camera_indices.squeeze(dim=-1)          # [N,1]
         N, S = ray_samples.shape
@@ -205,7 +207,7 @@ class NerfactoNuscMSModel(nn.Module):
                 parts.append(self.appearance_embedding(cam))
             if c.video_embed_dim > 0:
                 parts.append(self.video_embedding(ray_samples.metadata[VIDEO_ID].squeeze(dim=-1)))
-            emb = torch.cat(parts, dim=-1) if parts else None
+            emb = torch.cat(parts, dim=-1)[:, 0, :] if parts else None
         else:
             dim = c.appearance_embed_dim + c.video_embed_dim
             if dim == 0:
@@ -216,12 +218,10 @@ class NerfactoNuscMSModel(nn.Module):
                     parts.append(self.appearance_embedding.mean(dim=0))
                 if c.video_embed_dim > 0:
                     parts.append(self.video_embedding.mean(dim=0))
-                emb = torch.cat(parts, dim=-1)[None, None, :].expand(N, 1, dim)
+                emb = torch.cat(parts, dim=-1)[None, :].expand(N, dim)
             else:
-                emb = torch.zeros((N, 1, dim), device=cam.device)
-        if emb is None:
-            return None
-        return emb.expand(N, S, emb.shape[-1])
+                emb = torch.zeros((N, dim), device=cam.device)
+        return emb
 
     def forward(self, ray_bundle: RayBundle, jitters: Optional[List[Tensor]] = None,
                 appearance: Optional[Tensor] = None) -> Dict[str, object]:
@@ -235,14 +235,15 @@ class NerfactoNuscMSModel(nn.Module):
         ray_samples, weights_list, ray_samples_list = self.proposal_sampler(ray_bundle, density_fns=self.density_fns,
                                                                             jitters=jitters)
         N, S = ray_samples.shape
-        app = self._appearance(ray_samples) if appearance is None else appearance[:, None, :].expand(N, S, -1)
+        app = self._appearance(ray_samples) if appearance is None else appearance          # [N,A] per ray
         eu = ray_samples.frustums.eu_bins
         if self.use_fused and self.field.supports_fused():
             # level-fused fast path (presight_b200/fused.py): field + compositing as one autograd node
             weights, rgb, acc_raw, dexp_raw, depth, sem_out, tmm = self.field.fused_level(
-                ray_bundle.origins, ray_bundle.directions, eu, None if app is None else app[:, 0, :], 0.5)
+                ray_bundle.origins, ray_bundle.directions, eu, app, 0.5)
         else:
-            fo = self.field.forward(ray_samples, appearance_embedding=app)
+            fo = self.field.forward(ray_samples, appearance_embedding=None if app is None
+                                    else app[:, None, :].expand(N, S, -1))
             sem = fo.get(FieldHeadNames.SEMANTICS)
             # one-pass compositing kernel: weights + rgb + accumulation + both depths + semantics (:503-511, :530)
             w, rgb, acc_raw, dexp_raw, depth, sem_out, tmm = ops.composite(
@@ -251,19 +252,16 @@ class NerfactoNuscMSModel(nn.Module):
         weights_list.append(weights)
         ray_samples_list.append(ray_samples)
         expected_depth = torch.clip(dexp_raw, tmm[0], tmm[1])            # renderers.py:379 (batch-global clip)
-        accumulation = torch.clamp(acc_raw, min=0.0, max=1.0)
-        if not self.training:
-            rgb = torch.clamp(rgb, min=0.0, max=1.0)
         sky_outputs = {}
         if self.config.use_sky_model:
             sky_outputs = self.sky_model(ray_samples, appearance_embedding=app)
-            rgb = rgb + (1.0 - accumulation) * sky_outputs[FieldHeadNames.RGB]
+        # epilogue (:512-532) as one kernel: accumulation clamp, sky colour / sky semantics behind the scene
+        rgb, accumulation, semantics = ops.sky_blend(
+            rgb, acc_raw, sem_out if self.config.use_semantics else None, sky_outputs.get(FieldHeadNames.RGB),
+            sky_outputs.get(FieldHeadNames.SEMANTICS), clamp_rgb=not self.training)
         outputs: Dict[str, object] = {"rgb": rgb, "accumulation": accumulation, "depth": depth,
                                       "expected_depth": expected_depth}
         if self.config.use_semantics:
-            semantics = sem_out
-            if FieldHeadNames.SEMANTICS in sky_outputs:
-                semantics = semantics + (1.0 - accumulation) * sky_outputs[FieldHeadNames.SEMANTICS]
             outputs["semantics"] = semantics
         if self.training:
             outputs["weights_list"] = weights_list

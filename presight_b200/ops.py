@@ -471,5 +471,93 @@ def interlevel_loss_level(c: Tensor, w: Tensor, t_env: Tensor, w_env: Tensor) ->
     return _InterlevelLoss.apply(c, w, t_env, w_env)
 
 
+# --------------------------------------------------------------------------------------------------
+# loss stack: model epilogue (sky blending) and the rendered-output loss terms, one kernel per direction
+# --------------------------------------------------------------------------------------------------
+class _SkyBlend(torch.autograd.Function):
+    """nerfacto_nusc_ms.py:512-532: (rgb_f [N,3], acc_raw [N,1], sem_f [N,C]|None, sky_rgb|None, sky_sem|None) ->
+    (rgb, accumulation [N,1], semantics|None)."""
+
+    @staticmethod
+    def forward(ctx, rgb_f, acc_raw, sem_f, sky_rgb, sky_sem, clamp_rgb):
+        r, a = _f32c(rgb_f.detach()), _f32c(acc_raw.detach())
+        s = None if sem_f is None else _f32c(sem_f.detach())
+        kr = None if sky_rgb is None else _f32c(sky_rgb.detach())
+        ks = None if (sky_sem is None or s is None) else _f32c(sky_sem.detach())
+        N = r.shape[0]
+        C = 0 if s is None else s.shape[1]
+        rgb, acc = torch.empty_like(r), torch.empty_like(a)
+        sem = None if s is None else torch.empty_like(s)
+        call("ps_sky_blend_fwd", ptr(r), ptr(a), ptr(s), ptr(kr), ptr(ks), N, C, 1 if clamp_rgb else 0, ptr(rgb), ptr(acc),
+             ptr(sem), stream())
+        ctx.save_for_backward(r, a, kr, ks)
+        ctx.meta = (N, C, bool(clamp_rgb), s is not None)
+        ctx.set_materialize_grads(False)
+        if sem is None:
+            sem = torch.empty(0, device=r.device)
+            ctx.mark_non_differentiable(sem)
+        return rgb, acc, sem
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_acc, d_sem):
+        N, C, clamp_rgb, has_sem = ctx.meta
+        r, a, kr, ks = ctx.saved_tensors
+        dr = None if d_rgb is None else _f32c(d_rgb)
+        da = None if d_acc is None else _f32c(d_acc)
+        ds = None if (d_sem is None or not has_sem) else _f32c(d_sem)
+        need = ctx.needs_input_grad
+        d_acc_raw = torch.empty_like(a)
+        d_rgb_f = torch.empty_like(r) if (clamp_rgb and need[0]) else None
+        d_kr = torch.empty_like(kr) if (kr is not None and need[3]) else None
+        d_ks = torch.empty_like(ks) if (ks is not None and need[4]) else None
+        call("ps_sky_blend_bwd", ptr(r), ptr(a), ptr(kr), ptr(ks), ptr(dr), ptr(da), ptr(ds), N, C, 1 if clamp_rgb else 0,
+             ptr(d_rgb_f), ptr(d_acc_raw), ptr(d_kr), ptr(d_ks), stream())
+        g_rgb_f = d_rgb_f if clamp_rgb else dr          # identity paths hand the upstream gradient through
+        return g_rgb_f, d_acc_raw, ds, d_kr, d_ks, None
+
+
+def sky_blend(rgb_f: Tensor, acc_raw: Tensor, sem_f: Optional[Tensor], sky_rgb: Optional[Tensor],
+              sky_sem: Optional[Tensor], clamp_rgb: bool = False):
+    """-> (rgb [N,3], accumulation [N,1], semantics [N,C] or None)."""
+    rgb, acc, sem = _SkyBlend.apply(rgb_f, acc_raw, sem_f, sky_rgb, sky_sem, clamp_rgb)
+    return rgb, acc, (None if sem_f is None else sem)
+
+
+class _RenderLosses(torch.autograd.Function):
+    """[rgb MSE, sky BCE, semantic MSE] (nerfacto_nusc_ms.py:560-576, PreSight/losses.py:106-125) and their gradients
+    in one kernel; absent terms are zero."""
+
+    @staticmethod
+    def forward(ctx, rgb, gt_rgb, acc, sky_mask, sem, gt_sem, eps):
+        ref = rgb if rgb is not None else (acc if acc is not None else sem)
+        c = lambda t: None if t is None else _f32c(t.detach())
+        r, gr, a, km, s, gs = c(rgb), c(gt_rgb), c(acc), c(sky_mask), c(sem), c(gt_sem)
+        N = ref.shape[0]
+        C = 0 if s is None else s.shape[1]
+        need = ctx.needs_input_grad
+        losses = torch.zeros(3, device=ref.device, dtype=torch.float32)
+        g_r = torch.empty_like(r) if (r is not None and need[0]) else None
+        g_a = torch.empty_like(a) if (a is not None and need[2]) else None
+        g_s = torch.empty_like(s) if (s is not None and need[4]) else None
+        with _probe("render_losses"):
+            call("ps_render_losses", ptr(r), ptr(gr), ptr(a), ptr(km), ptr(s), ptr(gs), N, C, float(eps), ptr(losses),
+                 ptr(g_r), ptr(g_a), ptr(g_s), stream())
+        ctx.grads = (g_r, g_a, g_s)
+        return losses
+
+    @staticmethod
+    def backward(ctx, g):
+        g_r, g_a, g_s = ctx.grads
+        ctx.grads = None
+        return (None if g_r is None else g_r * g[0], None, None if g_a is None else g_a * g[1], None,
+                None if g_s is None else g_s * g[2], None, None)
+
+
+def render_losses(rgb: Optional[Tensor], gt_rgb: Optional[Tensor], acc: Optional[Tensor], sky_mask: Optional[Tensor],
+                  sem: Optional[Tensor], gt_sem: Optional[Tensor], eps: float = 1e-7) -> Tensor:
+    """-> [3] = (rgb_loss, sky_loss, semantic_loss), each a mean; pass None pairs to skip a term."""
+    return _RenderLosses.apply(rgb, gt_rgb, acc, sky_mask, sem, gt_sem, eps)
+
+
 def launch_count() -> int:
     return _lib.launch_count()

@@ -439,6 +439,66 @@ def test_interlevel_loss_kernel_random(ops):
         assert_close(wg.grad.cpu(), we.grad, TOL32, f"grad {N}x{S}x{Sp}")
 
 
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_sky_blend_and_render_losses_golden(ops, case):
+    """ps_sky_blend_fwd/bwd + ps_render_losses vs the live reference's fixture: blended outputs bit-exact, loss terms
+    1e-5, every gradient of the weighted total 1e-5 (fp32 class)."""
+    fx = Fixture("render_losses.npz")
+    names = ("rgb_f", "acc_raw", "sem_f", "sky_rgb", "sky_sem")
+    leaves = {k: fx[f"{case}/{k}"].to(DEV).requires_grad_(True) for k in names}
+    rgb, acc, sem = ops.sky_blend(leaves["rgb_f"], leaves["acc_raw"], leaves["sem_f"], leaves["sky_rgb"], leaves["sky_sem"])
+    assert torch.equal(rgb.cpu(), fx[f"{case}/rgb"]) and torch.equal(acc.cpu(), fx[f"{case}/acc"])
+    assert torch.equal(sem.cpu(), fx[f"{case}/sem"])
+    terms = ops.render_losses(rgb, fx[f"{case}/gt_rgb"].to(DEV), acc, fx[f"{case}/sky"].to(DEV), sem,
+                              fx[f"{case}/gt_sem"].to(DEV))
+    assert_close(terms.cpu(), fx[f"{case}/losses"], 1e-5, "loss terms")
+    (terms[0] + 0.001 * terms[1] + 0.5 * terms[2]).backward()
+    for k in names:
+        assert_close(leaves[k].grad.cpu(), fx[f"{case}/g_{k}"], 1e-5, f"grad {k}")
+
+
+def test_sky_blend_and_render_losses_variants(ops):
+    """optional inputs (no sky model, no semantics, eval-mode rgb clamp, skipped loss terms) and a ragged large batch
+    against the oracle."""
+    g = torch.Generator().manual_seed(5)
+    N, C = 4099, 24
+    rgb_f = (torch.rand(N, 3, generator=g) * 1.4 - 0.2)
+    acc_raw = torch.rand(N, 1, generator=g) * 1.4 - 0.2
+    sem_f, sky_rgb, sky_sem = torch.randn(N, C, generator=g), torch.rand(N, 3, generator=g), torch.randn(N, C, generator=g)
+    gt_rgb, sky, gt_sem = torch.rand(N, 3, generator=g), (torch.rand(N, 1, generator=g) < 0.5).float(), torch.randn(N, C, generator=g)
+    for (use_sem, use_sky_rgb, use_sky_sem, training) in [(True, True, True, False), (True, True, False, True),
+                                                         (False, True, False, True), (True, False, False, True),
+                                                         (False, False, False, False)]:
+        cpu = [t.clone().requires_grad_(True) for t in (rgb_f, acc_raw, sem_f, sky_rgb, sky_sem)]
+        dev = [t.to(DEV).requires_grad_(True) for t in (rgb_f, acc_raw, sem_f, sky_rgb, sky_sem)]
+
+        def pick(ts):
+            return (ts[0], ts[1], ts[2] if use_sem else None, ts[3] if use_sky_rgb else None, ts[4] if use_sky_sem else None)
+        r0, a0, s0 = O.sky_blend(*pick(cpu), training=training)
+        r1, a1, s1 = ops.sky_blend(*pick(dev), clamp_rgb=not training)
+        assert torch.equal(r1.cpu(), r0) and torch.equal(a1.cpu(), a0)
+        assert (s1 is None) == (s0 is None) and (s0 is None or torch.equal(s1.cpu(), s0))
+        want = O.rgb_loss(gt_rgb, r0) + 0.01 * O.sky_loss(a0, sky)
+        terms = ops.render_losses(r1, gt_rgb.to(DEV), a1, sky.to(DEV), s1, None if s1 is None else gt_sem.to(DEV))
+        got = terms[0] + 0.01 * terms[1]
+        if s0 is not None:
+            want = want + 0.5 * O.semantic_loss(s0, gt_sem)
+            got = got + 0.5 * terms[2]
+        else:
+            assert float(terms[2]) == 0.0
+        assert_close(got.cpu(), want, 1e-5, "total")
+        want.backward()
+        got.backward()
+        for i, (c, d) in enumerate(zip(cpu, dev)):
+            if c.grad is None:
+                assert d.grad is None, i
+            else:
+                assert_close(d.grad.cpu(), c.grad, 1e-5, f"grad {i} variant {(use_sem, use_sky_rgb, use_sky_sem, training)}")
+    # a skipped term: rgb only
+    t = ops.render_losses(r1, gt_rgb.to(DEV), None, None, None, None)
+    assert float(t[1]) == 0.0 and float(t[2]) == 0.0 and float(t[0]) > 0.0
+
+
 def test_tcgen05_operand_conventions(ops):
     """K-major / MN-major UMMA descriptors over one chunk-major tile (csrc/tc5.cuh): forward, input-gradient and
     weight-gradient GEMM forms against fp32 matmuls of the bf16-rounded operands."""

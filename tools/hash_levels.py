@@ -50,6 +50,15 @@ def main():
         tot_f += tf; tot_b += tb
         print(f"level {l:2d} res {int(s):5d}: fwd {tf:6.3f} ms   bwd {tb:6.3f} ms", flush=True)
     print(f"sum: fwd {tot_f:.3f} bwd {tot_b:.3f}")
+    # all levels in one launch (what the model runs)
+    table = (torch.rand(L << log2T, F, device=dev) * 2 - 1) * 1e-3
+    dtable = torch.zeros_like(table)
+    out = torch.empty(P * L * F, device=dev)
+    dout = torch.randn(P * L * F, device=dev)
+    for _ in range(3):
+        tf = t(lambda: call("ps_hash_fwd_lm", ptr(x01), P, ptr(table), host_floats(scal), L, F, log2T, ptr(out), stream()))
+        tb = t(lambda: call("ps_hash_bwd_lm", ptr(x01), P, None, host_floats(scal), L, F, log2T, ptr(dout), ptr(dtable), None, stream()))
+    print(f"one launch, {L} levels: fwd {tf:.3f} ms  bwd {tb:.3f} ms")
 
 
 if __name__ == "__main__":
