@@ -215,6 +215,9 @@ def main() -> None:
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries exactly one JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) goes to stdout too
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     from presight_b200 import ops
     from presight_b200.cameras.rays import RayBundle
@@ -278,20 +281,76 @@ def main() -> None:
     ops.PROBE = None
     t_dev = ev0.elapsed_time(ev1) / 1e3
 
-    # ---- timed: end to end (pinned host batch -> device every step, loss read back every step)
-    for _ in range(2):
-        float(run_step({k: pinned[k].to(dev, non_blocking=True) for k in tensor_keys}))
+    # ---- timed: end to end.  Every step: this step's batch is copied from pinned host memory (double-buffered on a copy
+    # stream, so the copy of batch k+1 travels under the compute of batch k) and the step's loss is read back to the host
+    # (asynchronously into pinned memory; the host consumes it one step later, as a trainer's logger does).
+    from presight_b200.prefetch import DevicePrefetcher
+    pf = DevicePrefetcher(dev, tensor_keys)
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def e2e_loop(n_steps):
+        last_ = 0.0
+        pf.push(pinned)
+        for i in range(n_steps):
+            batch = pf.pop()
+            if i + 1 < n_steps:
+                pf.push(pinned)                      # next step's inputs: host -> device while this step computes
+            loss_ = run_step(batch)
+            pf.release()
+            loss_host[i % 2].copy_(loss_.detach(), non_blocking=True)      # device -> host read of the step's result
+            loss_ready[i % 2].record()
+            if i > 0:
+                loss_ready[(i - 1) % 2].synchronize()
+                last_ = float(loss_host[(i - 1) % 2])
+        loss_ready[(n_steps - 1) % 2].synchronize()
+        return float(loss_host[(n_steps - 1) % 2])
+    e2e_loop(2)
     barrier()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record()
-    last = 0.0
-    for _ in range(args.steps):
-        batch = {k: pinned[k].to(dev, non_blocking=True) for k in tensor_keys}
-        last = float(run_step(batch))        # .item(): device->host read of the step's result
+    last = e2e_loop(args.steps)
     ev3.record()
     barrier()
     t_e2e = ev2.elapsed_time(ev3) / 1e3
     clock_info = clocks.stop()
+
+    # ---- the roofline kernel alone: the main-grid scatter on the step's own final-level sample points (same ray slices
+    # as the step, nothing else on the device), CUDA events on its stream.  In the step it shares the SMs with the
+    # field / proposal backward kernels, so its in-step event time measures the pipeline, not the kernel.
+    alone_ms = None
+    if rank == 0 and cfg.num_levels * cfg.features_per_level <= 48:
+        from presight_b200 import fused
+        from presight_b200._lib import call, host_floats, ptr, stream
+        with torch.no_grad():
+            rb = RayBundle(origins=resident["origins"], directions=resident["directions"],
+                           camera_indices=resident["camera_indices"], metadata={VIDEO_ID: resident["video_ids"]})
+            eu = model(rb)["ray_samples_list"][-1].frustums.eu_bins.contiguous()
+        f0 = model.field.fields[0]
+        enc = f0.mlp_base_grid
+        x01, _ = fused._ray_points(resident["origins"], resident["directions"], eu, f0.aabb_host(),
+                                   f0.spatial_distortion is not None)
+        S_, L_, F_, T_ = eu.shape[1] - 1, cfg.num_levels, cfg.features_per_level, cfg.log2_hashmap_size
+        dfeat = torch.randn(x01.shape[0] * L_ * F_, device=dev) * 1e-3
+        dtab = torch.zeros_like(enc.hash_table)
+        bounds = fused._chunk_bounds(rays_per_rank, S_)
+
+        def scatter_all():
+            P_ = x01.shape[0]
+            for (c0, c1) in bounds:      # level-major gradient of a slice = [L][slice points][F]: rebuild the view
+                n_ = (c1 - c0) * S_
+                call("ps_hash_bwd_lm", ptr(x01[c0 * S_:c1 * S_]), n_, None, host_floats(enc._scalings_host), L_, F_, T_,
+                     ptr(dfeat[:n_ * L_ * F_]), ptr(dtab), None, stream())
+        scatter_all()
+        torch.cuda.synchronize()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for _ in range(5):
+            scatter_all()
+        eb.record()
+        torch.cuda.synchronize()
+        alone_ms = ea.elapsed_time(eb) / 5
+        del dfeat, dtab, x01
 
     if world > 1:
         t = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
@@ -335,7 +394,11 @@ def main() -> None:
                          "kernel_ms": k_ms, "launches_per_step": (n_launch / args.steps) if n_launch else None,
                          "algorithmic_bytes_per_launch": algo_bytes / max(1.0, n_launch / args.steps) if n_launch else None,
                          "algorithmic_bytes_per_step": algo_bytes,
-                         "step_frac_of_hbm_roofline": (step_bytes * total_rays / world) / (t_dev / args.steps) / 1e9 / peak},
+                         "step_frac_of_hbm_roofline": (step_bytes * total_rays / world) / (t_dev / args.steps) / 1e9 / peak,
+                         # the same launches with the device to themselves (see above)
+                         "alone": None if not alone_ms else {
+                             "kernel_ms": alone_ms, "achieved": algo_bytes / (alone_ms * 1e-3) / 1e9,
+                             "frac": algo_bytes / (alone_ms * 1e-3) / 1e9 / peak}},
             "kernels_ms_per_step": {k: round(v[0] * v[1] / args.steps, 4) for k, v in sorted(probe.items())},
             "loss": last,
         }

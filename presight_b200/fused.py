@@ -387,15 +387,7 @@ def tc5_field_forward(o, d, eu, app_c, table, aabb, contract, grid: GridMeta, ws
     return x01, sel, feat, w, rgb_out, acc, dexp, dthr, sem_out, tmm
 
 
-def _zeros_like_many(tensors: Sequence[Tensor]) -> List[Tensor]:
-    """Zero-filled buffers shaped like `tensors`, carved out of ONE allocation (one fill kernel instead of one each)."""
-    sizes = [((t.numel() + 3) // 4) * 4 for t in tensors]          # keep every view 16-byte aligned
-    flat = torch.zeros(sum(sizes), device=tensors[0].device, dtype=torch.float32)
-    out, off = [], 0
-    for t, n in zip(tensors, sizes):
-        out.append(flat[off:off + t.numel()].view(t.shape))
-        off += n
-    return out
+_zeros_like_many = ops.zeros_like_many
 
 
 def _chunk_bounds(N: int, S: int) -> List[Tuple[int, int]]:

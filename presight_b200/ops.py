@@ -74,6 +74,17 @@ def new_tminmax(dev) -> Tensor:
     return t
 
 
+def zeros_like_many(tensors: Sequence[Tensor]) -> List[Tensor]:
+    """Zero-filled fp32 buffers shaped like `tensors`, carved out of ONE allocation (one fill kernel instead of one each)."""
+    sizes = [((t.numel() + 3) // 4) * 4 for t in tensors]          # keep every view 16-byte aligned
+    flat = torch.zeros(sum(sizes), device=tensors[0].device, dtype=torch.float32)
+    out, off = [], 0
+    for t, n in zip(tensors, sizes):
+        out.append(flat[off:off + t.numel()].view(t.shape))
+        off += n
+    return out
+
+
 def _f32c(t: Tensor) -> Tensor:
     if t.dtype != torch.float32:
         t = t.float()
@@ -204,8 +215,9 @@ class _Mlp(torch.autograd.Function):
         bd = [rest.pop(0) if hb else None for hb in has_b]
         dy2 = _f32c(dy).view(-1, dims[-1])
         dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
-        dW = [torch.zeros_like(w) for w in wd]
-        db = [None if b is None else torch.zeros_like(b) for b in bd]
+        zs = zeros_like_many([*wd, *[b for b in bd if b is not None]])      # one fill kernel for all gradients
+        dW, zb = zs[:n_layers], zs[n_layers:]
+        db = [None if b is None else zb.pop(0) for b in bd]
         with _probe("mlp_bwd_" + "x".join(map(str, dims))):
             call("ps_mlp_bwd", ptr(x2), None, ptr(dy2), x2.shape[0], host_ptrs(wd), host_ptrs(bd), host_ints(dims),
                  n_layers, out_act, precision, ptr(dx), host_ptrs(dW), host_ptrs(db), stream())
