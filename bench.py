@@ -166,7 +166,26 @@ def time_cpu_reference(model, cfg, batch, sample_rays, steps, warmup):
 
 
 # ------------------------------------------------------------------------------------------------ main
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main() -> None:
+    # stdout carries exactly one JSON line: anything libraries print while the run is going on (NCCL writes its
+    # "NCCL version ..." banner to stdout when NCCL_DEBUG is set) is sent to stderr at the file-descriptor level
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -199,14 +218,14 @@ def main() -> None:
         rps, med = time_cpu_reference(model, cfg, batch, args.cpu_sample_rays, max(1, args.steps), max(1, args.warmup))
         cores = os.cpu_count() or 1
         sample = f"{args.cpu_sample_rays} rays/step of the same workload, torch CPU fp32, {cores} threads"
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": METRIC, "value": rps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.config), "rays_per_step": args.cpu_sample_rays},
             "cpu_baseline": {"value": rps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "wall_s": time.perf_counter() - t_start}))
+            "wall_s": time.perf_counter() - t_start})
         return
 
     # ---------------------------------------------------------------- b200 arm
@@ -215,10 +234,8 @@ def main() -> None:
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) goes to stdout too
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        from presight_b200.parallel import init_nccl
+        init_nccl(dev, high_priority=os.environ.get("PS_NCCL_PRIO", "1") == "1")
     from presight_b200 import ops
     from presight_b200.cameras.rays import RayBundle
     from presight_b200.model import VIDEO_ID, NerfactoNuscMSModel
@@ -409,7 +426,7 @@ def main() -> None:
             line["cpu_baseline"] = {"value": rps, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{n} rays/step of the same workload and weights, torch CPU fp32, "
                                               f"{cores} threads, median of 3 steps ({med:.2f} s/step)"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -17,12 +17,22 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--rays", type=int, default=65536)
 ap.add_argument("--config", default="c2")
 args = ap.parse_args()
-dev = torch.device("cuda", 0)
+# under torchrun (WORLD_SIZE > 1): data-parallel step with the gradient exchange; rank 0 prints its own timeline
+import torch.distributed as dist
+rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+sync = None
+if world > 1:
+    from presight_b200.parallel import GradSynchronizer, init_nccl
+    init_nccl(dev)
 cfg = bench.build_config(args.config, "b200")
 torch.manual_seed(42)
 host = synthetic.make_rays(args.rays, seed=42)
 model = NerfactoNuscMSModel(cfg, torch.zeros(1, 3), synthetic.tile_aabb(), host["n_cameras"], host["n_videos"]).to(dev).train()
 params = [p for p in model.parameters() if p.requires_grad]
+if world > 1:
+    sync = GradSynchronizer(params, overlap=True)
 keys = ("origins", "directions", "camera_indices", "video_ids", "rgb", "features", "sky")
 b = {k: host[k].to(dev) for k in keys}
 
@@ -36,6 +46,8 @@ def step():
     out = model(rb)
     loss = bench.step_loss(model, out, b)
     loss.backward()
+    if sync is not None:
+        sync.finish()
     return loss
 
 
@@ -48,6 +60,10 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         with torch.profiler.record_function("PS_STEP"):
             step()
         torch.cuda.synchronize()
+if rank != 0:
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0)
 path = os.path.join(tempfile.gettempdir(), "ps_trace.json")
 prof.export_chrome_trace(path)
 tr = json.load(open(path))["traceEvents"]
@@ -71,3 +87,6 @@ for e in gpu:
 print(f"# device idle inside the step: {idle / 1e3:.3f} ms in {len(gaps)} gaps; largest:")
 for g, at, nm in sorted(gaps, reverse=True)[:15]:
     print(f"#   {g / 1e3:.3f} ms at {at:.3f} ms before {nm}")
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
