@@ -32,8 +32,10 @@ def init_nccl(device: torch.device, high_priority: bool = True, **kw) -> None:
     # Protocol: on the NVLink-only (no NVLS multicast) B200 boxes measured here NCCL's tuner moves the 512 MiB table gradient
     # with the Simple protocol; LL128 is 0.67 ms per step faster at 4 GPUs (13.20 vs 13.87 ms, tools/nccl_variants.sh).
     # An NCCL_PROTO already in the environment wins.
+    # At 2 GPUs the default (LL) is as fast (12.44 vs 12.57 ms), so it is left alone there.
     import os
-    os.environ.setdefault("NCCL_PROTO", "LL128")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 2:
+        os.environ.setdefault("NCCL_PROTO", "LL128")
     opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=high_priority)
     dist.init_process_group("nccl", device_id=device, pg_options=opts, **kw)
 
