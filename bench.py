@@ -91,12 +91,14 @@ def workload_name(name: str) -> str:
 
 # ------------------------------------------------------------------------------------------------ loss
 def step_loss(model, out, batch):
-    """rgb MSE + sky BCE + semantic MSE + interlevel (nerfacto_nusc_ms.py:558-645, multipliers :167,:192,:145)."""
+    """rgb MSE + sky BCE + semantic MSE + interlevel + distortion — the loss dict of a camera-only training step
+    (nerfacto_nusc_ms.py:558-645, multipliers :127,:133,:167,:192)."""
     from presight_b200 import losses
     terms = losses.render_losses(out, batch, model.config.use_sky_model, model.config.use_semantics)   # one kernel
     loss = terms[0] + 0.001 * terms[1] + 0.5 * terms[2]
     sp = [rs.sp_bins for rs in out["ray_samples_list"]]
     loss = loss + 1.0 * losses.interlevel_loss(out["weights_list"], sp)
+    loss = loss + 0.002 * losses.distortion_loss(out["weights_list"], sp)          # distortion_loss_mult (:133)
     return loss
 
 
@@ -145,6 +147,7 @@ def cpu_reference_step(omodel, emb, cfg, batch, n):
     if cfg.use_semantics:
         loss = loss + 0.5 * O.semantic_loss(out["semantics"], batch["features"][:n])
     loss = loss + O.interlevel_loss(out["weights_list"], [b[0] for b in out["bins_list"]])
+    loss = loss + 0.002 * O.distortion_loss(out["weights_list"], [b[0] for b in out["bins_list"]])
     params = [f.grid.table for f in omodel.fields] + [p.grid.table for lvl in omodel.props for p in lvl]
     for p in params:
         p.grad = None

@@ -206,6 +206,12 @@ int ps_composite_bwd(const float* eu_bins, const float* density, const float* rg
  */
 int ps_interlevel_loss(const float* c, const float* w, const float* t_env, const float* w_env, int64_t N, int S,
                        int Sp, float* loss_sum, float* grad_w_env, void* stream);
+/* Distortion loss of mip-NeRF 360 (lossfun_distortion / distortion_loss, model_components/losses.py:130-149).
+ *   c [N,S+1] spacing-domain bin edges and w [N,S] weights of the final level
+ *   loss_sum [1] += sum over rays of (sum_ij w_i w_j |u_i - u_j| + sum_i w_i^2 (c_{i+1} - c_i) / 3), u = bin mid-points
+ *   (caller-zeroed; the reference's value is loss_sum / N);  grad_w [N,S] (nullable) = d loss_sum / d w (written).
+ *   S <= 1024. */
+int ps_distortion_loss(const float* c, const float* w, int64_t N, int S, float* loss_sum, float* grad_w, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Loss stack, per-ray tail of the step: model epilogue and rendered-output loss terms, one kernel each.

@@ -34,6 +34,7 @@ __all__ = [
     "render_depth_expected", "render_depth_threshold", "proposal_sample", "model_outputs",
     "model_depth", "prior_query", "sky_outputs", "PRIME_Y", "PRIME_Z", "mlp_forward_bf16_emulated",
     "loss_outer", "lossfun_outer", "interlevel_loss", "sky_blend", "rgb_loss", "sky_loss", "semantic_loss",
+    "lossfun_distortion", "distortion_loss",
 ]
 
 PRIME_Y = 2654435761  # ENC:336
@@ -484,6 +485,20 @@ def interlevel_loss(weights_list: Sequence[Tensor], sp_bins_list: Sequence[Tenso
     for sdist, weights in zip(sp_bins_list[:-1], weights_list[:-1]):
         loss = loss + torch.mean(lossfun_outer(c, w, sdist, weights[..., 0]))
     return loss
+
+
+def lossfun_distortion(t: Tensor, w: Tensor) -> Tensor:
+    """LS:130-143: sum_ij w_i w_j |u_i - u_j| + sum_i w_i^2 (t_{i+1} - t_i) / 3 per ray, u = bin mid-points."""
+    ut = (t[..., 1:] + t[..., :-1]) / 2
+    dut = torch.abs(ut[..., :, None] - ut[..., None, :])
+    loss_inter = torch.sum(w * torch.sum(w[..., None, :] * dut, dim=-1), dim=-1)
+    loss_intra = torch.sum(w ** 2 * (t[..., 1:] - t[..., :-1]), dim=-1) / 3
+    return loss_inter + loss_intra
+
+
+def distortion_loss(weights_list: Sequence[Tensor], sp_bins_list: Sequence[Tensor]) -> Tensor:
+    """LS:145-149 (the final level's weights are NOT detached here: the gradient reaches the field)."""
+    return torch.mean(lossfun_distortion(sp_bins_list[-1], weights_list[-1][..., 0]))
 
 
 def sky_blend(rgb_f: Tensor, acc_raw: Tensor, sem_f: Optional[Tensor], sky_rgb: Optional[Tensor],

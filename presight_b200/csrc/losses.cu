@@ -75,9 +75,53 @@ __global__ void __launch_bounds__(kLossWarps * 32) interlevel_kernel(const float
     }
 }
 
+// Distortion loss of mip-NeRF 360 with its gradient w.r.t. the weights, ONE kernel (model_components/losses.py:130-149):
+//   u = bin mid-points;  loss_n = sum_i w_i sum_j w_j |u_i - u_j| + sum_i w_i^2 (t_{i+1} - t_i) / 3
+//   d loss_n / d w_k = 2 sum_j w_j |u_k - u_j| + 2 w_k (t_{k+1} - t_k) / 3
+// One warp per ray; the O(S^2) pair sum is evaluated as written (no sortedness assumption) from shared memory:
+// S = 64 costs 4 096 multiply-adds per ray — 0.3 GFLOP for a 65 536-ray batch.
+__global__ void __launch_bounds__(kLossWarps * 32) distortion_kernel(const float* __restrict__ c,
+                                                                     const float* __restrict__ w, int64_t N, int S,
+                                                                     float* __restrict__ loss_sum,
+                                                                     float* __restrict__ grad_w) {
+    extern __shared__ float smem[];  // per warp: u[S] | w[S]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * kLossWarps + warp;
+    if (n >= N) return;
+    float* us = smem + (size_t)warp * 2 * S;
+    float* ws = us + S;
+    for (int k = lane; k < S; k += 32) {
+        us[k] = __fdiv_rn(__fadd_rn(__ldg(c + n * (S + 1) + k + 1), __ldg(c + n * (S + 1) + k)), 2.f);
+        ws[k] = __ldg(w + n * S + k);
+    }
+    __syncwarp();
+    float loss = 0.f;
+    for (int i = lane; i < S; i += 32) {
+        const float ui = us[i], wi = ws[i];
+        float a = 0.f;
+        for (int j = 0; j < S; ++j) a = fmaf(ws[j], fabsf(ui - us[j]), a);
+        const float dt = __fsub_rn(__ldg(c + n * (S + 1) + i + 1), __ldg(c + n * (S + 1) + i));
+        loss += wi * a + wi * wi * dt / 3.f;
+        if (grad_w) grad_w[n * S + i] = 2.f * a + 2.f * wi * dt / 3.f;
+    }
+    loss = warp_sum(loss);
+    if (lane == 0) atomicAdd(loss_sum, loss);
+}
+
 }  // namespace ps
 
 using namespace ps;
+
+extern "C" int ps_distortion_loss(const float* c, const float* w, int64_t N, int S, float* loss_sum, float* grad_w,
+                                  void* stream) {
+    if (N == 0) return 0;
+    PS_REQUIRE(c && w && loss_sum, "distortion_loss: null pointer");
+    PS_REQUIRE(S >= 1 && S <= 1024, "distortion_loss: samples per ray %d out of range [1,1024]", S);
+    const size_t smem = (size_t)kLossWarps * 2 * S * sizeof(float);
+    distortion_kernel<<<(unsigned)cdiv(N, kLossWarps), kLossWarps * 32, smem, (cudaStream_t)stream>>>(c, w, N, S, loss_sum,
+                                                                                                   grad_w);
+    return check_launch("distortion_loss");
+}
 
 extern "C" int ps_interlevel_loss(const float* c, const float* w, const float* t_env, const float* w_env, int64_t N,
                                   int S, int Sp, float* loss_sum, float* grad_w_env, void* stream) {

@@ -47,6 +47,25 @@ def interlevel_loss(weights_list: List[Tensor], sp_bins_list: List[Tensor]) -> T
     return loss
 
 
+def lossfun_distortion(t: Tensor, w: Tensor) -> Tensor:
+    """losses.py:130-143 (torch restatement; documents the arithmetic of `ps_distortion_loss`)."""
+    ut = (t[..., 1:] + t[..., :-1]) / 2
+    dut = torch.abs(ut[..., :, None] - ut[..., None, :])
+    loss_inter = torch.sum(w * torch.sum(w[..., None, :] * dut, dim=-1), dim=-1)
+    loss_intra = torch.sum(w ** 2 * (t[..., 1:] - t[..., :-1]), dim=-1) / 3
+    return loss_inter + loss_intra
+
+
+def distortion_loss(weights_list: List[Tensor], sp_bins_list: List[Tensor]) -> Tensor:
+    """losses.py:145-149: distortion of the final level's weights along the spacing-domain bins.  CUDA tensors: one
+    kernel producing the loss and d loss / d weights (`ps_distortion_loss`)."""
+    c, w = sp_bins_list[-1].detach(), weights_list[-1]
+    if w.is_cuda:
+        from . import ops
+        return ops.distortion_loss(c, w)
+    return torch.mean(lossfun_distortion(c, w[..., 0]))
+
+
 def sky_loss(accumulation: Tensor, sky_mask: Tensor, eps: float = 1e-7) -> Tensor:
     """PreSight/losses.py:104-114."""
     target = 1.0 - sky_mask

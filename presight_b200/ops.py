@@ -477,6 +477,37 @@ class _InterlevelLoss(torch.autograd.Function):
         return None, None, None, out
 
 
+class _DistortionLoss(torch.autograd.Function):
+    """mean over rays of lossfun_distortion(c, w) (model_components/losses.py:130-149) with the gradient w.r.t. the
+    weights produced in the same kernel; c (bin edges) is a constant."""
+
+    @staticmethod
+    def forward(ctx, c, w):
+        cc, wc = _f32c(c.detach()), _f32c(w.detach())
+        N, S = wc.shape[0], wc.shape[1]
+        assert cc.shape == (N, S + 1) and wc.numel() == N * S, "distortion_loss: c must be [N,S+1], w [N,S] or [N,S,1]"
+        loss = torch.zeros(1, device=wc.device, dtype=torch.float32)
+        need = ctx.needs_input_grad[1]
+        grad = torch.empty(N, S, device=wc.device, dtype=torch.float32) if need else None
+        with _probe("distortion_loss"):
+            call("ps_distortion_loss", ptr(cc), ptr(wc.view(N, S)), N, S, ptr(loss), ptr(grad), stream())
+        ctx.scale = 1.0 / float(max(N, 1))
+        ctx.wshape = w.shape
+        if need:
+            ctx.save_for_backward(grad)
+        return loss[0] * ctx.scale
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return None, (grad * (g * ctx.scale)).view(ctx.wshape)
+
+
+def distortion_loss(c: Tensor, w: Tensor) -> Tensor:
+    """c [N,S+1] spacing-domain bin edges, w [N,S] or [N,S,1] weights of the final level -> scalar."""
+    return _DistortionLoss.apply(c, w)
+
+
 def interlevel_loss_level(c: Tensor, w: Tensor, t_env: Tensor, w_env: Tensor) -> Tensor:
     """One proposal level's term of interlevel_loss: c [N,S+1], w [N,S], t_env [N,Sp+1], w_env [N,Sp] or [N,Sp,1]
     (the gradient comes back in w_env's shape) -> scalar."""

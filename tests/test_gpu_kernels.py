@@ -439,6 +439,32 @@ def test_interlevel_loss_kernel_random(ops):
         assert_close(wg.grad.cpu(), we.grad, TOL32, f"grad {N}x{S}x{Sp}")
 
 
+@pytest.mark.parametrize("case", ["a", "b", "c", "d"])
+def test_distortion_loss_kernel_golden(ops, case):
+    """ps_distortion_loss (loss + gradient in one kernel) vs the live reference's fixture, and on a large ragged batch vs
+    the oracle."""
+    from presight_b200 import losses
+    fx = Fixture("distortion.npz")
+    c, w = fx[f"{case}/c"].to(DEV), fx[f"{case}/w"].to(DEV).requires_grad_(True)
+    loss = losses.distortion_loss([w], [c])
+    assert_close(loss.cpu(), fx[f"{case}/loss"], 1e-5, "distortion loss")
+    (loss * 3.0).backward()
+    assert w.grad.shape == w.shape
+    assert_close(w.grad.cpu(), 3.0 * fx[f"{case}/g"], 1e-5, "grad")
+    if case == "a":
+        g = torch.Generator().manual_seed(2)
+        N, S = 3001, 64
+        cc = torch.rand(N, S + 1, generator=g).sort(-1).values
+        ww = (torch.rand(N, S, generator=g) ** 3 * 0.1).requires_grad_(True)
+        want = O.distortion_loss([ww[..., None]], [cc])
+        want.backward()
+        wg = ww.detach().to(DEV).requires_grad_(True)
+        got = ops.distortion_loss(cc.to(DEV), wg)
+        got.backward()
+        assert_close(got.cpu(), want, 1e-5, "loss (random)")
+        assert_close(wg.grad.cpu(), ww.grad, 1e-5, "grad (random)")
+
+
 @pytest.mark.parametrize("case", ["a", "b"])
 def test_sky_blend_and_render_losses_golden(ops, case):
     """ps_sky_blend_fwd/bwd + ps_render_losses vs the live reference's fixture: blended outputs bit-exact, loss terms
