@@ -91,14 +91,13 @@ def workload_name(name: str) -> str:
 
 # ------------------------------------------------------------------------------------------------ loss
 def step_loss(model, out, batch):
-    """rgb MSE + sky BCE + semantic MSE + interlevel + distortion — the loss dict of a camera-only training step
-    (nerfacto_nusc_ms.py:558-645, multipliers :127,:133,:167,:192)."""
-    from presight_b200 import losses
-    terms = losses.render_losses(out, batch, model.config.use_sky_model, model.config.use_semantics)   # one kernel
-    loss = terms[0] + 0.001 * terms[1] + 0.5 * terms[2]
-    sp = [rs.sp_bins for rs in out["ray_samples_list"]]
-    loss = loss + 1.0 * losses.interlevel_loss(out["weights_list"], sp)
-    loss = loss + 0.002 * losses.distortion_loss(out["weights_list"], sp)          # distortion_loss_mult (:133)
+    """The loss dict of a camera-only training step — rgb MSE, sky BCE, semantic MSE, (z-anti-aliased) interlevel,
+    distortion — summed as the trainer does (nerfacto_nusc_ms.py:558-645 with the multipliers of :127-133,167,192;
+    trainer.py:498 `functools.reduce(torch.add, loss_dict.values())`)."""
+    loss_dict = model.get_loss_dict(out, batch)
+    loss = None
+    for v in loss_dict.values():
+        loss = v if loss is None else loss + v
     return loss
 
 
@@ -146,8 +145,12 @@ def cpu_reference_step(omodel, emb, cfg, batch, n):
         loss = loss + 0.001 * O.sky_loss(out["accumulation"].view(-1, 1), batch["sky"][:n].view(-1, 1))
     if cfg.use_semantics:
         loss = loss + 0.5 * O.semantic_loss(out["semantics"], batch["features"][:n])
-    loss = loss + O.interlevel_loss(out["weights_list"], [b[0] for b in out["bins_list"]])
-    loss = loss + 0.002 * O.distortion_loss(out["weights_list"], [b[0] for b in out["bins_list"]])
+    sp = [b[0] for b in out["bins_list"]]
+    if cfg.enable_z_anti_aliasing:
+        loss = loss + cfg.interlevel_loss_mult * O.z_anti_aliasing_interlevel_loss(out["weights_list"], sp, cfg.pulse_width)
+    else:
+        loss = loss + cfg.interlevel_loss_mult * O.interlevel_loss(out["weights_list"], sp)
+    loss = loss + cfg.distortion_loss_mult * O.distortion_loss(out["weights_list"], sp)
     params = [f.grid.table for f in omodel.fields] + [p.grid.table for lvl in omodel.props for p in lvl]
     for p in params:
         p.grad = None

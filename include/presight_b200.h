@@ -206,6 +206,15 @@ int ps_composite_bwd(const float* eu_bins, const float* density, const float* rg
  */
 int ps_interlevel_loss(const float* c, const float* w, const float* t_env, const float* w_env, int64_t N, int S,
                        int Sp, float* loss_sum, float* grad_w_env, void* stream);
+/* z-anti-aliased (zip-NeRF) interlevel loss — the reference's DEFAULT proposal loss (enable_z_anti_aliasing,
+ * models/PreSight/nerfacto_nusc_ms.py:129,293-295): blur_stepfun + sorted_interp_quad + the per-level body of
+ * z_anti_anliasing_interlevel_loss (model_components/PreSight/losses.py:127-206), one launch per proposal level.
+ *   c [N,S+1], w [N,S]            final level's spacing-domain bin edges and weights (constants), S <= 128
+ *   t_env [N,Sp+1], w_env [N,Sp]  proposal level's bin edges and weights;  pulse_width = config.pulse_width[level]
+ *   loss_sum [1] += sum over rays and proposal samples of max(w_s - w_env, 0)^2 / (w_env + 1e-5)  (caller-zeroed; the
+ *   reference's value is loss_sum / (N * Sp));  grad_w_env [N,Sp] (nullable) = d loss_sum / d w_env (written). */
+int ps_zaa_interlevel_loss(const float* c, const float* w, int64_t N, int S, const float* t_env, const float* w_env,
+                           int Sp, double pulse_width, float* loss_sum, float* grad_w_env, void* stream);
 /* Distortion loss of mip-NeRF 360 (lossfun_distortion / distortion_loss, model_components/losses.py:130-149).
  *   c [N,S+1] spacing-domain bin edges and w [N,S] weights of the final level
  *   loss_sum [1] += sum over rays of (sum_ij w_i w_j |u_i - u_j| + sum_i w_i^2 (c_{i+1} - c_i) / 3), u = bin mid-points

@@ -34,7 +34,7 @@ __all__ = [
     "render_depth_expected", "render_depth_threshold", "proposal_sample", "model_outputs",
     "model_depth", "prior_query", "sky_outputs", "PRIME_Y", "PRIME_Z", "mlp_forward_bf16_emulated",
     "loss_outer", "lossfun_outer", "interlevel_loss", "sky_blend", "rgb_loss", "sky_loss", "semantic_loss",
-    "lossfun_distortion", "distortion_loss",
+    "lossfun_distortion", "distortion_loss", "blur_stepfun", "sorted_interp_quad", "z_anti_aliasing_interlevel_loss",
 ]
 
 PRIME_Y = 2654435761  # ENC:336
@@ -484,6 +484,56 @@ def interlevel_loss(weights_list: Sequence[Tensor], sp_bins_list: Sequence[Tenso
     loss = 0.0
     for sdist, weights in zip(sp_bins_list[:-1], weights_list[:-1]):
         loss = loss + torch.mean(lossfun_outer(c, w, sdist, weights[..., 0]))
+    return loss
+
+
+def blur_stepfun(x: Tensor, y: Tensor, r: float) -> Tuple[Tensor, Tensor]:
+    """Step function (x [.., S+1] edges, y [.., S] heights) convolved with a box of half-width r -> piecewise-linear
+    (xr [.., 2S+2], yr [.., 2S+2]).  Restates model_components/PreSight/losses.py:127-139."""
+    xr, xr_idx = torch.sort(torch.cat([x - r, x + r], dim=-1))
+    y1 = (torch.cat([y, torch.zeros_like(y[..., :1])], dim=-1)
+          - torch.cat([torch.zeros_like(y[..., :1]), y], dim=-1)) / (2 * r)
+    y2 = torch.cat([y1, -y1], dim=-1).take_along_dim(xr_idx[..., :-1], dim=-1)
+    yr = torch.cumsum((xr[..., 1:] - xr[..., :-1]) * torch.cumsum(y2, dim=-1), dim=-1).clamp_min(0)
+    yr = torch.cat([torch.zeros_like(yr[..., :1]), yr], dim=-1)
+    return xr, yr
+
+
+def sorted_interp_quad(x: Tensor, xp: Tensor, fpdf: Tensor, fcdf: Tensor) -> Tensor:
+    """Integral of the piecewise-linear density (knots xp, values fpdf, running integral fcdf) evaluated at the sorted
+    query points x.  Restates PreSight/losses.py:141-164."""
+    mask = x[..., None, :] >= xp[..., :, None]
+
+    def find_interval(v, return_idx=False):
+        v0, i0 = torch.max(torch.where(mask, v[..., None], v[..., :1, None]), -2)
+        v1, i1 = torch.min(torch.where(~mask, v[..., None], v[..., -1:, None]), -2)
+        return (v0, v1, i0, i1) if return_idx else (v0, v1)
+
+    fcdf0, fcdf1, i0, i1 = find_interval(fcdf, return_idx=True)
+    fpdf0 = fpdf.take_along_dim(i0, dim=-1)
+    fpdf1 = fpdf.take_along_dim(i1, dim=-1)
+    xp0, xp1 = find_interval(xp)
+    offset = torch.clip(torch.nan_to_num((x - xp0) / (xp1 - xp0), 0), 0, 1)
+    return fcdf0 + (x - xp0) * (fpdf0 + fpdf1 * offset + fpdf0 * (1 - offset)) / 2
+
+
+def z_anti_aliasing_interlevel_loss(weights_list: Sequence[Tensor], sp_bins_list: Sequence[Tensor],
+                                    pulse_width: Sequence[float]) -> Tensor:
+    """zip-NeRF proposal loss, the reference's default (`enable_z_anti_aliasing`, MODEL:129,293-295).  Restates
+    PreSight/losses.py:166-206: the final level's histogram, blurred with a per-level pulse width, is integrated over
+    each proposal level's bins and the proposal weights are pushed up to that envelope."""
+    c = sp_bins_list[-1].detach()
+    w = weights_list[-1][..., 0].detach()
+    w_normalized = w / (c[..., 1:] - c[..., :-1])
+    loss = 0.0
+    for i, (cp, weights) in enumerate(zip(sp_bins_list[:-1], weights_list[:-1])):
+        ci, wi = blur_stepfun(c, w_normalized, pulse_width[i])
+        area = 0.5 * (wi[..., 1:] + wi[..., :-1]) * (ci[..., 1:] - ci[..., :-1])
+        cdfs = torch.cat([torch.zeros_like(area[..., :1]), torch.cumsum(area, dim=-1)], dim=-1)
+        wp = weights[..., 0]
+        cdf_interp = sorted_interp_quad(cp, ci, wi, cdfs)
+        w_s = torch.diff(cdf_interp, dim=-1)
+        loss = loss + ((w_s - wp).clamp_min(0) ** 2 / (wp + 1e-5)).mean()
     return loss
 
 

@@ -54,6 +54,7 @@ SIGNATURES = {
     "ps_composite_bwd": [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "ps_interlevel_loss": [_p, _p, _p, _p, _i64, _i, _i, _p, _p, _p],
     "ps_distortion_loss": [_p, _p, _i64, _i, _p, _p, _p],
+    "ps_zaa_interlevel_loss": [_p, _p, _i64, _i, _p, _p, _i, C.c_double, _p, _p, _p],
     "ps_sky_blend_fwd": [_p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p],
     "ps_sky_blend_bwd": [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p],
     "ps_render_losses": [_p, _p, _p, _p, _p, _p, _i64, _i, _f, _p, _p, _p, _p, _p],

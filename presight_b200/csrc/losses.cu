@@ -8,6 +8,8 @@
 // d loss_i / d w_env[k] = g_i * ([k <= idx_hi_i] - [k < idx_lo_i]),  g_i = -2 max(w_i - w_outer_i, 0) / (w_i + 1e-7),
 // accumulated through two per-ray histograms (A over idx_hi, B over idx_lo) and suffix sums.
 #include "sampler.cuh"
+#define PS_HD __host__ __device__
+#include "zaa_core.h"
 
 namespace ps {
 
@@ -108,9 +110,40 @@ __global__ void __launch_bounds__(kLossWarps * 32) distortion_kernel(const float
     if (lane == 0) atomicAdd(loss_sum, loss);
 }
 
+// z-anti-aliased (zip-NeRF) interlevel loss, one proposal level per launch: one THREAD per ray runs zaa_core.h's
+// sequential per-ray code (merge of the two shifted edge lists, the nested fp64-carried cumsums, a forward sweep over
+// the sorted query edges).  First version: correctness against the reference's tie semantics first; a warp-per-ray
+// variant (merge by rank, warp scans) is the obvious next step if it ever shows up in the step's profile.
+__global__ void __launch_bounds__(128) zaa_interlevel_kernel(const float* __restrict__ c, const float* __restrict__ w,
+                                                             int64_t N, int S, const float* __restrict__ cp,
+                                                             const float* __restrict__ wp, int Sp, double r,
+                                                             float* __restrict__ loss_sum, float* __restrict__ grad_wp) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float l = 0.f;
+    if (n < N)
+        l = zaa::ray_loss(c + n * (S + 1), w + n * S, S, cp + n * (Sp + 1), wp + n * Sp, Sp, r,
+                          grad_wp ? grad_wp + n * Sp : nullptr);
+    l = warp_sum(l);
+    if ((threadIdx.x & 31) == 0 && l != 0.f) atomicAdd(loss_sum, l);
+}
+
 }  // namespace ps
 
 using namespace ps;
+
+extern "C" int ps_zaa_interlevel_loss(const float* c, const float* w, int64_t N, int S, const float* t_env,
+                                      const float* w_env, int Sp, double pulse_width, float* loss_sum, float* grad_w_env,
+                                      void* stream) {
+    if (N == 0) return 0;
+    PS_REQUIRE(c && w && t_env && w_env && loss_sum, "zaa_interlevel_loss: null pointer");
+    PS_REQUIRE(S >= 1 && S <= zaa::kMaxS, "zaa_interlevel_loss: final-level samples per ray %d out of range [1,%d]", S,
+               zaa::kMaxS);
+    PS_REQUIRE(Sp >= 1, "zaa_interlevel_loss: proposal samples per ray %d < 1", Sp);
+    PS_REQUIRE(pulse_width > 0.0, "zaa_interlevel_loss: pulse width must be positive");
+    zaa_interlevel_kernel<<<(unsigned)cdiv(N, 128), 128, 0, (cudaStream_t)stream>>>(c, w, N, S, t_env, w_env, Sp,
+                                                                                  pulse_width, loss_sum, grad_w_env);
+    return check_launch("zaa_interlevel_loss");
+}
 
 extern "C" int ps_distortion_loss(const float* c, const float* w, int64_t N, int S, float* loss_sum, float* grad_w,
                                   void* stream) {

@@ -47,6 +47,20 @@ def interlevel_loss(weights_list: List[Tensor], sp_bins_list: List[Tensor]) -> T
     return loss
 
 
+def z_anti_aliasing_interlevel_loss(weights_list: List[Tensor], sp_bins_list: List[Tensor],
+                                    pulse_width=(0.03, 0.003)) -> Tensor:
+    """zip-NeRF proposal loss, the reference's default (`enable_z_anti_aliasing`, nerfacto_nusc_ms.py:129,293-295;
+    model_components/PreSight/losses.py:166-206).  One kernel per proposal level (`ps_zaa_interlevel_loss`: loss and
+    d loss / d proposal weights), CUDA tensors only."""
+    from . import ops
+    c = sp_bins_list[-1].detach()
+    w = weights_list[-1][..., 0].detach()
+    loss = 0.0
+    for i, (sdist, weights) in enumerate(zip(sp_bins_list[:-1], weights_list[:-1])):
+        loss = loss + ops.zaa_interlevel_loss_level(c, w, sdist, weights, pulse_width[i])
+    return loss
+
+
 def lossfun_distortion(t: Tensor, w: Tensor) -> Tensor:
     """losses.py:130-143 (torch restatement; documents the arithmetic of `ps_distortion_loss`)."""
     ut = (t[..., 1:] + t[..., :-1]) / 2

@@ -66,6 +66,13 @@ class NerfactoNuscMSModelConfig:
     semantic_dim: int = 64
     use_average_appearance_embedding: bool = True
     eval_num_rays_per_chunk: int = 1 << 15
+    # loss dict (nerfacto_nusc_ms.py:127-133,167,192)
+    interlevel_loss_mult: float = 1.0
+    enable_z_anti_aliasing: bool = True
+    pulse_width: Tuple[float, ...] = (0.03, 0.003)
+    distortion_loss_mult: float = 0.002
+    sky_loss_mult: float = 0.001
+    semantic_loss_mult: float = 0.5
 
 
 class _EmbeddingLookup(torch.autograd.Function):
@@ -269,6 +276,31 @@ class NerfactoNuscMSModel(nn.Module):
         for i in range(self.config.num_proposal_iterations):
             outputs[f"prop_depth_{i}"] = self.renderer_depth(weights=weights_list[i], ray_samples=ray_samples_list[i])
         return outputs
+
+    def get_loss_dict(self, outputs: Dict[str, object], batch: Dict[str, Tensor]) -> Dict[str, Tensor]:
+        """The camera-only terms of nerfacto_nusc_ms.py:558-645 (rgb, sky, semantic, interlevel, distortion), each on its
+        kernel: `ps_render_losses` for the three rendered-output terms, `ps_zaa_interlevel_loss` / `ps_interlevel_loss`
+        per proposal level, `ps_distortion_loss`.  batch: "rgb" [N,3], "sky" [N,1] (1 = sky), "features" [N,C]."""
+        from . import losses
+        c = self.config
+        use_sky = c.use_sky_model and "sky" in batch
+        use_sem = c.use_semantics and "features" in batch
+        terms = losses.render_losses(outputs, batch, use_sky, use_sem)
+        loss_dict = {"rgb_loss": terms[0]}
+        if use_sky:
+            loss_dict["sky_loss"] = c.sky_loss_mult * terms[1]
+        if use_sem:
+            loss_dict["semantic_loss"] = c.semantic_loss_mult * terms[2]
+        if self.training:
+            wl = outputs["weights_list"]
+            sp = [rs.sp_bins for rs in outputs["ray_samples_list"]]
+            if c.enable_z_anti_aliasing:
+                il = losses.z_anti_aliasing_interlevel_loss(wl, sp, c.pulse_width)
+            else:
+                il = losses.interlevel_loss(wl, sp)
+            loss_dict["interlevel_loss"] = c.interlevel_loss_mult * il
+            loss_dict["distortion_loss"] = c.distortion_loss_mult * losses.distortion_loss(wl, sp)
+        return loss_dict
 
     def get_depth(self, ray_bundle: RayBundle, threshold: float = 0.5) -> Dict[str, object]:
         """nerfacto_nusc_ms.py:688-708."""

@@ -477,6 +477,41 @@ class _InterlevelLoss(torch.autograd.Function):
         return None, None, None, out
 
 
+class _ZaaInterlevelLoss(torch.autograd.Function):
+    """One proposal level's term of z_anti_anliasing_interlevel_loss (model_components/PreSight/losses.py:166-206) with
+    the gradient w.r.t. the proposal weights produced in the same kernel; c and w are constants (detached there)."""
+
+    @staticmethod
+    def forward(ctx, c, w, t_env, w_env, pulse_width):
+        c, w, t_env, we = _f32c(c.detach()), _f32c(w.detach()), _f32c(t_env.detach()), _f32c(w_env.detach())
+        N, S = w.shape[0], w.shape[1]
+        Sp = we.shape[1]
+        assert c.shape == (N, S + 1) and t_env.shape == (N, Sp + 1) and we.numel() == N * Sp
+        loss = torch.zeros(1, device=w.device, dtype=torch.float32)
+        need = ctx.needs_input_grad[3]
+        grad = torch.empty(N, Sp, device=w.device, dtype=torch.float32) if need else None
+        with _probe("zaa_interlevel_loss"):
+            call("ps_zaa_interlevel_loss", ptr(c), ptr(w), N, S, ptr(t_env), ptr(we.view(N, Sp)), Sp, float(pulse_width),
+                 ptr(loss), ptr(grad), stream())
+        ctx.scale = 1.0 / float(N * Sp)
+        ctx.wshape = w_env.shape
+        if need:
+            ctx.save_for_backward(grad)
+        return loss[0] * ctx.scale
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        out = (grad * (g * ctx.scale)).view(ctx.wshape)
+        publish_grad_event(out)
+        return None, None, None, out, None
+
+
+def zaa_interlevel_loss_level(c: Tensor, w: Tensor, t_env: Tensor, w_env: Tensor, pulse_width: float) -> Tensor:
+    """c [N,S+1], w [N,S] final level (constants); t_env [N,Sp+1], w_env [N,Sp] or [N,Sp,1] -> scalar."""
+    return _ZaaInterlevelLoss.apply(c, w, t_env, w_env, float(pulse_width))
+
+
 class _DistortionLoss(torch.autograd.Function):
     """mean over rays of lossfun_distortion(c, w) (model_components/losses.py:130-149) with the gradient w.r.t. the
     weights produced in the same kernel; c (bin edges) is a constant."""

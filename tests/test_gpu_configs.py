@@ -126,6 +126,37 @@ def test_c2_shapes_match_oracle(impl, tol, gtol):
     assert rel_l2(g["field.fields.0.rgb_head.layers.0.weight"].grad.cpu(), om.fields[0].rgb.weights[0].grad) < gtol
 
 
+def test_c2_loss_dict_matches_oracle():
+    """`get_loss_dict` (rgb / sky / semantic / z-anti-aliased interlevel / distortion kernels) at C2 shapes: every term
+    against the oracle's restatement of the reference's loss function evaluated on the SAME rendered outputs, weights
+    and bins (so the comparison isolates the loss kernels from the sampling), fp32 tolerances."""
+    from presight_b200.cameras.rays import RayBundle
+    from presight_b200.model import VIDEO_ID
+    n = 256
+    model, cfg, host = build("c2", "b200", n)
+    rb = RayBundle(origins=host["origins"].to(DEV), directions=host["directions"].to(DEV),
+                   camera_indices=host["camera_indices"].to(DEV), metadata={VIDEO_ID: host["video_ids"].to(DEV)})
+    model.proposal_sampler._step = 0
+    out = model(rb)
+    batch = {k: host[k].to(DEV) for k in ("rgb", "sky", "features")}
+    ld = model.get_loss_dict(out, batch)
+    assert set(ld) == {"rgb_loss", "sky_loss", "semantic_loss", "interlevel_loss", "distortion_loss"}
+    wl = [w.detach().cpu() for w in out["weights_list"]]
+    sp = [rs.sp_bins.detach().cpu() for rs in out["ray_samples_list"]]
+    rgb, acc, sem = (out[k].detach().cpu() for k in ("rgb", "accumulation", "semantics"))
+    want = {"rgb_loss": O.rgb_loss(host["rgb"], rgb),
+            "sky_loss": cfg.sky_loss_mult * O.sky_loss(acc.view(-1, 1), host["sky"].view(-1, 1)),
+            "semantic_loss": cfg.semantic_loss_mult * O.semantic_loss(sem, host["features"]),
+            "interlevel_loss": cfg.interlevel_loss_mult * O.z_anti_aliasing_interlevel_loss(wl, sp, cfg.pulse_width),
+            "distortion_loss": cfg.distortion_loss_mult * O.distortion_loss(wl, sp)}
+    for k, v in want.items():
+        assert_close(ld[k].detach().cpu(), v, 1e-4, k)
+    sum(ld.values()).backward()
+    grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    assert len(grads) >= 30 and all(bool(torch.isfinite(g).all()) for g in grads.values())
+    assert "proposal_networks.0.fields.0.encoding.hash_table" in grads and "field.fields.0.mlp_base_grid.hash_table" in grads
+
+
 @pytest.mark.parametrize("impl,tol", [("b200+fp32", 1e-3), ("b200", 1e-2)])
 def test_c5_prior_query_full_grid(impl, tol):
     """C5: the 400 x 200 x 16 grid of one tile (1.28 M points) through query_priors; the oracle checks a random

@@ -439,6 +439,25 @@ def test_interlevel_loss_kernel_random(ops):
         assert_close(wg.grad.cpu(), we.grad, TOL32, f"grad {N}x{S}x{Sp}")
 
 
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_zaa_interlevel_loss_kernel_golden(ops, case):
+    """ps_zaa_interlevel_loss (the reference's default proposal loss; loss + gradient in one kernel per level) vs the
+    live reference's fixture, incl. the rays with near-degenerate bins whose result depends on the reference's
+    argmax-on-ties interval selection."""
+    from presight_b200 import losses
+    fx = Fixture("zaa.npz")
+    pulse = [float(v) for v in fx.np("pulse_width")]
+    n = int(fx.np(f"{case}/n_levels"))
+    c, w = fx[f"{case}/c"].to(DEV), fx[f"{case}/w"].to(DEV)
+    ws = [fx[f"{case}/w{i}"].to(DEV).requires_grad_(True) for i in range(n)]
+    ts = [fx[f"{case}/t{i}"].to(DEV) for i in range(n)]
+    loss = losses.z_anti_aliasing_interlevel_loss([x[..., None] for x in ws] + [w[..., None]], ts + [c], pulse)
+    assert_close(loss.cpu(), fx[f"{case}/loss"], 1e-5, "zaa interlevel loss")
+    (loss * 2.0).backward()
+    for i in range(n):
+        assert_close(ws[i].grad.cpu(), 2.0 * fx[f"{case}/g{i}"], 2e-5, f"grad level {i}")
+
+
 @pytest.mark.parametrize("case", ["a", "b", "c", "d"])
 def test_distortion_loss_kernel_golden(ops, case):
     """ps_distortion_loss (loss + gradient in one kernel) vs the live reference's fixture, and on a large ragged batch vs
