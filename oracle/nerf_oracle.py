@@ -35,6 +35,8 @@ __all__ = [
     "model_depth", "prior_query", "sky_outputs", "PRIME_Y", "PRIME_Z", "mlp_forward_bf16_emulated",
     "loss_outer", "lossfun_outer", "interlevel_loss", "sky_blend", "rgb_loss", "sky_loss", "semantic_loss",
     "lossfun_distortion", "distortion_loss", "blur_stepfun", "sorted_interp_quad", "z_anti_aliasing_interlevel_loss",
+    "normalize_depth", "expected_monodepth_loss", "expected_depth_loss", "line_of_sight_loss", "line_of_sight_sigma",
+    "line_of_sight_mult",
 ]
 
 PRIME_Y = 2654435761  # ENC:336
@@ -549,6 +551,68 @@ def lossfun_distortion(t: Tensor, w: Tensor) -> Tensor:
 def distortion_loss(weights_list: Sequence[Tensor], sp_bins_list: Sequence[Tensor]) -> Tensor:
     """LS:145-149 (the final level's weights are NOT detached here: the gradient reaches the field)."""
     return torch.mean(lossfun_distortion(sp_bins_list[-1], weights_list[-1][..., 0]))
+
+
+URF_SIGMA_SCALE_FACTOR = 3.0   # PL:22
+
+
+def normalize_depth(depth: Tensor, upper_bound: float = 75.0) -> Tensor:
+    """PL:25-26."""
+    return torch.clip(depth / upper_bound, 0.0, 1.0)
+
+
+def expected_monodepth_loss(termination_depth: Tensor, predicted_depth: Tensor, sky_mask: Tensor,
+                            upper_bound: float = 50.0, inverse: bool = False) -> Tensor:
+    """Monocular-depth supervision of the expected depth (model_components/PreSight/losses.py:83-103): MSE of the
+    normalised (or inverse) depths over rays with 1 < depth < upper_bound that are not sky."""
+    depth_mask = (termination_depth > 1.0) & (termination_depth < upper_bound) & (sky_mask == 0.0)
+    if inverse:
+        termination_depth = 1 / (termination_depth + 5)
+        predicted_depth = 1 / (predicted_depth + 5)
+    else:
+        termination_depth = normalize_depth(termination_depth, upper_bound=upper_bound)
+        predicted_depth = normalize_depth(predicted_depth, upper_bound=upper_bound)
+    return torch.mean(((termination_depth - predicted_depth) ** 2)[depth_mask])
+
+
+def expected_depth_loss(termination_depth: Tensor, predicted_depth: Tensor, upper_bound: float = 75.0) -> Tensor:
+    """LiDAR variant (PL:67-81): no sky mask."""
+    depth_mask = (termination_depth > 1.0) & (termination_depth < upper_bound)
+    t = normalize_depth(termination_depth, upper_bound=upper_bound)
+    p = normalize_depth(predicted_depth, upper_bound=upper_bound)
+    return torch.mean(((t - p) ** 2)[depth_mask])
+
+
+def line_of_sight_loss(weights: Tensor, termination_depth: Tensor, steps: Tensor, sigma: float,
+                       sky_mask: Optional[Tensor] = None, upper_bound: float = 75.0) -> Tensor:
+    """Urban-Radiance-Fields line-of-sight loss (PL:28-65).  weights [N,S,1], termination_depth [N,1], steps [N,S,1]
+    (sample mid-points in metres): inside +-sigma of the target depth the weights follow a Gaussian of std sigma / 3,
+    in front of it they are pushed to zero; mean over rays with a valid, non-sky depth."""
+    depth_mask = (termination_depth > 1.0) & (termination_depth < upper_bound)
+    if sky_mask is not None:
+        depth_mask = depth_mask & (sky_mask == 0.0)
+    steps = steps.detach()
+    td = termination_depth[:, None]
+    std = sigma / URF_SIGMA_SCALE_FACTOR
+    log_prob = -((steps - td) ** 2) / (2 * std ** 2) - math.log(std) - math.log(math.sqrt(2 * math.pi))
+    near_mask = torch.logical_and(steps <= td + sigma, steps >= td - sigma)
+    near = (near_mask * (weights - torch.exp(log_prob)) ** 2).sum(-2)
+    empty = ((steps < td - sigma) * weights ** 2).sum(-2)
+    return torch.mean((near + empty)[depth_mask])
+
+
+def line_of_sight_sigma(step: int, start_step: int = 1000, end_step: int = 30000, max_sigma: float = 5.0,
+                        min_sigma: float = 2.0) -> float:
+    """MODEL:387-396."""
+    frac = float(np.clip((step - start_step) / (end_step - start_step), 0.0, 1.0))
+    return max_sigma - frac * (max_sigma - min_sigma)
+
+
+def line_of_sight_mult(step: int, start_step: int = 1000, decay_steps: int = 5000, mult: float = 0.1) -> float:
+    """MODEL:398-403."""
+    if step <= start_step:
+        return 0.0
+    return mult / (2.0 ** (step // decay_steps))
 
 
 def sky_blend(rgb_f: Tensor, acc_raw: Tensor, sem_f: Optional[Tensor], sky_rgb: Optional[Tensor],

@@ -80,6 +80,49 @@ def distortion_loss(weights_list: List[Tensor], sp_bins_list: List[Tensor]) -> T
     return torch.mean(lossfun_distortion(c, w[..., 0]))
 
 
+# ---- depth supervision (PreSight/losses.py:25-103).  These three are still plain torch expressions (SURVEY 8f-1 lists
+# them as the remaining rows of the loss stack); they are reached only when the batch carries a "depth" target.
+URF_SIGMA_SCALE_FACTOR = 3.0
+
+
+def normalize_depth(depth: Tensor, upper_bound: float = 75.0) -> Tensor:
+    return torch.clip(depth / upper_bound, 0.0, 1.0)
+
+
+def expected_monodepth_loss(termination_depth: Tensor, predicted_depth: Tensor, sky_mask: Tensor,
+                            upper_bound: float = 50.0, inverse: bool = False) -> Tensor:
+    """PreSight/losses.py:83-103."""
+    depth_mask = (termination_depth > 1.0) & (termination_depth < upper_bound) & (sky_mask == 0.0)
+    if inverse:
+        termination_depth, predicted_depth = 1 / (termination_depth + 5), 1 / (predicted_depth + 5)
+    else:
+        termination_depth = normalize_depth(termination_depth, upper_bound)
+        predicted_depth = normalize_depth(predicted_depth, upper_bound)
+    return torch.mean(((termination_depth - predicted_depth) ** 2)[depth_mask])
+
+
+def expected_depth_loss(termination_depth: Tensor, predicted_depth: Tensor, upper_bound: float = 75.0) -> Tensor:
+    """PreSight/losses.py:67-81."""
+    depth_mask = (termination_depth > 1.0) & (termination_depth < upper_bound)
+    diff = normalize_depth(termination_depth, upper_bound) - normalize_depth(predicted_depth, upper_bound)
+    return torch.mean((diff ** 2)[depth_mask])
+
+
+def line_of_sight_loss(weights: Tensor, termination_depth: Tensor, steps: Tensor, sigma: float,
+                       sky_mask: Tensor = None, upper_bound: float = 75.0) -> Tensor:
+    """PreSight/losses.py:28-65 (Urban Radiance Fields): weights [N,S,1], termination_depth [N,1], steps [N,S,1]."""
+    depth_mask = (termination_depth > 1.0) & (termination_depth < upper_bound)
+    if sky_mask is not None:
+        depth_mask = depth_mask & (sky_mask == 0.0)
+    steps = steps.detach()
+    td = termination_depth[:, None]
+    target = torch.distributions.normal.Normal(0.0, sigma / URF_SIGMA_SCALE_FACTOR)
+    near_mask = torch.logical_and(steps <= td + sigma, steps >= td - sigma)
+    near = (near_mask * (weights - torch.exp(target.log_prob(steps - td))) ** 2).sum(-2)
+    empty = ((steps < td - sigma) * weights ** 2).sum(-2)
+    return torch.mean((near + empty)[depth_mask])
+
+
 def sky_loss(accumulation: Tensor, sky_mask: Tensor, eps: float = 1e-7) -> Tensor:
     """PreSight/losses.py:104-114."""
     target = 1.0 - sky_mask

@@ -73,6 +73,19 @@ class NerfactoNuscMSModelConfig:
     distortion_loss_mult: float = 0.002
     sky_loss_mult: float = 0.001
     semantic_loss_mult: float = 0.5
+    # depth supervision (:169-199); needs batch["depth"] (metres) and batch["pose_scale_factor"]
+    use_lidar_loss: bool = False
+    use_monodepth_loss: bool = False
+    expected_depth_loss_mult: float = 1.0
+    lidar_depth_upperbound: float = 75.0
+    monodepth_depth_upperbound: float = 40.0
+    monodepth_loss_inverse: bool = False
+    line_of_sight_mult: float = 0.1
+    line_of_sight_decay_steps: int = 5000
+    line_of_sight_start_step: int = 1000
+    line_of_sight_end_step: int = 30000
+    line_of_sight_max_sigma: float = 5.0
+    line_of_sight_min_sigma: float = 2.0
 
 
 class _EmbeddingLookup(torch.autograd.Function):
@@ -277,6 +290,22 @@ class NerfactoNuscMSModel(nn.Module):
             outputs[f"prop_depth_{i}"] = self.renderer_depth(weights=weights_list[i], ray_samples=ray_samples_list[i])
         return outputs
 
+    step: int = 0      # training step, set by the trainer's callback (drives the line-of-sight schedules)
+
+    def get_line_of_sight_sigma(self, step: int) -> float:
+        """nerfacto_nusc_ms.py:387-396."""
+        c = self.config
+        frac = float(np.clip((step - c.line_of_sight_start_step) / (c.line_of_sight_end_step - c.line_of_sight_start_step),
+                             0.0, 1.0))
+        return c.line_of_sight_max_sigma - frac * (c.line_of_sight_max_sigma - c.line_of_sight_min_sigma)
+
+    def get_line_of_sight_mult(self, step: int) -> float:
+        """nerfacto_nusc_ms.py:398-403."""
+        c = self.config
+        if step <= c.line_of_sight_start_step:
+            return 0.0
+        return c.line_of_sight_mult / (2.0 ** (step // c.line_of_sight_decay_steps))
+
     def get_loss_dict(self, outputs: Dict[str, object], batch: Dict[str, Tensor]) -> Dict[str, Tensor]:
         """The camera-only terms of nerfacto_nusc_ms.py:558-645 (rgb, sky, semantic, interlevel, distortion), each on its
         kernel: `ps_render_losses` for the three rendered-output terms, `ps_zaa_interlevel_loss` / `ps_interlevel_loss`
@@ -291,6 +320,25 @@ class NerfactoNuscMSModel(nn.Module):
             loss_dict["sky_loss"] = c.sky_loss_mult * terms[1]
         if use_sem:
             loss_dict["semantic_loss"] = c.semantic_loss_mult * terms[2]
+        if (c.use_monodepth_loss or c.use_lidar_loss) and "depth" in batch:
+            # :577-629 — torch expressions for now (the remaining rows of the loss stack)
+            depth = batch["depth"].view(-1, 1)
+            scale = float(batch.get("pose_scale_factor", 1.0))
+            last = outputs["ray_samples_list"][-1]
+            steps = (last.frustums.starts + last.frustums.ends) / 2 / scale
+            predicted = outputs["expected_depth"] / scale
+            sigma, mult = self.get_line_of_sight_sigma(self.step), self.get_line_of_sight_mult(self.step)
+            sky_mask = batch["sky"].view(-1, 1) if c.use_monodepth_loss else None
+            if c.use_monodepth_loss:
+                loss_dict["expected_depth_loss"] = c.expected_depth_loss_mult * losses.expected_monodepth_loss(
+                    depth, predicted, sky_mask, c.monodepth_depth_upperbound, c.monodepth_loss_inverse)
+                ub = c.monodepth_depth_upperbound
+            else:
+                loss_dict["expected_depth_loss"] = c.expected_depth_loss_mult * losses.expected_depth_loss(
+                    depth, predicted, c.lidar_depth_upperbound)
+                ub = c.lidar_depth_upperbound
+            loss_dict["line_of_sight_loss"] = mult * losses.line_of_sight_loss(
+                outputs["weights_list"][-1], depth, steps, sigma, sky_mask, ub)
         if self.training:
             wl = outputs["weights_list"]
             sp = [rs.sp_bins for rs in outputs["ray_samples_list"]]
