@@ -1,49 +1,27 @@
-"""Loss terms that seed the backward pass of the hot path (reference: model_components/losses.py and
-model_components/PreSight/losses.py).  They consume `weights_list` / rendered outputs (the "next" row); only the terms needed to drive
-every gradient path are restated.  On CUDA tensors the interlevel loss runs as one kernel per proposal level
-(`ps_interlevel_loss`); the torch expressions below are the host-side restatement used for CPU tensors (tests,
-the oracle leg of bench.py) and document the arithmetic."""
+"""The loss stack of the hot path (reference: model_components/losses.py and model_components/PreSight/losses.py;
+SURVEY §8(f)-1, the first "next" row): the terms that sit between compositing-forward and compositing-backward of every
+training step.  The proposal losses (z-anti-aliased and plain), the distortion loss and the rgb / sky / semantic terms
+each run as ONE kernel producing the loss and its gradient (`ps_zaa_interlevel_loss`, `ps_interlevel_loss`,
+`ps_distortion_loss`, `ps_render_losses`); they take CUDA tensors only — there is no torch fallback for them (the CPU
+restatements live in `oracle/`).  The depth-supervision terms at the end are the rows not yet written as kernels and are
+plain torch expressions."""
 from __future__ import annotations
 
 from typing import List
 
 import torch
-import torch.nn.functional as F
 from torch import Tensor
-
-EPS = 1.0e-7
-
-
-def outer(t0_starts: Tensor, t0_ends: Tensor, t1_starts: Tensor, t1_ends: Tensor, y1: Tensor) -> Tensor:
-    """Upper envelope of a step function on coarser intervals (losses.py:48-77)."""
-    cy1 = torch.cat([torch.zeros_like(y1[..., :1]), torch.cumsum(y1, dim=-1)], dim=-1)
-    idx_lo = torch.searchsorted(t1_starts.contiguous(), t0_starts.contiguous(), side="right") - 1
-    idx_lo = torch.clamp(idx_lo, min=0, max=y1.shape[-1] - 1)
-    idx_hi = torch.searchsorted(t1_ends.contiguous(), t0_ends.contiguous(), side="right")
-    idx_hi = torch.clamp(idx_hi, min=0, max=y1.shape[-1] - 1)
-    cy1_lo = torch.take_along_dim(cy1[..., :-1], idx_lo, dim=-1)
-    cy1_hi = torch.take_along_dim(cy1[..., 1:], idx_hi, dim=-1)
-    return cy1_hi - cy1_lo
-
-
-def lossfun_outer(t: Tensor, w: Tensor, t_env: Tensor, w_env: Tensor) -> Tensor:
-    """losses.py:80-97."""
-    w_outer = outer(t[..., :-1], t[..., 1:], t_env[..., :-1], t_env[..., 1:], w_env)
-    return torch.clip(w - w_outer, min=0) ** 2 / (w + EPS)
 
 
 def interlevel_loss(weights_list: List[Tensor], sp_bins_list: List[Tensor]) -> Tensor:
-    """Proposal loss of mip-NeRF 360 (losses.py:108-126); sp_bins_list holds the spacing-domain bin edges."""
+    """Proposal loss of mip-NeRF 360 (losses.py:48-126: outer / lossfun_outer / interlevel_loss); sp_bins_list holds the
+    spacing-domain bin edges.  One kernel per proposal level: loss and d loss / d proposal weights (csrc/losses.cu)."""
+    from . import ops
     c = sp_bins_list[-1].detach()
     w = weights_list[-1][..., 0].detach()
     loss = 0.0
     for sdist, weights in zip(sp_bins_list[:-1], weights_list[:-1]):
-        if w.is_cuda:
-            # one kernel per proposal level: loss and d loss / d proposal weights (csrc/losses.cu)
-            from . import ops
-            loss = loss + ops.interlevel_loss_level(c, w, sdist, weights)     # [N,Sp,1]: no slicing node in between
-        else:
-            loss = loss + torch.mean(lossfun_outer(c, w, sdist, weights[..., 0]))
+        loss = loss + ops.interlevel_loss_level(c, w, sdist, weights)     # [N,Sp,1]: no slicing node in between
     return loss
 
 
@@ -61,23 +39,11 @@ def z_anti_aliasing_interlevel_loss(weights_list: List[Tensor], sp_bins_list: Li
     return loss
 
 
-def lossfun_distortion(t: Tensor, w: Tensor) -> Tensor:
-    """losses.py:130-143 (torch restatement; documents the arithmetic of `ps_distortion_loss`)."""
-    ut = (t[..., 1:] + t[..., :-1]) / 2
-    dut = torch.abs(ut[..., :, None] - ut[..., None, :])
-    loss_inter = torch.sum(w * torch.sum(w[..., None, :] * dut, dim=-1), dim=-1)
-    loss_intra = torch.sum(w ** 2 * (t[..., 1:] - t[..., :-1]), dim=-1) / 3
-    return loss_inter + loss_intra
-
-
 def distortion_loss(weights_list: List[Tensor], sp_bins_list: List[Tensor]) -> Tensor:
-    """losses.py:145-149: distortion of the final level's weights along the spacing-domain bins.  CUDA tensors: one
-    kernel producing the loss and d loss / d weights (`ps_distortion_loss`)."""
-    c, w = sp_bins_list[-1].detach(), weights_list[-1]
-    if w.is_cuda:
-        from . import ops
-        return ops.distortion_loss(c, w)
-    return torch.mean(lossfun_distortion(c, w[..., 0]))
+    """losses.py:130-149 (lossfun_distortion / distortion_loss): distortion of the final level's weights along the
+    spacing-domain bins; one kernel producing the loss and d loss / d weights (`ps_distortion_loss`)."""
+    from . import ops
+    return ops.distortion_loss(sp_bins_list[-1].detach(), weights_list[-1])
 
 
 # ---- depth supervision (PreSight/losses.py:25-103).  These three are still plain torch expressions (SURVEY 8f-1 lists
@@ -121,20 +87,6 @@ def line_of_sight_loss(weights: Tensor, termination_depth: Tensor, steps: Tensor
     near = (near_mask * (weights - torch.exp(target.log_prob(steps - td))) ** 2).sum(-2)
     empty = ((steps < td - sigma) * weights ** 2).sum(-2)
     return torch.mean((near + empty)[depth_mask])
-
-
-def sky_loss(accumulation: Tensor, sky_mask: Tensor, eps: float = 1e-7) -> Tensor:
-    """PreSight/losses.py:104-114."""
-    target = 1.0 - sky_mask
-    accumulation = torch.clip(accumulation, min=eps, max=1 - eps)
-    return F.binary_cross_entropy(accumulation, target, reduction="none").mean()
-
-
-def semantic_loss(pred: Tensor, target: Tensor, clip: bool = True) -> Tensor:
-    """PreSight/losses.py:116-124."""
-    if clip:
-        target = torch.clip(target, min=0.0, max=1.0)
-    return F.mse_loss(pred, target, reduction="none").mean()
 
 
 def render_losses(outputs, batch, use_sky: bool = True, use_semantics: bool = True) -> Tensor:

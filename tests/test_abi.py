@@ -56,6 +56,17 @@ def test_no_cpu_fallback():
         ops.hash_encode(torch.zeros(4, 3), torch.zeros(32 * 4, 2), [16.0, 32.0, 64.0, 128.0], 5)
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.get_weights(torch.ones(2, 4), torch.ones(2, 4))
+    # the loss stack is kernels only as well
+    from presight_b200 import losses
+    c, w = torch.linspace(0, 1, 5).repeat(2, 1), torch.full((2, 4, 1), 0.25)
+    cp, wp = torch.linspace(0, 1, 9).repeat(2, 1), torch.full((2, 8, 1), 0.125, requires_grad=True)
+    for fn in (lambda: losses.interlevel_loss([wp, w], [cp, c]),
+               lambda: losses.z_anti_aliasing_interlevel_loss([wp, w], [cp, c], (0.03,)),
+               lambda: losses.distortion_loss([w], [c]),
+               lambda: losses.render_losses({"rgb": torch.zeros(2, 3), "accumulation": torch.zeros(2, 1)},
+                                            {"rgb": torch.zeros(2, 3), "sky": torch.zeros(2, 1)}, True, False)):
+        with pytest.raises(RuntimeError, match="CUDA"):
+            fn()
 
 
 def test_product_does_not_import_oracle():
