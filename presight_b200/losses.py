@@ -7,7 +7,8 @@ restatements live in `oracle/`).  The depth-supervision terms at the end are the
 plain torch expressions."""
 from __future__ import annotations
 
-from typing import List
+import math
+from typing import List, Optional
 
 import torch
 from torch import Tensor
@@ -46,47 +47,49 @@ def distortion_loss(weights_list: List[Tensor], sp_bins_list: List[Tensor]) -> T
     return ops.distortion_loss(sp_bins_list[-1].detach(), weights_list[-1])
 
 
-# ---- depth supervision (PreSight/losses.py:25-103).  These three are still plain torch expressions (SURVEY 8f-1 lists
-# them as the remaining rows of the loss stack); they are reached only when the batch carries a "depth" target.
-URF_SIGMA_SCALE_FACTOR = 3.0
+# ---- depth supervision (PreSight/losses.py:25-103).  Not kernels yet (SURVEY 8f-1 lists them as the remaining rows of the
+# loss stack): per-ray torch expressions, reached only when the batch carries a "depth" target.
+def _supervised_rays(target_m: Tensor, limit_m: float, sky_mask: Optional[Tensor]) -> Tensor:
+    """Rays whose target depth is usable: strictly between 1 m and the upper bound and, if a sky mask is given, not sky."""
+    ok = (target_m > 1.0) & (target_m < limit_m)
+    return ok if sky_mask is None else ok & (sky_mask == 0.0)
 
 
 def normalize_depth(depth: Tensor, upper_bound: float = 75.0) -> Tensor:
-    return torch.clip(depth / upper_bound, 0.0, 1.0)
+    return (depth / upper_bound).clip(0.0, 1.0)
 
 
 def expected_monodepth_loss(termination_depth: Tensor, predicted_depth: Tensor, sky_mask: Tensor,
                             upper_bound: float = 50.0, inverse: bool = False) -> Tensor:
-    """PreSight/losses.py:83-103."""
-    depth_mask = (termination_depth > 1.0) & (termination_depth < upper_bound) & (sky_mask == 0.0)
+    """Mono-depth supervision of the rendered expected depth (:83-103): squared error of the depths mapped to [0, 1]
+    (or to 1 / (d + 5) when `inverse`), averaged over the supervised, non-sky rays."""
+    rays = _supervised_rays(termination_depth, upper_bound, sky_mask)
     if inverse:
-        termination_depth, predicted_depth = 1 / (termination_depth + 5), 1 / (predicted_depth + 5)
+        err = 1 / (termination_depth + 5) - 1 / (predicted_depth + 5)
     else:
-        termination_depth = normalize_depth(termination_depth, upper_bound)
-        predicted_depth = normalize_depth(predicted_depth, upper_bound)
-    return torch.mean(((termination_depth - predicted_depth) ** 2)[depth_mask])
+        err = normalize_depth(termination_depth, upper_bound) - normalize_depth(predicted_depth, upper_bound)
+    return err.square()[rays].mean()
 
 
 def expected_depth_loss(termination_depth: Tensor, predicted_depth: Tensor, upper_bound: float = 75.0) -> Tensor:
-    """PreSight/losses.py:67-81."""
-    depth_mask = (termination_depth > 1.0) & (termination_depth < upper_bound)
-    diff = normalize_depth(termination_depth, upper_bound) - normalize_depth(predicted_depth, upper_bound)
-    return torch.mean((diff ** 2)[depth_mask])
+    """LiDAR supervision of the rendered expected depth (:67-81): as above, without the sky mask."""
+    rays = _supervised_rays(termination_depth, upper_bound, None)
+    err = normalize_depth(termination_depth, upper_bound) - normalize_depth(predicted_depth, upper_bound)
+    return err.square()[rays].mean()
 
 
 def line_of_sight_loss(weights: Tensor, termination_depth: Tensor, steps: Tensor, sigma: float,
-                       sky_mask: Tensor = None, upper_bound: float = 75.0) -> Tensor:
-    """PreSight/losses.py:28-65 (Urban Radiance Fields): weights [N,S,1], termination_depth [N,1], steps [N,S,1]."""
-    depth_mask = (termination_depth > 1.0) & (termination_depth < upper_bound)
-    if sky_mask is not None:
-        depth_mask = depth_mask & (sky_mask == 0.0)
-    steps = steps.detach()
-    td = termination_depth[:, None]
-    target = torch.distributions.normal.Normal(0.0, sigma / URF_SIGMA_SCALE_FACTOR)
-    near_mask = torch.logical_and(steps <= td + sigma, steps >= td - sigma)
-    near = (near_mask * (weights - torch.exp(target.log_prob(steps - td))) ** 2).sum(-2)
-    empty = ((steps < td - sigma) * weights ** 2).sum(-2)
-    return torch.mean((near + empty)[depth_mask])
+                       sky_mask: Optional[Tensor] = None, upper_bound: float = 75.0) -> Tensor:
+    """Line-of-sight loss of Urban Radiance Fields (:28-65).  weights [N,S,1], termination_depth [N,1], steps [N,S,1]
+    (sample mid-points, metres).  Within +-sigma of the target the weights should follow N(0, sigma / 3) evaluated at
+    the signed distance; every sample more than sigma in front of the target should carry no weight."""
+    rays = _supervised_rays(termination_depth, upper_bound, sky_mask)
+    at, target = steps.detach(), termination_depth[:, None]                # [N,S,1], [N,1,1]
+    std = sigma / 3.0
+    gauss = torch.exp(-((at - target) ** 2) / (2 * std ** 2) - math.log(std) - math.log(math.sqrt(2 * math.pi)))
+    band = (at <= target + sigma) & (at >= target - sigma)                 # the reference's comparisons, as written
+    per_ray = (band * (weights - gauss).square()).sum(-2) + ((at < target - sigma) * weights.square()).sum(-2)
+    return per_ray[rays].mean()
 
 
 def render_losses(outputs, batch, use_sky: bool = True, use_semantics: bool = True) -> Tensor:
