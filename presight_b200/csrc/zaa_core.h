@@ -28,9 +28,11 @@ constexpr int kMaxKnots = 2 * kMaxS + 2;
 // Returns the ray's sum of loss terms; grad_wp [Sp] (nullable) receives d(sum)/d wp.
 PS_HD inline float ray_loss(const float* c, const float* w, int S, const float* cp, const float* wp, int Sp, double r,
                             float* grad_wp) {
-    float xr[kMaxKnots], yr[kMaxKnots], cdf[kMaxKnots];
+    float xr[kMaxKnots], yr[kMaxKnots], cdf[kMaxKnots], wn[kMaxS];
     const float rf = (float)r, two_r = (float)(2.0 * r);
     const int K = 2 * S + 2;
+    for (int k = 0; k < S; ++k) wn[k] = w[k] / (c[k + 1] - c[k]);        // each bin's density once (every edge is visited
+                                                                          // twice, and needs the bins on both sides)
     // ---- blur_stepfun: merge the two sorted edge lists (c - r first on ties), run the two nested cumsums ------------
     int ia = 0, ib = 0;
     double s1 = 0.0, s2 = 0.0;
@@ -41,8 +43,8 @@ PS_HD inline float ray_loss(const float* c, const float* w, int S, const float* 
         const bool take_a = ia <= S && (ib > S || a <= b);
         const int e = take_a ? ia : ib;                                   // edge index of this knot
         const float x = take_a ? a : b;
-        const float hi = e < S ? w[e] / (c[e + 1] - c[e]) : 0.f;          // wn_pad[e]
-        const float lo = e > 0 ? w[e - 1] / (c[e] - c[e - 1]) : 0.f;      // wn_pad[e - 1]
+        const float hi = e < S ? wn[e] : 0.f;                             // wn_pad[e]
+        const float lo = e > 0 ? wn[e - 1] : 0.f;                         // wn_pad[e - 1]
         const float y1 = (hi - lo) / two_r;
         if (take_a) ++ia; else ++ib;
         xr[k] = x;
