@@ -9,6 +9,7 @@ Every function cites the reference lines it restates.  Shorthand for paths:
   RS   = model_components/ray_samplers.py     RN   = model_components/renderers.py
   RAYS = cameras/rays.py                      MATH = utils/math.py
   MODEL= models/PreSight/nerfacto_nusc_ms.py  XP   = scripts/extract_priors.py
+  LS   = model_components/losses.py           PL   = model_components/PreSight/losses.py
 
 The code is written functionally over plain tensors (no nn.Module tree) so that the
 same functions serve as (a) checker for the CUDA kernels, (b) generator-independent
