@@ -47,3 +47,12 @@ def test_zaa_core_matches_reference(host_lib, case):
         total += loss_i
         assert_close(grad_i, fx[f"{case}/g{i}"], 2e-5, f"grad level {i}")
     assert abs(total - float(fx[f"{case}/loss"])) <= 1e-5 * abs(float(fx[f"{case}/loss"])), (total, float(fx[f"{case}/loss"]))
+
+
+def test_parallel_formulation_matches_reference():
+    """The loop-free formulation planned for the warp-per-ray kernel (tools/zaa_parallel_prototype.py: merge by rank,
+    scans, binary-search interval and flat-run lookup) reproduces the live reference's fixture."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tools"))
+    import zaa_parallel_prototype as proto
+    assert proto.check(os.path.join(HERE, "golden", "zaa.npz")) < 2e-5
