@@ -7,6 +7,8 @@
 //   loss_i    = max(w_i - w_outer_i, 0)^2 / (w_i + 1e-7)
 // d loss_i / d w_env[k] = g_i * ([k <= idx_hi_i] - [k < idx_lo_i]),  g_i = -2 max(w_i - w_outer_i, 0) / (w_i + 1e-7),
 // accumulated through two per-ray histograms (A over idx_hi, B over idx_lo) and suffix sums.
+#include <cstdlib>
+
 #include "sampler.cuh"
 #define PS_HD __host__ __device__
 #include "zaa_core.h"
@@ -127,6 +129,131 @@ __global__ void __launch_bounds__(128) zaa_interlevel_kernel(const float* __rest
     if ((threadIdx.x & 31) == 0 && l != 0.f) atomicAdd(loss_sum, l);
 }
 
+// EXPERIMENTAL (opt-in with PS_ZAA_WARP=1; written after the round's GPU budget was spent, so NOT yet run on a GPU):
+// the same loss with one WARP per ray, following the loop-free formulation that tools/zaa_parallel_prototype.py checks
+// against the reference's fixture — merge by rank (two binary searches per knot; "c - r first on ties"), fp64-carried
+// warp scans over the knots in chunks of 32, interval lookup and flat-run lookup by binary search per query.
+// Shared memory per warp (floats): c[S+1] | wn[S+1] | xr[K] | y2[K] | yr[K] | cdf[K] | ret[Sp+1],  K = 2S + 2.
+constexpr int kZaaWarps = 4;
+
+__device__ __forceinline__ int zaa_count_le(const float* a, int n, float v) {   // #{i : a[i] <= v}, a sorted
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] <= v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ int zaa_count_lt(const float* a, int n, float v) {   // #{i : a[i] < v}, a sorted
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kZaaWarps * 32) zaa_interlevel_warp_kernel(
+    const float* __restrict__ c, const float* __restrict__ w, int64_t N, int S, const float* __restrict__ cp,
+    const float* __restrict__ wp, int Sp, double r, float* __restrict__ loss_sum, float* __restrict__ grad_wp) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * kZaaWarps + warp;
+    if (n >= N) return;                                      // warp-uniform; only __syncwarp below
+    const int K = 2 * S + 2;
+    float* cs = smem + (size_t)warp * (2 * (S + 1) + 4 * K + (Sp + 1));
+    float* wn = cs + (S + 1);
+    float* xr = wn + (S + 1);
+    float* y2 = xr + K;
+    float* yr = y2 + K;
+    float* cdf = yr + K;
+    float* ret = cdf + K;
+    const float rf = (float)r, two_r = (float)(2.0 * r);
+    for (int k = lane; k <= S; k += 32) cs[k] = __ldg(c + n * (S + 1) + k);
+    __syncwarp();
+    for (int k = lane; k <= S; k += 32) wn[k] = k < S ? __fdiv_rn(__ldg(w + n * S + k), __fsub_rn(cs[k + 1], cs[k])) : 0.f;
+    __syncwarp();
+    // ---- merge by rank ----------------------------------------------------------------------------------------------
+    for (int e = lane; e <= S; e += 32) {
+        const float a = __fsub_rn(cs[e], rf), b = __fadd_rn(cs[e], rf);
+        int lo = 0, hi = S + 1;                              // #{k : c[k] + r < a}
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__fadd_rn(cs[mid], rf) < a) lo = mid + 1; else hi = mid;
+        }
+        const int pos_a = e + lo;
+        lo = 0; hi = S + 1;                                  // #{k : c[k] - r <= b}
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__fsub_rn(cs[mid], rf) <= b) lo = mid + 1; else hi = mid;
+        }
+        const int pos_b = e + lo;
+        const float y1 = __fdiv_rn(__fsub_rn(wn[e], e > 0 ? wn[e - 1] : 0.f), two_r);     // wn[S] = 0 is the right pad
+        xr[pos_a] = a; y2[pos_a] = y1;
+        xr[pos_b] = b; y2[pos_b] = -y1;
+    }
+    __syncwarp();
+    // ---- the two nested running sums (fp64 carry, fp32 outputs), then the running integral -------------------------------
+    double carry1 = 0.0, carry2 = 0.0;
+    if (lane == 0) { yr[0] = 0.f; cdf[0] = 0.f; }
+    for (int base = 0; base < K - 1; base += 32) {
+        const int k = base + lane;
+        const bool on = k < K - 1;
+        const double in1 = warp_scan_incl(on ? (double)y2[k] : 0.0, lane) + carry1;
+        const float prod = on ? __fmul_rn(__fsub_rn(xr[k + 1], xr[k]), (float)in1) : 0.f;
+        const double in2 = warp_scan_incl((double)prod, lane) + carry2;
+        if (on) yr[k + 1] = fmaxf((float)in2, 0.f);
+        carry1 = __shfl_sync(0xffffffffu, in1, 31);
+        carry2 = __shfl_sync(0xffffffffu, in2, 31);
+    }
+    __syncwarp();
+    double carry3 = 0.0;
+    for (int base = 0; base < K - 1; base += 32) {
+        const int k = base + lane;
+        const bool on = k < K - 1;
+        const float area = on ? __fmul_rn(__fmul_rn(0.5f, __fadd_rn(yr[k + 1], yr[k])), __fsub_rn(xr[k + 1], xr[k])) : 0.f;
+        const double in3 = warp_scan_incl((double)area, lane) + carry3;
+        if (on) cdf[k + 1] = (float)in3;
+        carry3 = __shfl_sync(0xffffffffu, in3, 31);
+    }
+    __syncwarp();
+    // ---- sorted_interp_quad at the proposal bin edges -------------------------------------------------------------------
+    const float cdf_last = cdf[K - 1], yr_first = yr[0];
+    for (int m = lane; m <= Sp; m += 32) {
+        const float x = __ldg(cp + n * (Sp + 1) + m);
+        const int j = zaa_count_le(xr, K, x) - 1;            // last knot <= x
+        float v = 0.f;
+        if (j >= 0) {
+            const float x0 = xr[j], c0 = cdf[j];
+            const float f0 = yr[zaa_count_lt(cdf, K, c0)];   // first knot of the flat run of the integral (argmax on ties)
+            float f1, o;
+            if (j + 1 < K) {
+                f1 = cdf_last == cdf[j + 1] ? yr_first : yr[j + 1];
+                o = __fdiv_rn(__fsub_rn(x, x0), __fsub_rn(xr[j + 1], x0));
+                o = o != o ? 0.f : fminf(fmaxf(o, 0.f), 1.f);
+            } else {
+                f1 = yr_first;
+                o = x > x0 ? 1.f : 0.f;
+            }
+            const float inner = __fadd_rn(__fadd_rn(f0, __fmul_rn(f1, o)), __fmul_rn(f0, __fsub_rn(1.f, o)));
+            v = __fadd_rn(c0, __fdiv_rn(__fmul_rn(__fsub_rn(x, x0), inner), 2.f));
+        }
+        ret[m] = v;
+    }
+    __syncwarp();
+    float loss = 0.f;
+    for (int m = lane; m < Sp; m += 32) {
+        const float q = __ldg(wp + n * Sp + m);
+        const float d = __fsub_rn(__fsub_rn(ret[m + 1], ret[m]), q);
+        const float rr = d > 0.f ? d : 0.f;
+        const float den = q + 1e-5f;
+        loss += rr * rr / den;
+        if (grad_wp) grad_wp[n * Sp + m] = -2.f * rr / den - rr * rr / (den * den);
+    }
+    loss = warp_sum(loss);
+    if (lane == 0 && loss != 0.f) atomicAdd(loss_sum, loss);
+}
+
 }  // namespace ps
 
 using namespace ps;
@@ -140,6 +267,19 @@ extern "C" int ps_zaa_interlevel_loss(const float* c, const float* w, int64_t N,
                zaa::kMaxS);
     PS_REQUIRE(Sp >= 1, "zaa_interlevel_loss: proposal samples per ray %d < 1", Sp);
     PS_REQUIRE(pulse_width > 0.0, "zaa_interlevel_loss: pulse width must be positive");
+    static const bool warp_per_ray = getenv("PS_ZAA_WARP") != nullptr && atoi(getenv("PS_ZAA_WARP")) != 0;
+    if (warp_per_ray) {                                      // experimental, see zaa_interlevel_warp_kernel
+        const size_t smem = (size_t)kZaaWarps * (2 * (S + 1) + 4 * (2 * S + 2) + (Sp + 1)) * sizeof(float);
+        PS_REQUIRE(smem <= 200 * 1024, "zaa_interlevel_loss: %zu bytes of shared memory", smem);
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(zaa_interlevel_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            configured = true;
+        }
+        zaa_interlevel_warp_kernel<<<(unsigned)cdiv(N, kZaaWarps), kZaaWarps * 32, smem, (cudaStream_t)stream>>>(
+            c, w, N, S, t_env, w_env, Sp, pulse_width, loss_sum, grad_w_env);
+        return check_launch("zaa_interlevel_loss(warp)");
+    }
     zaa_interlevel_kernel<<<(unsigned)cdiv(N, 128), 128, 0, (cudaStream_t)stream>>>(c, w, N, S, t_env, w_env, Sp,
                                                                                   pulse_width, loss_sum, grad_w_env);
     return check_launch("zaa_interlevel_loss");
