@@ -37,7 +37,7 @@ __all__ = [
     "loss_outer", "lossfun_outer", "interlevel_loss", "sky_blend", "rgb_loss", "sky_loss", "semantic_loss",
     "lossfun_distortion", "distortion_loss", "blur_stepfun", "sorted_interp_quad", "z_anti_aliasing_interlevel_loss",
     "normalize_depth", "expected_monodepth_loss", "expected_depth_loss", "line_of_sight_loss", "line_of_sight_sigma",
-    "line_of_sight_mult",
+    "line_of_sight_mult", "pinhole_rays",
 ]
 
 PRIME_Y = 2654435761  # ENC:336
@@ -649,6 +649,36 @@ def semantic_loss(pred: Tensor, target: Tensor, clip: bool = True) -> Tensor:
     if clip:
         target = torch.clip(target, min=0.0, max=1.0)
     return torch.mean((pred - target) ** 2)
+
+
+# --------------------------------------------------------------------------------------
+# 8f-3  ray generation (the caller on the input side of the path)
+# --------------------------------------------------------------------------------------
+def pinhole_rays(c2w: Tensor, fx: Tensor, fy: Tensor, cx: Tensor, cy: Tensor, ray_indices: Tensor,
+                 pixel_offset: float = 0.5) -> Dict[str, Tensor]:
+    """Perspective ray generation without lens distortion: RayGenerator.forward (model_components/ray_generators.py:43-61)
+    -> Cameras._generate_rays_from_coords (cameras/cameras.py:497-880, PERSPECTIVE branch :773-779).
+
+    c2w [C,3,4], fx/fy/cx/cy [C], ray_indices [N,3] = (camera, row, col) -> origins [N,3], unit directions [N,3],
+    pixel_area [N,1] (product of the distances to the directions of the +1-column and +1-row pixels), directions_norm."""
+    cam, row, col = ray_indices[:, 0], ray_indices[:, 1], ray_indices[:, 2]
+    y, x = row.float() + pixel_offset, col.float() + pixel_offset            # image_coords[y, x] (:311-312), (y, x) order
+    fxr, fyr, cxr, cyr = fx[cam], fy[cam], cx[cam], cy[cam]
+    coord = torch.stack([(x - cxr) / fxr, -(y - cyr) / fyr], -1)            # :613-615
+    coord_x = torch.stack([(x - cxr + 1) / fxr, -(y - cyr) / fyr], -1)
+    coord_y = torch.stack([(x - cxr) / fxr, -(y - cyr + 1) / fyr], -1)
+    stack = torch.stack([coord, coord_x, coord_y], dim=0)                    # [3,N,2]
+    dirs = torch.cat([stack, -torch.ones_like(stack[..., :1])], dim=-1)      # camera looks down -z (:777-779)
+    rot = c2w[cam][:, :3, :3]
+    dirs = torch.sum(dirs[..., None, :] * rot, dim=-1)                       # :844-846
+    eps = torch.tensor([float(np.finfo(float).eps * 4.0)])                                              # camera_utils.py:30
+    norm = torch.maximum(torch.linalg.vector_norm(dirs, dim=-1, keepdim=True), eps.to(dirs))            # camera_utils.py:299
+    dirs = dirs / norm
+    d = dirs[0]
+    dx = torch.sqrt(torch.sum((d - dirs[1]) ** 2, dim=-1))                   # :854-855
+    dy = torch.sqrt(torch.sum((d - dirs[2]) ** 2, dim=-1))
+    return {"origins": c2w[cam][:, :3, 3], "directions": d, "pixel_area": (dx * dy)[..., None],
+            "directions_norm": norm[0]}
 
 
 # --------------------------------------------------------------------------------------
