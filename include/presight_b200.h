@@ -245,6 +245,15 @@ int ps_render_losses(const float* rgb, const float* gt_rgb, const float* acc, co
                      const float* gt_sem, int64_t N, int C, float eps, float* losses, float* g_rgb, float* g_acc,
                      float* g_sem, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Ray generation: RayGenerator.forward + Cameras.generate_rays for PERSPECTIVE cameras without distortion
+ * (model_components/ray_generators.py:43-61, cameras/cameras.py:497-880).
+ *   c2w [C,3,4], fx / fy / cx / cy [C] fp32; ray_indices [N,3] int64 = (camera, row, col); pixel_offset = 0.5
+ *   -> origins [N,3], directions [N,3] (unit), pixel_area [N], directions_norm [N] (nullable). */
+int ps_generate_rays(const float* c2w, const float* fx, const float* fy, const float* cx, const float* cy, int C,
+                     const int64_t* ray_indices, int64_t N, float pixel_offset, float* origins, float* directions,
+                     float* pixel_area, float* directions_norm, void* stream);
+
 /* Self-test of the tcgen05 operand conventions used by the fused kernels (csrc/tc5.cuh): one CTA computes, from
  * X [128,64], Y [128,64], W [64,64] (fp32, rounded to bf16 on chip), C1 = X W^T (K-major operands), C2 = X W
  * (MN-major B: the input-gradient form) and C3 = 2 X^T Y (MN-major A and B, reduction over rows, accumulated over two

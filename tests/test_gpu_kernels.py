@@ -544,6 +544,23 @@ def test_sky_blend_and_render_losses_variants(ops):
     assert float(t[1]) == 0.0 and float(t[2]) == 0.0 and float(t[0]) > 0.0
 
 
+def test_generate_rays_golden(ops):
+    """ps_generate_rays (pinhole RayGenerator) vs the live reference's Cameras.generate_rays on nuScenes-shaped
+    cameras: origins exact, unit directions and norms 1e-6, pixel area 1e-3 per ray (a product of differences of nearly
+    equal unit vectors; fp32 class)."""
+    from presight_b200.cameras.ray_generator import RayGenerator
+    fx = Fixture("rays.npz")
+    gen = RayGenerator(fx["c2w"], fx["fx"], fx["fy"], fx["cx"], fx["cy"]).to(DEV)
+    rb = gen(fx["ray_indices"].to(DEV))
+    assert torch.equal(rb.origins.cpu(), fx["origins"])
+    assert_close(rb.directions.cpu(), fx["directions"], 1e-6, "directions")
+    assert_close(rb.metadata["directions_norm"].cpu(), fx["directions_norm"], 1e-6, "directions_norm")
+    rel = ((rb.pixel_area.cpu() - fx["pixel_area"]).abs() / fx["pixel_area"]).max()
+    assert float(rel) < 1e-3, float(rel)
+    assert torch.equal(rb.camera_indices.cpu(), fx["ray_indices"][:, :1])
+    assert len(gen(torch.zeros(0, 3, dtype=torch.int64, device=DEV))) == 0
+
+
 def test_tcgen05_operand_conventions(ops):
     """K-major / MN-major UMMA descriptors over one chunk-major tile (csrc/tc5.cuh): forward, input-gradient and
     weight-gradient GEMM forms against fp32 matmuls of the bf16-rounded operands."""
