@@ -254,6 +254,15 @@ int ps_generate_rays(const float* c2w, const float* fx, const float* fy, const f
                      const int64_t* ray_indices, int64_t N, float pixel_offset, float* origins, float* directions,
                      float* pixel_area, float* directions_norm, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Fused Adam step: torch.optim.Adam without amsgrad as PreSight configures it
+ * (configs/method_configs.py:115: lr 1e-2, eps 1e-15, weight_decay 1e-5; engine/optimizers.py:133-140), one pass.
+ *   param / exp_avg / exp_avg_sq [n] fp32 updated in place, grad [n] read; step = 1 for the first update;
+ *   all four buffers 16-byte aligned; hyper-parameters as doubles (torch keeps them as Python floats and derives the
+ *   bias corrections in double precision). */
+int ps_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                 double beta2, double eps, double weight_decay, int64_t step, void* stream);
+
 /* Self-test of the tcgen05 operand conventions used by the fused kernels (csrc/tc5.cuh): one CTA computes, from
  * X [128,64], Y [128,64], W [64,64] (fp32, rounded to bf16 on chip), C1 = X W^T (K-major operands), C2 = X W
  * (MN-major B: the input-gradient form) and C3 = 2 X^T Y (MN-major A and B, reduction over rows, accumulated over two

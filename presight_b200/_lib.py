@@ -59,6 +59,7 @@ SIGNATURES = {
     "ps_sky_blend_bwd": [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p],
     "ps_render_losses": [_p, _p, _p, _p, _p, _p, _i64, _i, _f, _p, _p, _p, _p, _p],
     "ps_generate_rays": [_p, _p, _p, _p, _p, _i, _p, _i64, _f, _p, _p, _p, _p, _p],
+    "ps_adam_step": [_p, _p, _p, _p, _i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _i64, _p],
     "ps_tc5_probe": [_p, _p, _p, _p, _p, _p, _p, _p],
     "ps_field_level_fwd": [_p, _p, _i, _i, _p, _p, _p, _p, _i64, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p],
     "ps_field_level_bwd": [_p, _p, _i, _i, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
