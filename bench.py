@@ -203,6 +203,9 @@ def main() -> None:
     ap.add_argument("--strong", action="store_true", help="fixed global batch split across ranks (reference semantics)")
     ap.add_argument("--cpu-sample-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--optimizer", default="none", choices=["none", "torch", "fused"],
+                    help="also take an Adam step inside the timed step (SURVEY 8f-2; the headline metric excludes it): "
+                         "torch.optim.Adam or presight_b200.optim.FusedAdam with PreSight's hyper-parameters")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -254,6 +257,12 @@ def main() -> None:
     model.train()
     params = [p for p in model.parameters() if p.requires_grad]
     sync = GradSynchronizer(params, overlap=True) if world > 1 else None
+    optimizer = None
+    if args.optimizer == "torch":
+        optimizer = torch.optim.Adam(params, lr=1e-2, eps=1e-15, weight_decay=1e-5)
+    elif args.optimizer == "fused":
+        from presight_b200.optim import FusedAdam
+        optimizer = FusedAdam(params, lr=1e-2, eps=1e-15, weight_decay=1e-5)
 
     tensor_keys = ("origins", "directions", "camera_indices", "video_ids", "rgb", "features", "sky")
     pinned = {k: host[k].pin_memory() for k in tensor_keys}
@@ -271,6 +280,8 @@ def main() -> None:
         loss.backward()
         if sync is not None:
             sync.finish()
+        if optimizer is not None:
+            optimizer.step()
         return loss
 
     def barrier():
@@ -402,7 +413,9 @@ def main() -> None:
             "dtype": "f32 (hash/compositing) + " + ("tf32x3 MLP" if args.fp32 else "bf16 MLP, fp32 accumulate"),
             "data": "synthetic",
             "config": {"workload": workload_name(args.config), "rays_per_gpu": rays_per_rank, "global_rays": total_rays,
-                       "parallelism": f"dp{world}", "step": "update step (proposal nets trained), optimizer excluded",
+                       "parallelism": f"dp{world}",
+                       "step": "update step (proposal nets trained), " + ("optimizer excluded" if optimizer is None
+                                                                          else f"Adam step included ({args.optimizer})"),
                        "l2": "inputs larger than L2 (576 MiB of hash tables + grads re-zeroed every step)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": t_e2e / args.steps * 1e3},
