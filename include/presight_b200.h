@@ -246,6 +246,25 @@ int ps_render_losses(const float* rgb, const float* gt_rgb, const float* acc, co
                      float* g_sem, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Loss stack, depth supervision: expected-depth loss + line-of-sight loss, loss sums and gradients in one
+ * kernel.  Replaces model_components/PreSight/losses.py:24-103 (normalize_depth, line_of_sight_loss,
+ * expected_depth_loss, expected_monodepth_loss) as called from models/PreSight/nerfacto_nusc_ms.py:577-629.
+ *   weights [N,S] final-level weights (nullable: no line-of-sight term); sample mid-points in metres either given as
+ *   steps_m [N,S] or derived as (eu_bins[s] + eu_bins[s+1]) / 2 / pose_scale from eu_bins [N,S+1] (exactly one of the
+ *   two); expected_depth [N] rendered expected depth in scene units (nullable: no expected-depth term), divided by
+ *   pose_scale inside; target_depth_m [N] metres; sky_mask [N] (1 = sky; nullable = the LiDAR variants);
+ *   pose_scale_dev (nullable): one device float that overrides pose_scale — the reference keeps the factor as a tensor
+ *   element (ray_samples.metadata["pose_scale_factor"][0,0,0]); reading it on the device avoids a host sync per step;
+ *   mode 0 = depths mapped by clip(d / upper_bound, 0, 1), 1 = by 1 / (d + 5) (monodepth_loss_inverse).
+ *   sums[3] += {#rays with 1 < target < upper_bound [and sky == 0], sum of squared errors, sum of line-of-sight terms}
+ *   over those rays (caller-zeroed); g_expected [N] = d sums[1] / d expected_depth, g_weights [N,S] = d sums[2] / d weights
+ *   (written, nullable).  The reference's means are sums[1] / sums[0] and sums[2] / sums[0]. */
+int ps_depth_losses(const float* weights, const float* eu_bins, const float* steps_m, const float* expected_depth,
+                    const float* target_depth_m, const float* sky_mask, int64_t N, int S, float pose_scale,
+                    const float* pose_scale_dev, float sigma, float upper_bound, int mode, float* sums, float* g_expected,
+                    float* g_weights, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Ray generation: RayGenerator.forward + Cameras.generate_rays for PERSPECTIVE cameras without distortion
  * (model_components/ray_generators.py:43-61, cameras/cameras.py:497-880).
  *   c2w [C,3,4], fx / fy / cx / cy [C] fp32; ray_indices [N,3] int64 = (camera, row, col); pixel_offset = 0.5

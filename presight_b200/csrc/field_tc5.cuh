@@ -87,7 +87,8 @@ struct WLayout {
     static constexpr uint32_t r2 = r1 + cm_bytes(kHid, kHid);
     static constexpr uint32_t bt0 = r2 + cm_bytes(kRgbOut, kHid);            // bias tiles, layer order B0..R2
     static constexpr uint32_t ones = bt0 + 480 * 32;                          // 256 B
-    static constexpr uint32_t end = ones + 256;
+    static constexpr uint32_t onehot = ones + 256;                            // kLayers x 256 B (backward: bias gradients)
+    static constexpr uint32_t end = onehot + kLayers * 256;
     __host__ __device__ static constexpr int rows(int l) {
         return l == B1 ? kBaseOut : (l == R2 ? kRgbOut : kHid);
     }
@@ -97,6 +98,22 @@ struct WLayout {
         return off;
     }
 };
+
+// Bias gradients on the tensor core (backward): dB_l = dZ_l^T 1 is one more reduction over the tile's 128 points, against
+// a constant B operand [K = 128 points x N = 16] that is 1 in column kBiasCol0 + l and 0 elsewhere — stored once as a
+// 128-byte core-matrix block pair (8 K-rows x 16 columns) that every 8-row group of the reduction re-reads (the
+// descriptor's K stride is 0).  All layers accumulate into ONE 16-column accumulator, column kBiasCol0 + l = layer l
+// (rows = out features); the colour head's last layer (3 real outputs) keeps its bias gradient in warp sums.
+constexpr int kBiasCol0 = 3;
+static_assert(kBiasCol0 + kLayers - 1 <= 16, "one-hot columns");
+
+// D[dz column][kBiasCol0 + l] += sum over the 128 points of dZ[p][column]   (dz_addr: first column chunk of the dZ tile)
+__device__ __forceinline__ void gemm_bias_grad(uint32_t tmem_d, uint32_t dz_addr, uint32_t onehot_addr) {
+    const uint32_t idesc = make_idesc(16, 1, 1);
+#pragma unroll
+    for (int kk = 0; kk < kRows / 16; ++kk)
+        umma_bf16(tmem_d, make_desc(dz_addr + kk * 256, 128, kRows * 16), make_desc(onehot_addr, 0, 128), idesc, 1u);
+}
 
 // D[128 x N] = 1 * bias^T : the first K step of every forward GEMM (accumulate = false)
 __device__ __forceinline__ void gemm_bias(uint32_t tmem_d, uint32_t ones_addr, uint32_t bias_tile, int b_rows, int N) {
@@ -141,6 +158,12 @@ __device__ __forceinline__ void load_all_weights(const FieldNet& net, unsigned c
     // constant blocks: element e of a 128-byte block = row e / 8, column e % 8
     for (int i = tid; i < 128; i += nthreads) {
         reinterpret_cast<__nv_bfloat16*>(wbase + WL::ones)[i] = __float2bfloat16_rn((i < 64 && (i & 7) < 2) ? 1.f : 0.f);
+    }
+    // one-hot blocks of the bias-gradient GEMMs: layer l has ones in column kBiasCol0 + l of its [8 x 16] block pair
+    for (int i = tid; i < kLayers * 128; i += nthreads) {
+        const int l = i >> 7, e = i & 127;
+        const int col = (e >> 6) * 8 + (e & 7);
+        reinterpret_cast<__nv_bfloat16*>(wbase + WL::onehot)[i] = __float2bfloat16_rn(col == kBiasCol0 + l ? 1.f : 0.f);
     }
 }
 

@@ -15,8 +15,12 @@
 // tc5.cuh and serve all three forms without a transpose.  The weight-gradient GEMM of a layer is issued behind its
 // input-gradient GEMM and is not waited for: it overlaps the next epilogue; the two gradient tiles alternate so a
 // tile is rewritten only after the GEMMs reading it have completed (in-order tensor pipe).
-// Biases: the forward adds them as one more K step against a constant operand; their gradients dB_l = dZ_l^T 1 are warp
-// column sums of the dZ values the epilogues already hold in registers, computed while the next GEMM group runs.
+// Biases: the forward adds them as one more K step against a constant operand; their gradients dB_l = dZ_l^T 1 are one
+// more reduction over the points on the tensor core, against a one-hot constant operand (field_tc5.cuh:gemm_bias_grad),
+// all layers into the 16-column accumulator that also holds the colour head's last weight gradient.  (Round 1 summed
+// them in registers with a transposing shuffle butterfly per epilogue because each tcgen05.mma then cost ~100 issue
+// cycles; with the elected-lane issue an MMA is a handful of instructions and the butterflies — 30 % of the kernel's
+// executed instructions, profiles/r1_z — are gone.)
 #include "field_tc5.cuh"
 
 namespace ps {
@@ -91,48 +95,15 @@ __device__ __forceinline__ float column_sums32(const float (&v)[32], int lane) {
     return t[0];
 }
 
-// same for 16 columns: lanes l and l + 16 both receive the total of column l (l < 16)
-__device__ __forceinline__ float column_sums16(const float (&v)[16], int lane) {
-    float t[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) t[i] = v[i];
-#pragma unroll
-    for (int step = 0, half = 8; step < 4; ++step, half >>= 1) {
-        const int bit = 8 >> step;
-        const bool upper = (lane & bit) != 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (j < half) {
-                const float keep = upper ? t[j + half] : t[j];
-                const float send = upper ? t[j] : t[j + half];
-                t[j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
-            }
-        }
-    }
-    return t[0] + __shfl_xor_sync(0xffffffffu, t[0], 16);
-}
 // input-gradient epilogue of a hidden layer: 32 accumulator columns, gated by the sign of the layer's forward
 // activation (read back from its tile) -> bf16 dZ
-// (dz[] returns the stored values — the bf16-rounded dZ the weight-gradient GEMM will read — for the bias gradient)
 __device__ __forceinline__ void dgrad_epilogue32(uint32_t trow, int c0, const unsigned char* act_tile, unsigned char* dz_tile,
-                                                 int r, float (&dz)[32]) {
+                                                 int r) {
     float v[32];
     tmem_ld32_nowait(trow + c0, v);
     tmem_wait_ld();
 #pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-        const uint4 a = *reinterpret_cast<const uint4*>(act_tile + cm_off(kRows, r, c0 + i));
-        uint4 q;
-        q.x = relu_grad_pack_bf16x2(v[i + 0], v[i + 1], a.x);
-        q.y = relu_grad_pack_bf16x2(v[i + 2], v[i + 3], a.y);
-        q.z = relu_grad_pack_bf16x2(v[i + 4], v[i + 5], a.z);
-        q.w = relu_grad_pack_bf16x2(v[i + 6], v[i + 7], a.w);
-        *reinterpret_cast<uint4*>(dz_tile + cm_off(kRows, r, c0 + i)) = q;
-        dz[i + 0] = __uint_as_float(q.x << 16); dz[i + 1] = __uint_as_float(q.x & 0xffff0000u);
-        dz[i + 2] = __uint_as_float(q.y << 16); dz[i + 3] = __uint_as_float(q.y & 0xffff0000u);
-        dz[i + 4] = __uint_as_float(q.z << 16); dz[i + 5] = __uint_as_float(q.z & 0xffff0000u);
-        dz[i + 6] = __uint_as_float(q.w << 16); dz[i + 7] = __uint_as_float(q.w & 0xffff0000u);
-    }
+    for (int i = 0; i < 32; i += 8) store_chunk_relu_grad(dz_tile, act_tile, kRows, r, c0 + i, v + i);
 }
 
 template <int K0>
@@ -177,11 +148,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
     const uint32_t tmem = *tmem_slot;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     const uint32_t bar = smem_u32(bar_ptr), barB0 = smem_u32(bar_ptr + 1), barB1 = smem_u32(bar_ptr + 2);
-    const uint32_t wb = smem_u32(wbase), ones = wb + WL::ones;
+    const uint32_t wb = smem_u32(wbase), ones = wb + WL::ones, onehot = wb + WL::onehot;
     const uint32_t aDZa = smem_u32(DZa), aDZb = smem_u32(DZb), aA1 = smem_u32(A1), aA2 = smem_u32(A2),
                    aX0 = smem_u32(X0), aH1 = smem_u32(H1), aH = smem_u32(Ht), aSH = smem_u32(SHAPPt);
     constexpr uint32_t CH = kRows * 16;     // bytes per 8-column chunk of a 128-row tile
     uint32_t phase = 0, phaseB0 = 0, phaseB1 = 0;
+    // warp index of the CTA as a provably warp-uniform value: the MMA-issuing branches below are taken by whole warps
+    // and one elected lane issues (see tc5::elect_one)
+    const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
     const int S = a.S;
     const int rpt = kRows / S, rows_used = rpt * S, wpr = S / 32;
@@ -189,22 +163,20 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
     const int64_t ntiles = (a.N + rpt - 1) / rpt;
     const int A = a.net.app_dim;
     bool first = true;
-    // Bias gradients dB_l = dZ_l^T 1: every epilogue that produces a dZ tile keeps its 32 values in registers and, once
-    // the next GEMM group has been issued (i.e. under the tensor pipe's shadow), sums them over the warp's 32 rows with a
-    // transposing butterfly (lane l receives column l).  One register per layer and 32-column block accumulates over
-    // the CTA's tiles; flushed with one atomic per lane at the end.  (On the tensor core each of these sums costs a full
-    // 8-instruction K loop — tcgen05.mma takes ~112 cycles per instruction whatever N is, tools/mma_cost.py — which
-    // made them a third of the kernel's tensor-pipe time.)
-    float db_r2 = 0.f, db_r1 = 0.f, db_r0 = 0.f, db_s2 = 0.f, db_s1 = 0.f, db_s0 = 0.f, db_b1 = 0.f, db_b1lo = 0.f,
-          db_b0 = 0.f;
+    // Bias gradients dB_l = dZ_l^T 1 ride on the tensor core behind each layer's weight-gradient GEMM (gemm_bias_grad) and
+    // share the 16-column accumulator TM::r2; only the colour head's output layer (3 columns) is summed in registers.
+    float db_r2 = 0.f;
 
 #define FB_SYNC_ISSUE(...)     \
     fence_async_smem();        \
     fence_before();            \
     __syncthreads();           \
-    if (tid == 0) {            \
-        fence_after();         \
-        __VA_ARGS__;           \
+    if (warp_u == 0) {         \
+        if (elect_one()) {     \
+            fence_after();     \
+            __VA_ARGS__;       \
+        }                      \
+        __syncwarp();          \
     }
 #define FB_WAIT()           \
     mbar_wait(bar, phase);  \
@@ -219,14 +191,20 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
     fence_async_smem();                    \
     fence_before();                        \
     __syncthreads();                       \
-    if (tid == 0) {                        \
-        fence_after();                     \
-        A_LIST;                            \
-        umma_commit(bar);                  \
-    } else if (tid == 128) {               \
-        fence_after();                     \
-        B_LIST;                            \
-        umma_commit(KB ? barB1 : barB0);   \
+    if (warp_u == 0) {                     \
+        if (elect_one()) {                 \
+            fence_after();                 \
+            A_LIST;                        \
+            umma_commit(bar);              \
+        }                                  \
+        __syncwarp();                      \
+    } else if (warp_u == 4) {              \
+        if (elect_one()) {                 \
+            fence_after();                 \
+            B_LIST;                        \
+            umma_commit(KB ? barB1 : barB0); \
+        }                                  \
+        __syncwarp();                      \
     }
 #define FB_WAIT_B(KB)                  \
     if (KB) {                          \
@@ -359,20 +337,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
             const float s0 = warp_sum(dz3[0]), s1 = warp_sum(dz3[1]), s2 = warp_sum(dz3[2]);
             db_r2 += lane == 0 ? s0 : (lane == 1 ? s1 : s2);
         }
-        float dzv[32];
         FB_WAIT()
-        dgrad_epilogue32(trow + TM::acc, 32 * half, A2, DZb, r, dzv);
+        dgrad_epilogue32(trow + TM::acc, 32 * half, A2, DZb, r);
         FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::r1, kHid, kHid, kHid, false),
-                       gemm_wgrad(tmem + TM::r1, aDZb, aA1, kHid, acc_dw), 1)
-        db_r1 += column_sums32(dzv, lane);
+                       gemm_wgrad(tmem + TM::r1, aDZb, aA1, kHid, acc_dw);
+                       gemm_bias_grad(tmem + TM::r2, aDZb, onehot + R1 * 256), 1)
         FB_WAIT()
         FB_WAIT_B(0)      // the r2 group (read DZa, A2) is complete: DZa may be rewritten
-        dgrad_epilogue32(trow + TM::acc, 32 * half, A1, DZa, r, dzv);
+        dgrad_epilogue32(trow + TM::acc, 32 * half, A1, DZa, r);
         FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::r0, kHid, kRgbIn, kHid, false),
                        gemm_wgrad(tmem + TM::r0, aDZa, aSH, 16, acc_dw);
                        gemm_wgrad(tmem + TM::r0 + 16, aDZa, aH, 16, acc_dw);
-                       gemm_wgrad(tmem + TM::r0 + 32, aDZa, aSH + 2 * CH, 16, acc_dw), 0)
-        db_r0 += column_sums32(dzv, lane);
+                       gemm_wgrad(tmem + TM::r0 + 32, aDZa, aSH + 2 * CH, 16, acc_dw);
+                       gemm_bias_grad(tmem + TM::r2, aDZa, onehot + R0 * 256), 0)
         FB_WAIT()
         FB_WAIT_B(1)      // the r1 group (read DZb, A1) is complete
         float d_h01[16];   // half 0: gradient of h[0:16] from the colour head (column 0 is zero by construction)
@@ -425,22 +402,20 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
             dots[half * 128 + r] = dot;
 #pragma unroll
             for (int i = 0; i < 32; i += 8) store_chunk(DZb, kRows, r, 32 * half + i, v + i);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) dzv[i] = v[i];
         }
         FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::s2, kSem, kHid, kSem, false),
-                       gemm_wgrad(tmem + TM::s2, aDZb, aA2, kHid, acc_dw), 1)
-        db_s2 += column_sums32(dzv, lane);
+                       gemm_wgrad(tmem + TM::s2, aDZb, aA2, kHid, acc_dw);
+                       gemm_bias_grad(tmem + TM::r2, aDZb, onehot + S2 * 256), 1)
         // compositing backward, pass 1 (the barrier above published dots[]): total gradient on this weight
         float g = gw_in + rc[67] + rc[68] * (tm - rc[69]) * rc[70] + dots[r] + dots[128 + r] + dots[256 + r];
         if (!finite) g = 0.f;
         const double gw_incl = warp_scan_incl((double)g * (double)w, lane);
         if (lane == 31) tails[warp * 2 + 1] = gw_incl;
         FB_WAIT()
-        dgrad_epilogue32(trow + TM::acc, 32 * half, A2, DZa, r, dzv);
+        dgrad_epilogue32(trow + TM::acc, 32 * half, A2, DZa, r);
         FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::s1, kHid, kHid, kHid, false),
-                       gemm_wgrad(tmem + TM::s1, aDZa, aA1, kHid, acc_dw), 0)
-        db_s1 += column_sums32(dzv, lane);
+                       gemm_wgrad(tmem + TM::s1, aDZa, aA1, kHid, acc_dw);
+                       gemm_bias_grad(tmem + TM::r2, aDZa, onehot + S1 * 256), 0)
         // pass 2: d sigma_i = delta_i * (g_i T_{i+1} - sum_{k>i} g_k w_k); d raw = d sigma * sel * exp(clamp(raw))
         float d_raw;
         {
@@ -455,10 +430,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
         }
         FB_WAIT()
         FB_WAIT_B(1)      // the s2 group (read DZb, A2) is complete: DZb may be rewritten
-        dgrad_epilogue32(trow + TM::acc, 32 * half, A1, DZb, r, dzv);
+        dgrad_epilogue32(trow + TM::acc, 32 * half, A1, DZb, r);
         FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::s0, kHid, kSem, kHid, false),
-                       gemm_wgrad(tmem + TM::s0, aDZb, aH + 2 * CH, kSem, acc_dw), 1)
-        db_s0 += column_sums32(dzv, lane);
+                       gemm_wgrad(tmem + TM::s0, aDZb, aH + 2 * CH, kSem, acc_dw);
+                       gemm_bias_grad(tmem + TM::r2, aDZb, onehot + S0 * 256), 1)
         FB_WAIT()
         FB_WAIT_B(0)      // the s1 group (read DZa, A1) is complete: DZa may take dH
         // ---- base network, backward: dH = [d raw | colour head (15) | semantic head (64)] ----------------------
@@ -472,8 +447,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
             }
 #pragma unroll
             for (int i = 0; i < 32; i += 8) store_chunk(DZa, kRows, r, 16 + 32 * half + i, v + i);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) dzv[i] = v[i];
             if (half == 0) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) d_h01[i] = valid ? d_h01[i] : 0.f;
@@ -483,15 +456,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
             }
         }
         FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::b1, kBaseOut, kHid, kBaseOut, false),
-                       gemm_wgrad(tmem + TM::b1, aDZa, aH1, kHid, acc_dw), 0)
-        db_b1 += column_sums32(dzv, lane);                        // columns 16 + 32 * half + lane
-        if (half == 0) db_b1lo += column_sums16(d_h01, lane);     // columns 0..15 (lanes 0..15)
+                       gemm_wgrad(tmem + TM::b1, aDZa, aH1, kHid, acc_dw);
+                       gemm_bias_grad(tmem + TM::r2, aDZa, onehot + B1 * 256), 0)
         FB_WAIT()
         FB_WAIT_B(1)      // the s0 group (read DZb, H) is complete
-        dgrad_epilogue32(trow + TM::acc, 32 * half, H1, DZb, r, dzv);
+        dgrad_epilogue32(trow + TM::acc, 32 * half, H1, DZb, r);
         FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::b0, kHid, K0, kHid, false),
-                       gemm_wgrad(tmem + TM::b0, aDZb, aX0, K0, acc_dw), 1)
-        db_b0 += column_sums32(dzv, lane);
+                       gemm_wgrad(tmem + TM::b0, aDZb, aX0, K0, acc_dw);
+                       gemm_bias_grad(tmem + TM::r2, aDZb, onehot + B0 * 256), 1)
         FB_WAIT()
         FB_WAIT_B(0)      // the b1 group (read DZa, H1) ...
         FB_WAIT_B(1)      // ... and the b0 group (read DZb, X0) are complete: every tile may be restaged
@@ -571,20 +543,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
         flush(TM::r0, kHid, kRgbIn, a.net.dW[R0], 16 + kGeo + A, 1);
         flush(TM::r1, kHid, kHid, a.net.dW[R1], kHid, 0);
         flush(TM::r2, kHid, kRgbOut, a.net.dW[R2], kHid, 2);
-        // bias gradients: this warp's partial column sums (lane = column within the half's 32-column block)
-        {
-            const int c = 32 * half + lane;
-            if (a.net.dB[R1]) atomicAdd(a.net.dB[R1] + c, db_r1);
-            if (a.net.dB[R0]) atomicAdd(a.net.dB[R0] + c, db_r0);
-            if (a.net.dB[S2]) atomicAdd(a.net.dB[S2] + c, db_s2);
-            if (a.net.dB[S1]) atomicAdd(a.net.dB[S1] + c, db_s1);
-            if (a.net.dB[S0]) atomicAdd(a.net.dB[S0] + c, db_s0);
-            if (a.net.dB[B0]) atomicAdd(a.net.dB[B0] + c, db_b0);
-            if (a.net.dB[B1]) {
-                atomicAdd(a.net.dB[B1] + 16 + c, db_b1);
-                if (half == 0 && lane < 16) atomicAdd(a.net.dB[B1] + lane, db_b1lo);
+        // bias gradients: column kBiasCol0 + l of the shared 16-column accumulator, row = out feature
+        if (half == 0) {
+            float u[16];
+            tmem_ld16_nowait(trow + TM::r2, u);
+            tmem_wait_ld();
+            const int n = warp * 32 + lane;
+#pragma unroll
+            for (int l = 0; l < kLayers; ++l) {
+                if (l == R2) continue;
+                if (n < WL::rows(l) && a.net.dB[l]) atomicAdd(a.net.dB[l] + n, u[kBiasCol0 + l]);
             }
-            if (half == 0 && lane < 3 && a.net.dB[R2]) atomicAdd(a.net.dB[R2] + lane, db_r2);
+            if (lane < 3 && a.net.dB[R2]) atomicAdd(a.net.dB[R2] + lane, db_r2);
         }
     }
     fence_before();

@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
     const uint32_t wb = smem_u32(wbase), ones = wb + WL::ones;
     const uint32_t aH = smem_u32(Ht), aSH = smem_u32(SHAPPt), aA = smem_u32(BufA), aB = smem_u32(BufB);
     const int barid = 1 + g;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // provably warp-uniform copy (issue branch)
     uint32_t phase = 0;
 
     const int S = a.S;
@@ -116,10 +117,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
     fence_async_smem();                    \
     fence_before();                        \
     bar_sync(barid, 128);                  \
-    if (t == 0) {                          \
-        fence_after();                     \
-        __VA_ARGS__;                       \
-        umma_commit(bar);                  \
+    if (warp_u == 0) {                     \
+        if (elect_one()) {                 \
+            fence_after();                 \
+            __VA_ARGS__;                   \
+            umma_commit(bar);              \
+        }                                  \
+        __syncwarp();                      \
     }
 #define FT_WAIT()           \
     mbar_wait(bar, phase);  \

@@ -114,8 +114,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) distortion_kernel(const float
 
 // z-anti-aliased (zip-NeRF) interlevel loss, one proposal level per launch: one THREAD per ray runs zaa_core.h's
 // sequential per-ray code (merge of the two shifted edge lists, the nested fp64-carried cumsums, a forward sweep over
-// the sorted query edges).  First version: correctness against the reference's tie semantics first; a warp-per-ray
-// variant (merge by rank, warp scans) is the obvious next step if it ever shows up in the step's profile.
+// the sorted query edges).  First version (PS_ZAA_WARP=0): correctness against the reference's tie semantics first.
 __global__ void __launch_bounds__(128) zaa_interlevel_kernel(const float* __restrict__ c, const float* __restrict__ w,
                                                              int64_t N, int S, const float* __restrict__ cp,
                                                              const float* __restrict__ wp, int Sp, double r,
@@ -129,8 +128,8 @@ __global__ void __launch_bounds__(128) zaa_interlevel_kernel(const float* __rest
     if ((threadIdx.x & 31) == 0 && l != 0.f) atomicAdd(loss_sum, l);
 }
 
-// EXPERIMENTAL (opt-in with PS_ZAA_WARP=1; written after the round's GPU budget was spent, so NOT yet run on a GPU):
-// the same loss with one WARP per ray, following the loop-free formulation that tools/zaa_parallel_prototype.py checks
+// The default kernel (B200, 65 536 rays, S = 64, Sp = 128: 0.24 ms per level against 0.91 ms for the thread-per-ray
+// kernel above, gpurun_out/r2_zaa_exp.txt; both pass the reference fixture): the same loss with one WARP per ray, following the loop-free formulation that tools/zaa_parallel_prototype.py checks
 // against the reference's fixture — merge by rank (two binary searches per knot; "c - r first on ties"), fp64-carried
 // warp scans over the knots in chunks of 32, interval lookup and flat-run lookup by binary search per query.
 // Shared memory per warp (floats): c[S+1] | wn[S+1] | xr[K] | y2[K] | yr[K] | cdf[K] | ret[Sp+1],  K = 2S + 2.
@@ -267,8 +266,9 @@ extern "C" int ps_zaa_interlevel_loss(const float* c, const float* w, int64_t N,
                zaa::kMaxS);
     PS_REQUIRE(Sp >= 1, "zaa_interlevel_loss: proposal samples per ray %d < 1", Sp);
     PS_REQUIRE(pulse_width > 0.0, "zaa_interlevel_loss: pulse width must be positive");
-    static const bool warp_per_ray = getenv("PS_ZAA_WARP") != nullptr && atoi(getenv("PS_ZAA_WARP")) != 0;
-    if (warp_per_ray) {                                      // experimental, see zaa_interlevel_warp_kernel
+    // PS_ZAA_WARP=0 selects the first, thread-per-ray kernel (kept as a second implementation of the same arithmetic)
+    static const bool warp_per_ray = getenv("PS_ZAA_WARP") == nullptr || atoi(getenv("PS_ZAA_WARP")) != 0;
+    if (warp_per_ray) {
         const size_t smem = (size_t)kZaaWarps * (2 * (S + 1) + 4 * (2 * S + 2) + (Sp + 1)) * sizeof(float);
         PS_REQUIRE(smem <= 200 * 1024, "zaa_interlevel_loss: %zu bytes of shared memory", smem);
         static bool configured = false;

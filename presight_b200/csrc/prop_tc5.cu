@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(kThreads) prop_fwd_kernel(PropArgs a) {
     __syncthreads();
     fence_after();
     const uint32_t tmem = *tmem_slot;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // provably warp-uniform (MMA issue branch, tc5::elect_one)
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     const uint32_t bar = smem_u32(bar_ptr);
     uint32_t phase = 0;
@@ -214,10 +215,13 @@ __global__ void __launch_bounds__(kThreads) prop_fwd_kernel(PropArgs a) {
         fence_async_smem();
         fence_before();
         __syncthreads();
-        if (tid == 0) {
-            fence_after();
-            gemm_kk(tmem, smem_u32(X0), kRows, smem_u32(smem + SM::w0), H, H, kK0, false);
-            umma_commit(bar);
+        if (warp_u == 0) {
+            if (elect_one()) {
+                fence_after();
+                gemm_kk(tmem, smem_u32(X0), kRows, smem_u32(smem + SM::w0), H, H, kK0, false);
+                umma_commit(bar);
+            }
+            __syncwarp();
         }
         mbar_wait(bar, phase);
         phase ^= 1;
@@ -293,6 +297,7 @@ __global__ void __launch_bounds__(kThreads) prop_bwd_kernel(PropArgs a) {
     __syncthreads();
     fence_after();
     const uint32_t tmem = *tmem_slot;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // provably warp-uniform (MMA issue branch, tc5::elect_one)
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     const uint32_t bar = smem_u32(bar_ptr);
     const uint32_t aH1 = smem_u32(H1), aDZ0 = smem_u32(DZ0), aX0 = smem_u32(X0), aDZ1 = smem_u32(DZ1),
@@ -323,10 +328,13 @@ __global__ void __launch_bounds__(kThreads) prop_bwd_kernel(PropArgs a) {
         fence_async_smem();
         fence_before();
         __syncthreads();
-        if (tid == 0) {
-            fence_after();
-            gemm_kk(tmem + TM::acc, aX0, kRows, aW0, H, H, kK0, false);
-            umma_commit(bar);
+        if (warp_u == 0) {
+            if (elect_one()) {
+                fence_after();
+                gemm_kk(tmem + TM::acc, aX0, kRows, aW0, H, H, kK0, false);
+                umma_commit(bar);
+            }
+            __syncwarp();
         }
         mbar_wait(bar, phase);
         phase ^= 1;
@@ -391,13 +399,16 @@ __global__ void __launch_bounds__(kThreads) prop_bwd_kernel(PropArgs a) {
         fence_async_smem();
         fence_before();
         __syncthreads();
-        if (tid == 0) {
-            fence_after();
-            gemm_dgrad(tmem + TM::acc, aDZ0, kRows, aW0, H, kK0, H, false);     // d feat [128 x 16]
-            gemm_wgrad(tmem + TM::dw0, aDZ0, aX0, kK0, acc_dw);                // dW0 [H x 16]
-            gemm_wgrad(tmem + TM::dw1, aH1, aDZ1, 16, acc_dw);                 // dW1^T [H x 16], column 0
-            gemm_wgrad(tmem + TM::db0, aDZ0, aONES, 16, acc_dw);               // hidden bias gradient = dZ0^T 1
-            umma_commit(bar);     // one commit: the tiles these GEMMs read are rewritten by the next tile
+        if (warp_u == 0) {
+            if (elect_one()) {
+                fence_after();
+                gemm_dgrad(tmem + TM::acc, aDZ0, kRows, aW0, H, kK0, H, false);     // d feat [128 x 16]
+                gemm_wgrad(tmem + TM::dw0, aDZ0, aX0, kK0, acc_dw);                // dW0 [H x 16]
+                gemm_wgrad(tmem + TM::dw1, aH1, aDZ1, 16, acc_dw);                 // dW1^T [H x 16], column 0
+                gemm_wgrad(tmem + TM::db0, aDZ0, aONES, 16, acc_dw);               // hidden bias gradient = dZ0^T 1
+                umma_commit(bar);     // one commit: the tiles these GEMMs read are rewritten by the next tile
+            }
+            __syncwarp();
         }
         mbar_wait(bar, phase);
         phase ^= 1;

@@ -93,19 +93,23 @@ extern "C" int ps_tc5_probe(const float* X, const float* Y, const float* W, floa
     return check_launch("tc5_probe");
 }
 
-// ---- timing probe: cycles per tcgen05.mma as a function of N and of the operand majorness (tools/mma_cost.py) --------
+// ---- timing probe: cycles per tcgen05.mma as a function of N, operand majorness, number of independent accumulators
+// and number of issuing threads (tools/mma_cost.py) ----------------------------------------------------------------
 namespace ps {
 namespace tc5 {
-__global__ void __launch_bounds__(128) mma_cost_kernel(int N, int mn_major, int n_mma, int same_acc, int M, long long* out) {
+// n_acc independent accumulators used round-robin (n_acc * N <= 512 columns); n_issuers threads (thread 0 of the
+// first n_issuers warps) issue n_mma instructions each, each issuer on its own accumulator set when n_acc >= n_issuers.
+// out[0] = cycles until issuer 0 has issued its last instruction, out[1] = until every issuer's commit has arrived.
+__global__ void __launch_bounds__(128) mma_cost_kernel(int N, int mn_major, int n_mma, int n_acc, int M, int n_issuers,
+                                                       long long* out) {
     extern __shared__ __align__(128) unsigned char smem[];      // 64 KB of zeros: operands
     uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(smem + 65536);
-    uint32_t* slot = reinterpret_cast<uint32_t*>(bar_ptr + 1);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar_ptr + 4);
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < 65536 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    const uint32_t bar = smem_u32(bar_ptr);
     if (warp == 0) tmem_alloc(slot, 512);
     if (tid == 0) {
-        mbar_init(bar, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(smem_u32(bar_ptr + i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_async_smem();
@@ -113,24 +117,35 @@ __global__ void __launch_bounds__(128) mma_cost_kernel(int N, int mn_major, int 
     __syncthreads();
     fence_after();
     const uint32_t tmem = *slot;
-    if (tid == 0) {
+    __shared__ long long ts[2];
+    long long t0 = 0, t1 = 0;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    if (warp_u < n_issuers) {
+      if (elect_one()) {
         const uint32_t a = smem_u32(smem), b = smem_u32(smem) + 32768;
         // make_idesc encodes M = 128; patch the M field (bits 24..28 = M >> 4) for the M = 64 variant
         const uint32_t idesc = (make_idesc(N, mn_major, mn_major) & ~(0x1Fu << 24)) | ((uint32_t)(M >> 4) << 24);
-        const long long t0 = clock64();
+        const int per = n_acc >= n_issuers ? n_acc / n_issuers : 1;       // accumulators per issuer
+        const int base = n_acc >= n_issuers ? warp * per : 0;
+        t0 = clock64();
         for (int i = 0; i < n_mma; ++i) {
-            const uint32_t d = tmem + (same_acc ? 0 : (i & 1) * 256);
+            const uint32_t d = tmem + (uint32_t)((base + i % per) * N);
             if (mn_major)
                 umma_bf16(d, make_desc(a + (i & 7) * 256, 128, kRows * 16), make_desc(b + (i & 7) * 256, 128, kRows * 16), idesc, 1u);
             else
                 umma_bf16(d, make_desc(a + (i & 3) * 4096, kRows * 16, 128), make_desc(b + (i & 3) * 4096, kRows * 16, 128), idesc, 1u);
         }
-        const long long t1 = clock64();
-        umma_commit(bar);
-        mbar_wait(bar, 0);
+        t1 = clock64();
+        if (warp == 0) { ts[0] = t0; ts[1] = t1; }
+        umma_commit(smem_u32(bar_ptr + warp));
+      }
+      __syncwarp();
+    }
+    if (tid == 0) {
+        for (int i = 0; i < n_issuers; ++i) mbar_wait(smem_u32(bar_ptr + i), 0);
         const long long t2 = clock64();
-        out[0] = t1 - t0;
-        out[1] = t2 - t0;
+        out[0] = ts[1] - ts[0];
+        out[1] = t2 - ts[0];
     }
     fence_before();
     __syncthreads();
@@ -140,14 +155,17 @@ __global__ void __launch_bounds__(128) mma_cost_kernel(int N, int mn_major, int 
 }  // namespace ps
 
 /* tools only (not declared in include/presight_b200.h) */
-extern "C" int ps_tc5_mma_cost(int N, int mn_major, int n_mma, int same_acc, int M, long long* out, void* stream) {
+extern "C" int ps_tc5_mma_cost(int N, int mn_major, int n_mma, int n_acc, int M, int n_issuers, long long* out,
+                               void* stream) {
     using namespace ps;
+    PS_REQUIRE(n_acc >= 1 && n_acc * N <= 512 && n_issuers >= 1 && n_issuers <= 4 && (!mn_major || N <= 128),
+               "tc5_mma_cost: bad shape");
     const size_t smem = 65536 + 64;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(tc5::mma_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
-    tc5::mma_cost_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(N, mn_major, n_mma, same_acc, M, out);
+    tc5::mma_cost_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(N, mn_major, n_mma, n_acc, M, n_issuers, out);
     return check_launch("tc5_mma_cost");
 }

@@ -3,11 +3,10 @@ SURVEY §8(f)-1, the first "next" row): the terms that sit between compositing-f
 training step.  The proposal losses (z-anti-aliased and plain), the distortion loss and the rgb / sky / semantic terms
 each run as ONE kernel producing the loss and its gradient (`ps_zaa_interlevel_loss`, `ps_interlevel_loss`,
 `ps_distortion_loss`, `ps_render_losses`); they take CUDA tensors only — there is no torch fallback for them (the CPU
-restatements live in `oracle/`).  The depth-supervision terms at the end are the rows not yet written as kernels and are
-plain torch expressions."""
+restatements live in `oracle/`).  The depth-supervision terms (expected LiDAR / mono depth, line of sight) are one more
+kernel, `ps_depth_losses`."""
 from __future__ import annotations
 
-import math
 from typing import List, Optional
 
 import torch
@@ -47,49 +46,41 @@ def distortion_loss(weights_list: List[Tensor], sp_bins_list: List[Tensor]) -> T
     return ops.distortion_loss(sp_bins_list[-1].detach(), weights_list[-1])
 
 
-# ---- depth supervision (PreSight/losses.py:25-103).  Not kernels yet (SURVEY 8f-1 lists them as the remaining rows of the
-# loss stack): per-ray torch expressions, reached only when the batch carries a "depth" target.
-def _supervised_rays(target_m: Tensor, limit_m: float, sky_mask: Optional[Tensor]) -> Tensor:
-    """Rays whose target depth is usable: strictly between 1 m and the upper bound and, if a sky mask is given, not sky."""
-    ok = (target_m > 1.0) & (target_m < limit_m)
-    return ok if sky_mask is None else ok & (sky_mask == 0.0)
+# ---- depth supervision (PreSight/losses.py:24-103): one kernel for both terms and both gradients (`ps_depth_losses`,
+# csrc/depth_loss.cu); CUDA tensors only, like the rest of the loss stack.
+def depth_supervision_losses(weights: Tensor, expected_depth: Tensor, target_depth_m: Tensor, sky_mask: Optional[Tensor],
+                             pose_scale: float, sigma: float, upper_bound: float, inverse: bool = False,
+                             eu_bins: Optional[Tensor] = None, steps_m: Optional[Tensor] = None) -> Tensor:
+    """-> [2] = (expected-depth loss, line-of-sight loss), each the reference's mean over the rays with
+    1 m < target < upper_bound (and sky == 0 when a sky mask is given), before their multipliers.
 
-
-def normalize_depth(depth: Tensor, upper_bound: float = 75.0) -> Tensor:
-    return (depth / upper_bound).clip(0.0, 1.0)
+    expected-depth term: `expected_depth_loss` (:67-81, LiDAR: sky_mask None) / `expected_monodepth_loss` (:83-103, with the
+    sky mask, `inverse` = compare 1 / (d + 5)); line-of-sight term: `line_of_sight_loss` (:28-65) on the final level's
+    weights with sample mid-points from `eu_bins` (scene units, divided by `pose_scale` like nerfacto_nusc_ms.py:584-586)
+    or given in metres as `steps_m`."""
+    from . import ops
+    return ops.depth_losses(weights, expected_depth, target_depth_m, sky_mask, pose_scale, sigma, upper_bound, inverse,
+                            eu_bins=eu_bins, steps_m=steps_m)
 
 
 def expected_monodepth_loss(termination_depth: Tensor, predicted_depth: Tensor, sky_mask: Tensor,
                             upper_bound: float = 50.0, inverse: bool = False) -> Tensor:
-    """Mono-depth supervision of the rendered expected depth (:83-103): squared error of the depths mapped to [0, 1]
-    (or to 1 / (d + 5) when `inverse`), averaged over the supervised, non-sky rays."""
-    rays = _supervised_rays(termination_depth, upper_bound, sky_mask)
-    if inverse:
-        err = 1 / (termination_depth + 5) - 1 / (predicted_depth + 5)
-    else:
-        err = normalize_depth(termination_depth, upper_bound) - normalize_depth(predicted_depth, upper_bound)
-    return err.square()[rays].mean()
+    """PreSight/losses.py:83-103 (depths in metres)."""
+    from . import ops
+    return ops.depth_losses(None, predicted_depth, termination_depth, sky_mask, 1.0, 1.0, upper_bound, inverse)[0]
 
 
 def expected_depth_loss(termination_depth: Tensor, predicted_depth: Tensor, upper_bound: float = 75.0) -> Tensor:
-    """LiDAR supervision of the rendered expected depth (:67-81): as above, without the sky mask."""
-    rays = _supervised_rays(termination_depth, upper_bound, None)
-    err = normalize_depth(termination_depth, upper_bound) - normalize_depth(predicted_depth, upper_bound)
-    return err.square()[rays].mean()
+    """PreSight/losses.py:67-81 (depths in metres)."""
+    from . import ops
+    return ops.depth_losses(None, predicted_depth, termination_depth, None, 1.0, 1.0, upper_bound, False)[0]
 
 
 def line_of_sight_loss(weights: Tensor, termination_depth: Tensor, steps: Tensor, sigma: float,
                        sky_mask: Optional[Tensor] = None, upper_bound: float = 75.0) -> Tensor:
-    """Line-of-sight loss of Urban Radiance Fields (:28-65).  weights [N,S,1], termination_depth [N,1], steps [N,S,1]
-    (sample mid-points, metres).  Within +-sigma of the target the weights should follow N(0, sigma / 3) evaluated at
-    the signed distance; every sample more than sigma in front of the target should carry no weight."""
-    rays = _supervised_rays(termination_depth, upper_bound, sky_mask)
-    at, target = steps.detach(), termination_depth[:, None]                # [N,S,1], [N,1,1]
-    std = sigma / 3.0
-    gauss = torch.exp(-((at - target) ** 2) / (2 * std ** 2) - math.log(std) - math.log(math.sqrt(2 * math.pi)))
-    band = (at <= target + sigma) & (at >= target - sigma)                 # the reference's comparisons, as written
-    per_ray = (band * (weights - gauss).square()).sum(-2) + ((at < target - sigma) * weights.square()).sum(-2)
-    return per_ray[rays].mean()
+    """PreSight/losses.py:28-65.  weights [N,S,1], termination_depth [N,1], steps [N,S,1] (sample mid-points, metres)."""
+    from . import ops
+    return ops.depth_losses(weights, None, termination_depth, sky_mask, 1.0, sigma, upper_bound, False, steps_m=steps)[1]
 
 
 def render_losses(outputs, batch, use_sky: bool = True, use_semantics: bool = True) -> Tensor:

@@ -306,10 +306,23 @@ class NerfactoNuscMSModel(nn.Module):
             return 0.0
         return c.line_of_sight_mult / (2.0 ** (step // c.line_of_sight_decay_steps))
 
+    @staticmethod
+    def _pose_scale_factor(ray_samples: RaySamples, batch: Dict[str, Tensor]):
+        """nerfacto_nusc_ms.py:584: the reference reads `ray_samples.metadata["pose_scale_factor"][0, 0, 0]`; a batch entry
+        of the same name is accepted too.  Missing from both is an error (depth units would silently be wrong).  A CUDA
+        tensor is handed to the kernel as it is and read on the device."""
+        md = getattr(ray_samples, "metadata", None) or {}
+        v = md.get("pose_scale_factor", batch.get("pose_scale_factor"))
+        if v is None:
+            raise KeyError("depth supervision needs `pose_scale_factor` in ray_samples.metadata (as the reference's "
+                           "datamanager provides) or in the batch")
+        return v if (torch.is_tensor(v) and v.is_cuda) else float(v.reshape(-1)[0] if torch.is_tensor(v) else v)
+
     def get_loss_dict(self, outputs: Dict[str, object], batch: Dict[str, Tensor]) -> Dict[str, Tensor]:
-        """The camera-only terms of nerfacto_nusc_ms.py:558-645 (rgb, sky, semantic, interlevel, distortion), each on its
-        kernel: `ps_render_losses` for the three rendered-output terms, `ps_zaa_interlevel_loss` / `ps_interlevel_loss`
-        per proposal level, `ps_distortion_loss`.  batch: "rgb" [N,3], "sky" [N,1] (1 = sky), "features" [N,C]."""
+        """nerfacto_nusc_ms.py:558-645, every term on a kernel: `ps_render_losses` for the three rendered-output terms
+        (rgb, sky, semantic), `ps_depth_losses` for the depth supervision (expected depth + line of sight),
+        `ps_zaa_interlevel_loss` / `ps_interlevel_loss` per proposal level, `ps_distortion_loss`.
+        batch: "rgb" [N,3], "sky" [N,1] (1 = sky), "features" [N,C], "depth" [N] (metres)."""
         from . import losses
         c = self.config
         use_sky = c.use_sky_model and "sky" in batch
@@ -321,24 +334,19 @@ class NerfactoNuscMSModel(nn.Module):
         if use_sem:
             loss_dict["semantic_loss"] = c.semantic_loss_mult * terms[2]
         if (c.use_monodepth_loss or c.use_lidar_loss) and "depth" in batch:
-            # :577-629 — torch expressions for now (the remaining rows of the loss stack)
-            depth = batch["depth"].view(-1, 1)
-            scale = float(batch.get("pose_scale_factor", 1.0))
+            # :577-629 — both terms and both gradients in ONE kernel (ps_depth_losses).  Branch order as in the reference:
+            # the mono-depth branch runs first and the LiDAR branch, when both are enabled, overwrites its entries.
             last = outputs["ray_samples_list"][-1]
-            steps = (last.frustums.starts + last.frustums.ends) / 2 / scale
-            predicted = outputs["expected_depth"] / scale
+            scale = self._pose_scale_factor(last, batch)
             sigma, mult = self.get_line_of_sight_sigma(self.step), self.get_line_of_sight_mult(self.step)
-            sky_mask = batch["sky"].view(-1, 1) if c.use_monodepth_loss else None
-            if c.use_monodepth_loss:
-                loss_dict["expected_depth_loss"] = c.expected_depth_loss_mult * losses.expected_monodepth_loss(
-                    depth, predicted, sky_mask, c.monodepth_depth_upperbound, c.monodepth_loss_inverse)
-                ub = c.monodepth_depth_upperbound
-            else:
-                loss_dict["expected_depth_loss"] = c.expected_depth_loss_mult * losses.expected_depth_loss(
-                    depth, predicted, c.lidar_depth_upperbound)
-                ub = c.lidar_depth_upperbound
-            loss_dict["line_of_sight_loss"] = mult * losses.line_of_sight_loss(
-                outputs["weights_list"][-1], depth, steps, sigma, sky_mask, ub)
+            lidar = c.use_lidar_loss
+            terms_d = losses.depth_supervision_losses(
+                outputs["weights_list"][-1], outputs["expected_depth"], batch["depth"].view(-1, 1),
+                None if lidar else batch["sky"].view(-1, 1), scale, sigma,
+                c.lidar_depth_upperbound if lidar else c.monodepth_depth_upperbound,
+                inverse=(not lidar) and c.monodepth_loss_inverse, eu_bins=last.frustums.eu_bins)
+            loss_dict["expected_depth_loss"] = c.expected_depth_loss_mult * terms_d[0]
+            loss_dict["line_of_sight_loss"] = mult * terms_d[1]
         if self.training:
             wl = outputs["weights_list"]
             sp = [rs.sp_bins for rs in outputs["ray_samples_list"]]

@@ -620,13 +620,14 @@ class _RenderLosses(torch.autograd.Function):
         with _probe("render_losses"):
             call("ps_render_losses", ptr(r), ptr(gr), ptr(a), ptr(km), ptr(s), ptr(gs), N, C, float(eps), ptr(losses),
                  ptr(g_r), ptr(g_a), ptr(g_s), stream())
-        ctx.grads = (g_r, g_a, g_s)
+        ctx.has = tuple(t is not None for t in (g_r, g_a, g_s))
+        ctx.save_for_backward(*(t for t in (g_r, g_a, g_s) if t is not None))
         return losses
 
     @staticmethod
     def backward(ctx, g):
-        g_r, g_a, g_s = ctx.grads
-        ctx.grads = None
+        rest = list(ctx.saved_tensors)
+        g_r, g_a, g_s = (rest.pop(0) if h else None for h in ctx.has)
         return (None if g_r is None else g_r * g[0], None, None if g_a is None else g_a * g[1], None,
                 None if g_s is None else g_s * g[2], None, None)
 
@@ -635,6 +636,54 @@ def render_losses(rgb: Optional[Tensor], gt_rgb: Optional[Tensor], acc: Optional
                   sem: Optional[Tensor], gt_sem: Optional[Tensor], eps: float = 1e-7) -> Tensor:
     """-> [3] = (rgb_loss, sky_loss, semantic_loss), each a mean; pass None pairs to skip a term."""
     return _RenderLosses.apply(rgb, gt_rgb, acc, sky_mask, sem, gt_sem, eps)
+
+
+class _DepthLosses(torch.autograd.Function):
+    """[expected-depth loss, line-of-sight loss] (model_components/PreSight/losses.py:28-103 as called from
+    nerfacto_nusc_ms.py:577-629): means over the rays passing the depth mask, with both gradients produced by the same
+    kernel.  The number of masked rays stays on the device (no host sync); an empty mask gives NaN like torch's mean."""
+
+    @staticmethod
+    def forward(ctx, weights, expected_depth, eu_bins, steps_m, target_m, sky_mask, pose_scale, sigma, upper_bound, mode):
+        c = lambda t: None if t is None else _f32c(t.detach())
+        w, e, b, st, tg, sk = c(weights), c(expected_depth), c(eu_bins), c(steps_m), c(target_m), c(sky_mask)
+        N = tg.numel()
+        S = 0 if w is None else w.numel() // max(N, 1)
+        if w is not None:
+            assert w.numel() == N * S and (b is None or b.shape == (N, S + 1)) and (st is None or st.numel() == N * S)
+        sums = torch.zeros(3, device=tg.device, dtype=torch.float32)
+        g_e = torch.empty(N, device=tg.device, dtype=torch.float32) if (e is not None and ctx.needs_input_grad[1]) else None
+        g_w = torch.empty(N, S, device=tg.device, dtype=torch.float32) if (w is not None and ctx.needs_input_grad[0]) else None
+        scale_dev = _f32c(pose_scale.detach()).reshape(-1)[:1] if torch.is_tensor(pose_scale) else None
+        with _probe("depth_losses"):
+            call("ps_depth_losses", ptr(w), ptr(b), ptr(st), ptr(e), ptr(tg), ptr(sk), N, S,
+                 1.0 if scale_dev is not None else float(pose_scale), ptr(scale_dev), float(sigma), float(upper_bound),
+                 int(mode), ptr(sums), ptr(g_e), ptr(g_w), stream())
+        inv = 1.0 / sums[0]
+        ctx.save_for_backward(inv, *(t for t in (g_e, g_w) if t is not None))
+        ctx.has = (g_e is not None, g_w is not None)
+        ctx.shapes = (None if weights is None else weights.shape, None if expected_depth is None else expected_depth.shape)
+        return sums[1:] * inv
+
+    @staticmethod
+    def backward(ctx, g):
+        inv, *rest = ctx.saved_tensors
+        g_e = rest.pop(0) if ctx.has[0] else None
+        g_w = rest.pop(0) if ctx.has[1] else None
+        d_w = None if g_w is None else (g_w * (g[1] * inv)).view(ctx.shapes[0])
+        d_e = None if g_e is None else (g_e * (g[0] * inv)).view(ctx.shapes[1])
+        return d_w, d_e, None, None, None, None, None, None, None, None
+
+
+def depth_losses(weights: Optional[Tensor], expected_depth: Optional[Tensor], target_depth_m: Tensor,
+                 sky_mask: Optional[Tensor], pose_scale, sigma: float, upper_bound: float, inverse: bool = False,
+                 eu_bins: Optional[Tensor] = None, steps_m: Optional[Tensor] = None) -> Tensor:
+    """-> [2] = (expected-depth loss, line-of-sight loss) before their multipliers.  weights [N,S(,1)] final-level
+    weights with their bin edges `eu_bins` [N,S+1] (scene units) or mid-points `steps_m` [N,S(,1)] (metres);
+    expected_depth [N(,1)] rendered depth in scene units; target_depth_m [N(,1)] metres; sky_mask [N(,1)] or None;
+    pose_scale: a float, or a CUDA tensor whose first element is read on the device (no host sync)."""
+    return _DepthLosses.apply(weights, expected_depth, eu_bins, steps_m, target_depth_m, sky_mask,
+                              pose_scale if torch.is_tensor(pose_scale) else float(pose_scale), float(sigma), float(upper_bound), 1 if inverse else 0)
 
 
 def launch_count() -> int:

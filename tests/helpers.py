@@ -59,6 +59,22 @@ def assert_close(a, b, tol, what=""):
     assert e <= tol, f"{what}: scale-relative error {e:.3e} > {tol:.1e}"
 
 
+def elem_rel_err(a, b, floor):
+    """max over elements of |a-b| / max(|b|, floor): the per-element relative error with an absolute floor — the metric
+    BASELINE.json's "within 1e-3 relative" reads as for every element that is not itself rounding noise (`floor` is set
+    per quantity, a few orders below its scale)."""
+    a = torch.as_tensor(a).detach().double()
+    b = torch.as_tensor(b).detach().double()
+    if a.numel() == 0:
+        return 0.0
+    return float(((a - b).abs() / b.abs().clamp_min(floor)).max())
+
+
+def assert_close_elem(a, b, tol, floor, what=""):
+    e = elem_rel_err(a, b, floor)
+    assert e <= tol, f"{what}: per-element relative error {e:.3e} > {tol:.1e} (floor {floor:.1e})"
+
+
 def ms_count(sd, prefix="fields."):
     n = 0
     while any(k.startswith(f"{prefix}{n}.") for k in sd):

@@ -157,6 +157,56 @@ def test_c2_loss_dict_matches_oracle():
     assert "proposal_networks.0.fields.0.encoding.hash_table" in grads and "field.fields.0.mlp_base_grid.hash_table" in grads
 
 
+@pytest.mark.parametrize("lidar", [False, True])
+def test_c2_loss_dict_with_depth_supervision(lidar):
+    """`get_loss_dict` with a depth target (nerfacto_nusc_ms.py:577-629): expected-depth and line-of-sight terms from
+    `ps_depth_losses` against the oracle's restatements on the SAME rendered depth / weights / bins, in the mono-depth
+    and the LiDAR variant (which, as in the reference, wins when both are enabled and ignores the sky mask); the step
+    drives the line-of-sight schedules; a missing pose scale factor is an error."""
+    from presight_b200.cameras.rays import RayBundle
+    from presight_b200.model import VIDEO_ID
+    n = 256
+    model, cfg, host = build("c2", "b200", n)
+    cfg.use_monodepth_loss = True
+    cfg.use_lidar_loss = lidar
+    model.step = 12000                      # past line_of_sight_start_step: mult = 0.1 / 2^2, sigma between max and min
+    scale = 0.05
+    rb = RayBundle(origins=host["origins"].to(DEV), directions=host["directions"].to(DEV),
+                   camera_indices=host["camera_indices"].to(DEV),
+                   metadata={VIDEO_ID: host["video_ids"].to(DEV),
+                             "pose_scale_factor": torch.full((n, 1), scale, device=DEV)})
+    model.proposal_sampler._step = 0
+    out = model(rb)
+    g = torch.Generator().manual_seed(11)
+    depth = torch.rand(n, generator=g) * 90.0
+    batch = {k: host[k].to(DEV) for k in ("rgb", "sky", "features")}
+    batch["depth"] = depth.to(DEV)
+    ld = model.get_loss_dict(out, batch)
+    assert {"expected_depth_loss", "line_of_sight_loss"} <= set(ld)
+    last = out["ray_samples_list"][-1]
+    eu = last.frustums.eu_bins.detach().cpu()
+    steps = ((eu[:, :-1] + eu[:, 1:]) / 2 / scale)[..., None]
+    pred = out["expected_depth"].detach().cpu() / scale
+    w = out["weights_list"][-1].detach().cpu()
+    sky = host["sky"].view(-1, 1)
+    sigma, mult = O.line_of_sight_sigma(12000), O.line_of_sight_mult(12000)
+    if lidar:
+        want_e = O.expected_depth_loss(depth.view(-1, 1), pred, cfg.lidar_depth_upperbound)
+        want_l = O.line_of_sight_loss(w, depth.view(-1, 1), steps, sigma, None, cfg.lidar_depth_upperbound)
+    else:
+        want_e = O.expected_monodepth_loss(depth.view(-1, 1), pred, sky, cfg.monodepth_depth_upperbound, False)
+        want_l = O.line_of_sight_loss(w, depth.view(-1, 1), steps, sigma, sky, cfg.monodepth_depth_upperbound)
+    assert_close(ld["expected_depth_loss"].detach().cpu(), cfg.expected_depth_loss_mult * want_e, 1e-4, "expected depth")
+    assert_close(ld["line_of_sight_loss"].detach().cpu(), mult * want_l, 1e-4, "line of sight")
+    sum(ld.values()).backward()
+    assert all(bool(torch.isfinite(p.grad).all()) for p in model.parameters() if p.grad is not None)
+    rb2 = RayBundle(origins=rb.origins, directions=rb.directions, camera_indices=rb.camera_indices,
+                    metadata={VIDEO_ID: host["video_ids"].to(DEV)})
+    out2 = model(rb2)
+    with pytest.raises(KeyError, match="pose_scale_factor"):
+        model.get_loss_dict(out2, batch)
+
+
 @pytest.mark.parametrize("impl,tol", [("b200+fp32", 1e-3), ("b200", 1e-2)])
 def test_c5_prior_query_full_grid(impl, tol):
     """C5: the 400 x 200 x 16 grid of one tile (1.28 M points) through query_priors; the oracle checks a random

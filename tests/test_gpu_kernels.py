@@ -544,6 +544,53 @@ def test_sky_blend_and_render_losses_variants(ops):
     assert float(t[1]) == 0.0 and float(t[2]) == 0.0 and float(t[0]) > 0.0
 
 
+def test_depth_losses_kernel_golden(ops):
+    """ps_depth_losses vs the live reference's fixture (tests/golden/depth_losses.npz, model_components/PreSight/
+    losses.py:28-103): expected mono-depth (normalised / inverse) and LiDAR depth losses with d/d predicted depth, the
+    line-of-sight loss with d/d weights (with and without sky mask); then both terms from ONE launch with the sample
+    mid-points derived from bin edges and a pose scale factor, against the oracle."""
+    from presight_b200 import losses
+    fx = Fixture("depth_losses.npz")
+    depth, sky, steps = fx["depth"].cuda(), fx["sky"].cuda(), fx["steps"].cuda()
+    for name, fn in {"mono": lambda p: losses.expected_monodepth_loss(depth, p, sky, 40.0, False),
+                     "mono_inv": lambda p: losses.expected_monodepth_loss(depth, p, sky, 40.0, True),
+                     "lidar": lambda p: losses.expected_depth_loss(depth, p, 75.0)}.items():
+        pred = fx["pred"].cuda().requires_grad_(True)
+        loss = fn(pred)
+        assert_close(loss.cpu(), fx[f"{name}/loss"], 1e-5, name)
+        loss.backward()
+        assert_close(pred.grad.cpu(), fx[f"{name}/g"], 1e-5, name + " grad")
+    for name, (sigma, use_sky, ub) in {"los_a": (5.0, True, 40.0), "los_b": (2.0, False, 75.0)}.items():
+        w = fx["w"].cuda().requires_grad_(True)
+        loss = losses.line_of_sight_loss(w, depth, steps, sigma, sky if use_sky else None, ub)
+        assert_close(loss.cpu(), fx[f"{name}/loss"], 1e-5, name)
+        loss.backward()
+        assert_close(w.grad.cpu(), fx[f"{name}/g"], 1e-5, name + " grad")
+    # one launch, mid-points from bin edges in scene units (nerfacto_nusc_ms.py:579-586)
+    g = torch.Generator().manual_seed(5)
+    n, S, scale = 1001, 48, 0.05
+    eu = (torch.sort(torch.rand(n, S + 1, generator=g) * 70.0, dim=1).values * scale)
+    wts = (torch.rand(n, S, 1, generator=g) ** 3 * 0.2)
+    tgt = torch.rand(n, 1, generator=g) * 80.0
+    skm = (torch.rand(n, 1, generator=g) < 0.2).float()
+    exp_d = (tgt + torch.randn(n, 1, generator=g) * 3.0).clamp_min(0.01) * scale
+    w_ref, e_ref = wts.clone().requires_grad_(True), exp_d.clone().requires_grad_(True)
+    steps_ref = ((eu[:, :-1] + eu[:, 1:]) / 2 / scale)[..., None]
+    want = [O.expected_monodepth_loss(tgt, e_ref / scale, skm, 40.0, False),
+            O.line_of_sight_loss(w_ref, tgt, steps_ref, 3.5, skm, 40.0)]
+    (want[0] + 0.3 * want[1]).backward()
+    w_gpu, e_gpu = wts.cuda().requires_grad_(True), exp_d.cuda().requires_grad_(True)
+    got = losses.depth_supervision_losses(w_gpu, e_gpu, tgt.cuda(), skm.cuda(), scale, 3.5, 40.0, False, eu_bins=eu.cuda())
+    (got[0] + 0.3 * got[1]).backward()
+    assert_close(got[0].cpu(), want[0].detach(), 1e-5, "expected depth (one launch)")
+    assert_close(got[1].cpu(), want[1].detach(), 1e-5, "line of sight (one launch)")
+    assert_close(e_gpu.grad.cpu(), e_ref.grad, 1e-5, "d expected depth")
+    assert_close(w_gpu.grad.cpu(), w_ref.grad, 1e-5, "d weights")
+    # an empty mask is NaN, as torch's mean over no rays
+    none = losses.expected_depth_loss(torch.zeros(4, 1).cuda(), torch.ones(4, 1).cuda(), 75.0)
+    assert bool(torch.isnan(none))
+
+
 def test_fused_adam_matches_torch_adam(ops):
     """FusedAdam (ps_adam_step) vs torch.optim.Adam — the reference's optimiser — with PreSight's
     hyper-parameters over several steps, on a table-shaped parameter and on small odd-sized ones (tail elements,

@@ -1,8 +1,9 @@
-"""Opt-in kernels that are NOT part of the default path yet.  Skipped unless PS_TEST_EXPERIMENTAL=1.
+"""Both implementations of the z-anti-aliased interlevel loss against the reference fixture, with a C2-sized timing:
 
-  PS_ZAA_WARP=1   warp-per-ray z-anti-aliased interlevel loss (csrc/losses.cu:zaa_interlevel_warp_kernel) — written after
-                  round 1's GPU budget was spent; this is the test to run first when picking it up:
-                      PS_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -m gpu -q
+  PS_ZAA_WARP=1 (default)  warp-per-ray kernel (csrc/losses.cu:zaa_interlevel_warp_kernel)
+  PS_ZAA_WARP=0            thread-per-ray kernel (zaa_interlevel_kernel), the first version
+
+Each runs in its own process because the library reads the switch once.
 """
 import os
 import subprocess
@@ -10,8 +11,7 @@ import sys
 
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PS_TEST_EXPERIMENTAL") != "1", reason="experimental kernels are opt-in")]
+pytestmark = [pytest.mark.gpu]
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

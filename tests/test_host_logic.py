@@ -61,31 +61,6 @@ def test_zeros_like_many_carves_aligned_views():
     assert float(zs[0].sum()) == 0.0 and float(zs[2].sum()) == 0.0               # views do not overlap
 
 
-def test_depth_loss_terms_match_reference_fixture():
-    """The depth-supervision terms of get_loss_dict are still torch expressions; they must reproduce the live
-    reference's fixture exactly like the oracle does."""
-    import os
-    import sys
-    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-    from helpers import Fixture, assert_close
-    from presight_b200 import losses
-    fx = Fixture("depth_losses.npz")
-    depth, sky, steps = fx["depth"], fx["sky"], fx["steps"]
-    pred = fx["pred"].clone().requires_grad_(True)
-    loss = losses.expected_monodepth_loss(depth, pred, sky, 40.0, False)
-    assert_close(loss, fx["mono/loss"], 1e-6, "mono")
-    loss.backward()
-    assert_close(pred.grad, fx["mono/g"], 1e-6, "mono grad")
-    assert_close(losses.expected_monodepth_loss(depth, fx["pred"], sky, 40.0, True), fx["mono_inv/loss"], 1e-6, "mono inverse")
-    assert_close(losses.expected_depth_loss(depth, fx["pred"], 75.0), fx["lidar/loss"], 1e-6, "lidar")
-    w = fx["w"].clone().requires_grad_(True)
-    loss = losses.line_of_sight_loss(w, depth, steps, 5.0, sky, 40.0)
-    assert_close(loss, fx["los_a/loss"], 2e-6, "line of sight")
-    loss.backward()
-    assert_close(w.grad, fx["los_a/g"], 2e-6, "line of sight grad")
-    assert_close(losses.line_of_sight_loss(fx["w"], depth, steps, 2.0, None, 75.0), fx["los_b/loss"], 2e-6, "line of sight b")
-
-
 def test_line_of_sight_schedules():
     from presight_b200.model import NerfactoNuscMSModel
     m = NerfactoNuscMSModel.__new__(NerfactoNuscMSModel)          # schedules only read the config
