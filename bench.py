@@ -203,6 +203,7 @@ def main() -> None:
     ap.add_argument("--strong", action="store_true", help="fixed global batch split across ranks (reference semantics)")
     ap.add_argument("--cpu-sample-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (short runs under ncu)")
     ap.add_argument("--optimizer", default="none", choices=["none", "torch", "fused"],
                     help="also take an Adam step inside the timed step (SURVEY 8f-2; the headline metric excludes it): "
                          "torch.optim.Adam or presight_b200.optim.FusedAdam with PreSight's hyper-parameters")
@@ -339,14 +340,17 @@ def main() -> None:
                 last_ = float(loss_host[(i - 1) % 2])
         loss_ready[(n_steps - 1) % 2].synchronize()
         return float(loss_host[(n_steps - 1) % 2])
-    e2e_loop(2)
-    barrier()
-    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev2.record()
-    last = e2e_loop(args.steps)
-    ev3.record()
-    barrier()
-    t_e2e = ev2.elapsed_time(ev3) / 1e3
+    if args.no_e2e:
+        t_e2e, last = float("nan"), float("nan")
+    else:
+        e2e_loop(2)
+        barrier()
+        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev2.record()
+        last = e2e_loop(args.steps)
+        ev3.record()
+        barrier()
+        t_e2e = ev2.elapsed_time(ev3) / 1e3
     clock_info = clocks.stop()
 
     # ---- the roofline kernel alone: the main-grid scatter on the step's own final-level sample points (same ray slices

@@ -265,6 +265,33 @@ int ps_depth_losses(const float* weights, const float* eu_bins, const float* ste
                     float* g_weights, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Prior post-processing: voxel down-sampling of extracted hit points with per-voxel means, on the GPU.
+ * Replaces scripts/extract_priors.py:156-165 (density > 1 filter), :216-245 (open3d voxel_down_sample_and_trace with
+ * bounds min - 1 / max + 1) and :175-191 (per-voxel hit count, colour mean, fp64 feature mean -> fp16, hit quantile).
+ *
+ * ps_voxel_min_bound: min_out[3] (caller-preset to +inf) = per-axis min over the points with densities > 1
+ *   (densities nullable = all points).  points [N,3] fp32 metres.
+ * ps_voxel_accumulate: adds the selected points to an open-addressing hash table keyed by open3d's voxel index
+ *   floor((p - ((min - 1) - voxel/2)) / voxel) (double arithmetic; min_point [3] on the device, as written by
+ *   ps_voxel_min_bound): keys [capacity] int64 preset to -1, counts [capacity] u32, sum_xyz / sum_col [capacity,3] and
+ *   sum_feat [capacity,C] fp64, all caller-zeroed; capacity a power of two.  features_f16 [N,C] / colors [N,3] nullable
+ *   together with their accumulators.  May be called repeatedly (streaming) with the same min_point.
+ *   status |= 1 table full, |= 2 voxel index outside 21 bits per axis (checked by the caller after a sync).
+ * ps_voxel_finalize: occupied slots -> rows 0..*n_out-1 (caller-zeroed counter; row order arbitrary): out_keys (packed
+ *   ix<<42 | iy<<21 | iz), out_xyz [.,3] = centre of mass, out_col [.,3], out_feat_f16 [.,C], out_hits.
+ * ps_hits_quantile: out[0] = np.quantile(hits[0..M), q) (linear interpolation); hist [bins] u32 caller-zeroed scratch,
+ *   bins > max(hits) (status |= 4 otherwise). */
+int ps_voxel_min_bound(const float* points, const float* densities, int64_t N, float* min_out, void* stream);
+int ps_voxel_accumulate(const float* points, const void* features_f16, const float* colors, const float* densities,
+                        int64_t N, int C, const float* min_point, double voxel_size, int64_t* keys, int64_t capacity,
+                        uint32_t* counts, double* sum_xyz, double* sum_col, double* sum_feat, int* status, void* stream);
+int ps_voxel_finalize(const int64_t* keys, int64_t capacity, const uint32_t* counts, const double* sum_xyz,
+                      const double* sum_col, const double* sum_feat, int C, uint64_t* n_out, int64_t* out_keys,
+                      float* out_xyz, float* out_col, void* out_feat_f16, int64_t* out_hits, void* stream);
+int ps_hits_quantile(const int64_t* hits, int64_t M, double q, uint32_t* hist, int64_t bins, double* out, int* status,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Ray generation: RayGenerator.forward + Cameras.generate_rays for PERSPECTIVE cameras without distortion
  * (model_components/ray_generators.py:43-61, cameras/cameras.py:497-880).
  *   c2w [C,3,4], fx / fy / cx / cy [C] fp32; ray_indices [N,3] int64 = (camera, row, col); pixel_offset = 0.5

@@ -59,6 +59,10 @@ SIGNATURES = {
     "ps_sky_blend_bwd": [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p],
     "ps_render_losses": [_p, _p, _p, _p, _p, _p, _i64, _i, _f, _p, _p, _p, _p, _p],
     "ps_depth_losses": [_p, _p, _p, _p, _p, _p, _i64, _i, _f, _p, _f, _f, _i, _p, _p, _p, _p],
+    "ps_voxel_min_bound": [_p, _p, _i64, _p, _p],
+    "ps_voxel_accumulate": [_p, _p, _p, _p, _i64, _i, _p, C.c_double, _p, _i64, _p, _p, _p, _p, _p, _p],
+    "ps_voxel_finalize": [_p, _i64, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p],
+    "ps_hits_quantile": [_p, _i64, C.c_double, _p, _i64, _p, _p, _p],
     "ps_generate_rays": [_p, _p, _p, _p, _p, _i, _p, _i64, _f, _p, _p, _p, _p, _p],
     "ps_adam_step": [_p, _p, _p, _p, _i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _i64, _p],
     "ps_tc5_probe": [_p, _p, _p, _p, _p, _p, _p, _p],

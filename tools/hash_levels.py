@@ -17,6 +17,9 @@ def main():
     ap.add_argument("--samples", type=int, default=64)
     ap.add_argument("--log2T", type=int, default=22)
     ap.add_argument("--F", type=int, default=2)
+    ap.add_argument("--sort-res", type=int, default=0,
+                    help="process the points in Morton order of a grid of this resolution (power of two) instead of ray "
+                         "order: what a cell-sorted scatter of the coarse levels would see")
     args = ap.parse_args()
     dev, n, S, F, log2T = "cuda", args.rays, args.samples, args.F, args.log2T
     rays = synthetic.make_rays(n, seed=1)
@@ -27,6 +30,15 @@ def main():
     aabb = [float(v) for v in synthetic.tile_aabb().reshape(-1)]
     x01, sel = fused._ray_points(o, d, eu.contiguous(), aabb, True)
     P = x01.shape[0]
+    if args.sort_res:
+        R = args.sort_res
+        q = (x01.clamp(0, 1) * R).long().clamp_(0, R - 1)
+        key = torch.zeros(P, dtype=torch.long, device=dev)
+        for b in range(R.bit_length() - 1):
+            for a in range(3):
+                key |= ((q[:, a] >> b) & 1) << (3 * b + a)
+        x01 = x01[torch.argsort(key)].contiguous()
+        print(f"points in Morton order of a {R}^3 grid")
     L = 16
     g = np.exp((np.log(2048) - np.log(16)) / (L - 1))
     scal = [float(np.floor(16 * g ** l)) for l in range(L)]
