@@ -35,6 +35,20 @@ UNIT = "rays/s"
 
 
 # ------------------------------------------------------------------------------------------------ helpers
+def roofline_traffic(kernel: str, config: str, rays: int) -> dict:
+    """{"traffic": dram bytes per launch of `kernel` or None, "traffic_source": ...} from profiles/roofline_traffic.json
+    (written from an `ncu --set full` capture of this command)."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        if t.get("kernel") == kernel and t.get("config") == config and int(t.get("rays_per_gpu", -1)) == rays:
+            return {"traffic": float(t["dram_bytes_per_launch"]), "traffic_source": t.get("source")}
+    except Exception:
+        pass
+    return {"traffic": None, "traffic_source": None}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -80,13 +94,86 @@ class ClockSampler(threading.Thread):
 
 def build_config(name: str, impl: str):
     from presight_b200 import synthetic
-    return {"c1": synthetic.config_c1, "c2": synthetic.config_c2}[name](impl)
+    return {"c1": synthetic.config_c1, "c3": synthetic.config_c1, "c2": synthetic.config_c2, "c5": synthetic.config_c2,
+            "presight": synthetic.config_presight}[name](impl)
 
 
 def workload_name(name: str) -> str:
     return {"c2": "PreSight city NeRF train step: 16-level 2^22-entry hash grid F2 + props L8 F1 2^20 (128/64/64 "
                   "samples), 6-cam nuScenes-shaped rays",
-            "c1": "nerfacto-style hash-grid field: main L16 F2 2^19 + props L5 F2 2^17 (256/96/48 samples)"}[name]
+            "c1": "nerfacto-style hash-grid field: main L16 F2 2^19 + props L5 F2 2^17 (256/96/48 samples)",
+            "c3": "proposal-heavy sampling: nerfacto-style field, 2 proposal nets (256/96) + 48 NeRF samples/ray",
+            "c5": "prior extraction: dense density/feature query on a 400x200x16 BEV voxel grid per tile (C2 model), "
+                  "tiles sharded over the GPUs, no communication",
+            "presight": "PreSight shipped shape: 16 sub-fields (nearest-centroid routing), main L10 F4 2^20 16->16384 each "
+                        "+ props L8 F1 2^20 (128/64/64 samples), 6-cam nuScenes-shaped rays"}[name]
+
+
+def build_model(config_name: str, cfg, host, dev):
+    """Random-init model of the named configuration (16 routed sub-fields for `presight`, one otherwise)."""
+    from presight_b200 import synthetic
+    from presight_b200.model import NerfactoNuscMSModel
+    if config_name == "presight":
+        centroids, aabbs = synthetic.sub_field_layout(16)
+    else:
+        centroids, aabbs = torch.zeros(1, 3), synthetic.tile_aabb()
+    return NerfactoNuscMSModel(cfg, centroids, aabbs, host["n_cameras"], host["n_videos"]).to(dev)
+
+
+# ------------------------------------------------------------------------------------------------ C5: prior query
+def time_prior_query(model, dev, rank, world, iters, tiles_total=8, with_e2e=True):
+    """BASELINE config 5: `model.query_priors` on the 400x200x16 grid of each of this rank's tiles (8 tiles, sharded by
+    tile with no communication — extract_priors.py:151-154 concatenates on the host).  -> dict with device-resident and
+    host-buffer (points copied in from pinned memory, densities + fp16 features copied out) timings, max over ranks."""
+    from presight_b200 import synthetic
+    from presight_b200.parallel import shard_range
+    lo, hi = shard_range(tiles_total, rank, world)
+    if world > tiles_total:
+        lo, hi = rank % tiles_total, rank % tiles_total + 1
+    host_grids = [synthetic.prior_tile_grid(t).pin_memory() for t in range(lo, hi)]
+    grids = [g.to(dev, non_blocking=True) for g in host_grids]
+    M = host_grids[0].shape[0]
+    for g in grids:
+        model.query_priors(g)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        for g in grids:
+            model.query_priors(g)
+    b.record()
+    torch.cuda.synchronize()
+    t_dev = a.elapsed_time(b) / 1e3
+    t_e2e = float("nan")
+    if with_e2e:
+        out_mean = torch.empty(M, dtype=torch.float32).pin_memory()
+        out_feat = torch.empty(M, 64, dtype=torch.float16).pin_memory()
+        if world > 1:
+            dist.barrier()
+        a.record()
+        for _ in range(iters):
+            for hg in host_grids:
+                mean, feats = model.query_priors(hg.to(dev, non_blocking=True))
+                out_mean.copy_(mean, non_blocking=True)
+                out_feat.copy_(feats, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize()
+        t_e2e = a.elapsed_time(b) / 1e3
+    if world > 1:
+        tt = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(tt[0]), float(tt[1])
+    n_tiles = max(1, hi - lo)
+    pts = M * n_tiles * iters * world
+    faithful, elided = synthetic.prior_query_bytes_per_point(model.config)
+    return {"points_per_s": pts / t_dev, "e2e_points_per_s": pts / t_e2e, "points_per_tile": M, "tiles": n_tiles * world,
+            "ms_per_tile": t_dev / (iters * n_tiles) * 1e3, "e2e_ms_per_tile": t_e2e / (iters * n_tiles) * 1e3,
+            "h2d_bytes_per_tile": M * 12, "d2h_bytes_per_tile": M * (4 + 128),
+            "algorithmic_bytes_per_point": {"reference_count": faithful, "duplicate_encode_elided": elided},
+            "GBps_per_gpu_reference_count": faithful * pts / t_dev / 1e9 / world,
+            "GBps_per_gpu_elided_count": elided * pts / t_dev / 1e9 / world}
 
 
 # ------------------------------------------------------------------------------------------------ loss
@@ -171,6 +258,76 @@ def time_cpu_reference(model, cfg, batch, sample_rays, steps, warmup):
     return sample_rays / statistics.median(ts), statistics.median(ts)
 
 
+def cpu_hash_only(cfg, n_points=1 << 16):
+    """The figure BASELINE.md §3 promises beside the step: the reference-style torch HashEncoding (oracle port of
+    encodings.py:343-384, main grid) forward + backward alone on the host cores -> points/s."""
+    import oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    grid = O.HashGrid(table=((torch.rand((cfg.num_levels << cfg.log2_hashmap_size), cfg.features_per_level) * 2 - 1)
+                             * 1e-3).requires_grad_(True),
+                      scalings=O.hash_scalings(cfg.num_levels, cfg.base_res, cfg.max_res), log2_T=cfg.log2_hashmap_size)
+    x = torch.rand(n_points, 3)
+    ts = []
+    for _ in range(3):
+        grid.table.grad = None
+        t0 = time.perf_counter()
+        O.hash_encode(x, grid).sum().backward()
+        ts.append(time.perf_counter() - t0)
+    return n_points / statistics.median(ts)
+
+
+def main_c5(args, model, cfg, host, dev, rank, world):
+    """`--config c5`: the prior query as the benchmarked step (one step = one tile's 1.28 M-point query)."""
+    from presight_b200 import ops, synthetic
+    model.eval()
+    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    clocks.start()
+    ops.PROBE = ops.KernelProbe()
+    l0 = ops.launch_count()
+    r = time_prior_query(model, dev, rank, world, max(args.steps, 1))
+    launches = ops.launch_count() - l0
+    probe = ops.PROBE.summary()
+    ops.PROBE = None
+    clock_info = clocks.stop()
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        L, F = cfg.num_levels, cfg.features_per_level
+        kname = f"hash_fwd_L{L}F{F}T{cfg.log2_hashmap_size}"
+        n_launch, k_mean = probe.get(kname, (0, float("nan")))
+        algo = synthetic.hash_bytes_fwd(L, F) * r["points_per_tile"]
+        line = {"metric": "prior_query_points_per_s", "value": r["points_per_s"], "unit": "points/s", "n_gpus": world,
+                "steps": args.steps, "warmup": 1, "ms_per_step": r["ms_per_tile"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 hash + bf16 MLP, fp16 features", "data": "synthetic",
+                "config": {"workload": workload_name("c5"), "points_per_tile": r["points_per_tile"], "tiles": r["tiles"],
+                           "parallelism": f"tiles sharded over {world} GPU(s), no communication",
+                           "l2": "inputs larger than L2 (576 MiB of hash tables)"},
+                "e2e": {"value": r["e2e_points_per_s"], "unit": "points/s", "h2d_bytes_per_step": r["h2d_bytes_per_tile"],
+                        "d2h_bytes_per_step": r["d2h_bytes_per_tile"], "ms_per_step": r["e2e_ms_per_tile"]},
+                "gpu_launches": int(launches), "clocks": clock_info,
+                "roofline": {"bound": "hbm", "kernel": kname, "achieved": algo / (k_mean * 1e-3) / 1e9 if n_launch else None,
+                             "peak": peak, "unit": "GB/s",
+                             "frac": algo / (k_mean * 1e-3) / 1e9 / peak if n_launch else None, "traffic": None,
+                             "peak_source": peak_src, "kernel_ms": k_mean,
+                             "step_GBps_reference_count": r["GBps_per_gpu_reference_count"],
+                             "step_GBps_elided_count": r["GBps_per_gpu_elided_count"],
+                             "step_frac_of_hbm_roofline_reference_count": r["GBps_per_gpu_reference_count"] / peak},
+                "kernels_ms_per_launch": {k: round(v[1], 4) for k, v in sorted(probe.items())}}
+        if world == 1 and not args.no_cpu_baseline:
+            import oracle as O
+            torch.set_num_threads(os.cpu_count() or 1)
+            om, _ = oracle_model_from(model, cfg)
+            n = 16384
+            pts = synthetic.prior_tile_grid(0)[:n]
+            t0 = time.perf_counter()
+            O.prior_query(om, pts)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": n / dt, "unit": "points/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": f"{n} points of tile 0, oracle port of extract_priors.py:130-138 (torch CPU fp32)"}
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------ main
 _REAL_STDOUT = None
 
@@ -197,7 +354,12 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="c2", choices=["c1", "c2"])
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c5", "presight"],
+                    help="c2 = the headline workload (BASELINE config 2 / 4); c1 / c3 = nerfacto-style shapes (config 1 / 3); "
+                         "c5 = prior query per tile; presight = the shipped 16-sub-field shape")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="default c2 run only: skip the short extra measurements folded into the line "
+                         "(C5 prior query per tile, strong-scaling step for N > 1)")
     ap.add_argument("--rays", type=int, default=65536, help="rays per GPU (weak scaling) or global (--strong)")
     ap.add_argument("--fp32", action="store_true", help="3xTF32 MLPs (1e-3 parity class) instead of bf16")
     ap.add_argument("--strong", action="store_true", help="fixed global batch split across ranks (reference semantics)")
@@ -254,7 +416,9 @@ def main() -> None:
     rays_per_rank = args.rays // world if args.strong else args.rays
     torch.manual_seed(42)                                        # identical weights on every rank
     host = synthetic.make_rays(rays_per_rank, seed=42 + rank)    # reference seeds data with seed + rank (train.py:99)
-    model = NerfactoNuscMSModel(cfg, torch.zeros(1, 3), synthetic.tile_aabb(), host["n_cameras"], host["n_videos"]).to(dev)
+    model = build_model(args.config, cfg, host, dev)
+    if args.config == "c5":
+        return main_c5(args, model, cfg, host, dev, rank, world)
     model.train()
     params = [p for p in model.parameters() if p.requires_grad]
     sync = GradSynchronizer(params, overlap=True) if world > 1 else None
@@ -390,6 +554,36 @@ def main() -> None:
         alone_ms = ea.elapsed_time(eb) / 5
         del dfeat, dtab, x01
 
+    # ---- extras folded into the default line (short; all ranks take part): the strong-scaling variant of the step — the
+    # reference's semantics, train_num_rays_per_batch // world_size per rank (my_datamanager.py:206) — and BASELINE
+    # config 5, the prior query per tile with tiles sharded over the ranks
+    extras = {}
+    if args.config == "c2" and not args.no_extras and optimizer is None:
+        if world > 1 and not args.strong:
+            n_s = args.rays // world
+            hs = synthetic.make_rays(n_s, seed=1042 + rank)
+            res_s = {k: hs[k].to(dev) for k in tensor_keys}
+            for _ in range(3):
+                run_step(res_s)
+            barrier()
+            es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k_s = max(5, min(args.steps, 20))
+            es0.record()
+            for _ in range(k_s):
+                run_step(res_s)
+            es1.record()
+            barrier()
+            ts = torch.tensor([es0.elapsed_time(es1) / 1e3], device=dev, dtype=torch.float64)
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            extras["strong"] = {"metric": METRIC, "value": n_s * world * k_s / float(ts), "unit": UNIT,
+                                "global_rays": n_s * world, "rays_per_gpu": n_s, "ms_per_step": float(ts) / k_s * 1e3,
+                                "steps": k_s, "scaling": "strong"}
+            del res_s
+        model.eval()
+        c5 = time_prior_query(model, dev, rank, world, 5)
+        model.train()
+        extras["c5_prior_query"] = c5
+
     if world > 1:
         t = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -427,9 +621,10 @@ def main() -> None:
             "clocks": clock_info,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
-                         # dram__bytes_read + write of ONE slice launch (21 846 rays) from the ncu --set full capture
-                         # profiles/r1_final_kernels_ncu_summary.jsonl (475.2 MB + 192.1 MB); valid for the default C2 run
-                         "traffic": 667.3e6 if (args.config == "c2" and rays_per_rank == 65536) else None,
+                         # dram__bytes_read + write of ONE launch of this kernel from the ncu --set full capture of this
+                         # same command, kept in profiles/roofline_traffic.json with its source file (null when the
+                         # run's shape is not the captured one)
+                         **roofline_traffic(kname, args.config, rays_per_rank),
                          "peak_source": peak_src,
                          "kernel_ms": k_ms, "launches_per_step": (n_launch / args.steps) if n_launch else None,
                          "algorithmic_bytes_per_launch": algo_bytes / max(1.0, n_launch / args.steps) if n_launch else None,
@@ -442,13 +637,18 @@ def main() -> None:
             "kernels_ms_per_step": {k: round(v[0] * v[1] / args.steps, 4) for k, v in sorted(probe.items())},
             "loss": last,
         }
+        if extras:
+            line["extras"] = extras
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n = args.cpu_sample_rays
             rps, med = time_cpu_reference(model, cfg, host, n, 3, 1)
             line["cpu_baseline"] = {"value": rps, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{n} rays/step of the same workload and weights, torch CPU fp32, "
-                                              f"{cores} threads, median of 3 steps ({med:.2f} s/step)"}
+                                    "sample": f"{n} rays/step of the same workload ({args.config}) and weights: the oracle "
+                                              f"port of the reference's torch path (the reference modules themselves "
+                                              f"cannot travel to this box), torch CPU fp32, {cores} threads, median of 3 "
+                                              f"steps ({med:.2f} s/step)",
+                                    "hash_only_points_per_s": cpu_hash_only(cfg)}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -93,6 +93,51 @@ def config_c2(implementation: str = "b200") -> NerfactoNuscMSModelConfig:
         sky_mlp_dims=32, implementation=implementation)
 
 
+def config_presight(implementation: str = "b200") -> NerfactoNuscMSModelConfig:
+    """PreSight's shipped shape (configs/method_configs.py:87-141 = the model's defaults): main L10 F4 T2^20 16->16384 per
+    sub-field, props L8 F1 T2^20 hidden 64 (16->1024 / 16->4096), samples 128/64/64, 64-d semantics, sky model; used with
+    16 sub-fields (`num_aabbs=16`), see `sub_field_layout`."""
+    return _common(implementation=implementation)
+
+
+def sub_field_layout(n_fields: int = 16) -> Tuple[torch.Tensor, torch.Tensor]:
+    """-> (centroids [nf,3], aabbs [nf,2,3]) in scene units: sub-fields on a sqrt(nf) x sqrt(nf) lattice over the 400 m
+    tile — what the dataparser's k-means over camera positions gives for a uniformly driven tile
+    (mynuscenes_ms_dataparser.py:230-271: a box around each cluster's cameras with a 15 m margin, -5..+15 m in z)."""
+    k = int(round(math.sqrt(n_fields)))
+    assert k * k == n_fields, "sub-field count must be a square"
+    cell = 400.0 / k
+    cx = (torch.arange(k, dtype=torch.float32) + 0.5) * cell - 200.0
+    cen = torch.stack(torch.meshgrid(cx, cx, indexing="ij"), dim=-1).reshape(-1, 2)
+    centroids = torch.cat([cen, torch.full((n_fields, 1), 1.5)], dim=-1)
+    half = cell / 2 + 15.0
+    lo = torch.cat([cen - half, torch.full((n_fields, 1), -5.0)], dim=-1)
+    hi = torch.cat([cen + half, torch.full((n_fields, 1), 15.0)], dim=-1)
+    return centroids * POSE_SCALE, torch.stack([lo, hi], dim=1) * POSE_SCALE
+
+
+def prior_tile_grid(tile_index: int) -> torch.Tensor:
+    """C5: 400 x 200 x 16 voxel centres = 100 m x 50 m x 8 m at 0.25 / 0.25 / 0.5 m around a tile-specific centre, world
+    metres x pose scale -> [1 280 000, 3] on the host."""
+    g = torch.Generator().manual_seed(tile_index)
+    centre = (torch.rand(2, generator=g) - 0.5) * 300.0
+    xs = torch.arange(400, dtype=torch.float32) * 0.25 - 50.0 + centre[0]
+    ys = torch.arange(200, dtype=torch.float32) * 0.25 - 25.0 + centre[1]
+    zs = torch.arange(16, dtype=torch.float32) * 0.5 - 2.0
+    pts = torch.stack(torch.meshgrid(xs, ys, zs, indexing="ij"), dim=-1).reshape(-1, 3)
+    return pts * POSE_SCALE
+
+
+def prior_query_bytes_per_point(cfg: NerfactoNuscMSModelConfig) -> Tuple[int, int]:
+    """(reference-faithful, duplicate-main-encode-elided) algorithmic bytes per queried point."""
+    props = 0
+    for i in range(cfg.num_proposal_iterations):
+        a = cfg.proposal_net_args_list[min(i, len(cfg.proposal_net_args_list) - 1)]
+        props += hash_bytes_fwd(a["num_levels"], a["features_per_level"])
+    main = hash_bytes_fwd(cfg.num_levels, cfg.features_per_level)
+    return 2 * main + props + 4 + 128, main + props + 4 + 128
+
+
 # algorithmic bytes (SURVEY §8d): hash fwd = 12 + 8LF*4 + LF*4, bwd = 12 + LF*4 + 2*8LF*4 per point
 def hash_bytes_fwd(L: int, F: int) -> int:
     return 12 + 8 * L * F * 4 + L * F * 4
