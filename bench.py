@@ -422,6 +422,11 @@ def main() -> None:
     model.train()
     params = [p for p in model.parameters() if p.requires_grad]
     sync = GradSynchronizer(params, overlap=True) if world > 1 else None
+    if world > 1:
+        # the 512 MiB main-table all-reduce hides under the proposal levels' backward only if that runs AFTER the final
+        # level (main stream) instead of early on the single-GPU side stream
+        from presight_b200 import fused
+        fused.set_overlap_prop_bwd(False)
     optimizer = None
     if args.optimizer == "torch":
         optimizer = torch.optim.Adam(params, lr=1e-2, eps=1e-15, weight_decay=1e-5)

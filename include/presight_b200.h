@@ -304,7 +304,7 @@ int ps_generate_rays(const float* c2w, const float* fx, const float* fy, const f
  * Fused Adam step: torch.optim.Adam without amsgrad as PreSight configures it
  * (configs/method_configs.py:115: lr 1e-2, eps 1e-15, weight_decay 1e-5; engine/optimizers.py:133-140), one pass.
  *   param / exp_avg / exp_avg_sq [n] fp32 updated in place, grad [n] read; step = 1 for the first update;
- *   all four buffers 16-byte aligned; hyper-parameters as doubles (torch keeps them as Python floats and derives the
+ *   16-byte aligned buffers take the float4 path, anything else an element-wise one; hyper-parameters as doubles (torch keeps them as Python floats and derives the
  *   bias corrections in double precision). */
 int ps_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
                  double beta2, double eps, double weight_decay, int64_t step, void* stream);

@@ -29,6 +29,7 @@ class RayGenerator(nn.Module):
                 raise ValueError(f"{name} must have one entry per camera")
             self.register_buffer(name, t.contiguous().clone(), persistent=False)
         self.pixel_offset = float(pixel_offset)
+        self.validate_indices = True
 
     def forward(self, ray_indices: Tensor, camera_opt_to_camera: Optional[Tensor] = None) -> RayBundle:
         """ray_indices [N,3] int64 = (camera, row, col) -> RayBundle (origins, unit directions, pixel_area [N,1],
@@ -38,6 +39,12 @@ class RayGenerator(nn.Module):
         assert ray_indices.dim() == 2 and ray_indices.shape[1] == 3, "ray_indices must be [N,3]"
         idx = ray_indices.to(torch.int64).contiguous()
         N, dev = idx.shape[0], self.camera_to_worlds.device
+        if self.validate_indices and N:
+            # the reference's gather raises on a bad camera index; the kernel cannot, so check on the device (an
+            # asynchronous assert: no host sync, the error surfaces at the next synchronisation)
+            cam = idx[:, 0]
+            torch._assert_async(((cam >= 0) & (cam < self.camera_to_worlds.shape[0])).all(),
+                                "RayGenerator: camera index out of range")
         origins = torch.empty(N, 3, device=dev, dtype=torch.float32)
         directions = torch.empty(N, 3, device=dev, dtype=torch.float32)
         pixel_area = torch.empty(N, 1, device=dev, dtype=torch.float32)

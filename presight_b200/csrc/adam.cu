@@ -9,11 +9,12 @@
 
 namespace ps {
 
+template <bool VEC>
 __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                         adam::Scalars s) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t n4 = n >> 2;
+    const int64_t n4 = VEC ? (n >> 2) : 0;          // VEC = false: buffers not 16-byte aligned (views at odd offsets)
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i],
                vv = reinterpret_cast<float4*>(v)[i];
@@ -39,8 +40,7 @@ extern "C" int ps_adam_step(float* param, const float* grad, float* exp_avg, flo
     if (n == 0) return 0;
     PS_REQUIRE(param && grad && exp_avg && exp_avg_sq, "adam_step: null pointer");
     PS_REQUIRE(step >= 1, "adam_step: step must be >= 1 (it counts the update being made)");
-    PS_REQUIRE(((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16 == 0,
-               "adam_step: buffers must be 16-byte aligned");
+    const bool vec = ((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16 == 0;
     // the scalars in double precision, as torch computes them (optim/adam.py, _single_tensor_adam)
     // (hyper-parameters arrive as doubles — torch holds them as Python floats; 1 - float(0.999) is off by 1.3e-5)
     const double bias1 = 1.0 - pow(beta1, (double)step), bias2 = 1.0 - pow(beta2, (double)step);
@@ -56,6 +56,7 @@ extern "C" int ps_adam_step(float* param, const float* grad, float* exp_avg, flo
     int64_t blocks = cdiv(work, 256);
     const int64_t cap = (int64_t)kNumSMs * 16;
     if (blocks > cap) blocks = cap;
-    adam_step_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, s);
+    if (vec) adam_step_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, s);
+    else adam_step_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, s);
     return check_launch("adam_step");
 }

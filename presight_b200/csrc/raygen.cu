@@ -23,7 +23,9 @@ __global__ void __launch_bounds__(256) generate_rays_kernel(const float* __restr
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     int64_t cam = ray_indices[3 * n];
-    cam = cam < 0 ? 0 : (cam >= C ? C - 1 : cam);            // indices are validated on the host; never read out of range
+    // the caller checks the camera indices (RayGenerator.forward: a device-side assert, where the reference's gather
+    // raises); the clamp only keeps a bad index from reading out of range before that assert is observed
+    cam = cam < 0 ? 0 : (cam >= C ? C - 1 : cam);
     float m[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) m[i] = __ldg(c2w + cam * 12 + i);

@@ -28,6 +28,16 @@ _f32c = ops._f32c
 USE_TC5_FIELD = os.environ.get("PS_TC5_FIELD", "1") == "1"
 USE_TC5_PROP = os.environ.get("PS_TC5_PROP", "1") == "1"
 OVERLAP_PROP_BWD = os.environ.get("PS_OVERLAP_PROP_BWD", "1") == "1"
+
+
+def set_overlap_prop_bwd(on: bool) -> bool:
+    """Scheduling policy of the proposal levels' backward: True = early, on a side stream beside the final level's
+    kernels (single GPU); False = on the main stream behind them (what a data-parallel run wants, so that the main
+    table's all-reduce has compute to hide under).  The caller decides (bench.py does, per world size); nothing in
+    the library flips it behind the caller's back.  -> the previous value."""
+    global OVERLAP_PROP_BWD
+    prev, OVERLAP_PROP_BWD = OVERLAP_PROP_BWD, bool(on)
+    return prev
 FIELD_CHUNKS = max(1, int(os.environ.get("PS_FIELD_CHUNKS", "3")))
 
 
@@ -162,8 +172,9 @@ def tc5_prop_supported(grid: GridMeta, net: MlpMeta, prec, S: int) -> bool:
 
 class _PropLevelTc5(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, origins, dirs, eu_bins, table, aabb, contract, grid: GridMeta, w0, b0, w1, b1):
+    def forward(ctx, origins, dirs, eu_bins, table, aabb, contract, grid: GridMeta, grad_key, w0, b0, w1, b1):
         import ctypes as C
+        ctx.grad_key = grad_key
         from ._lib import host_prop_net, load
         o, d, eu = _f32c(origins.detach()), _f32c(dirs.detach()), _f32c(eu_bins.detach())
         N, S = eu.shape[0], eu.shape[1] - 1
@@ -191,7 +202,7 @@ class _PropLevelTc5(torch.autograd.Function):
         # The proposal levels' gradients depend only on the interlevel loss, not on the final level's backward: when
         # the producer of `dw` published its completion event, run this backward on a side stream so that it overlaps
         # the field kernels / main hash scatter already queued on the main stream.
-        ev_in = ops.pop_grad_event(dw) if OVERLAP_PROP_BWD else None
+        ev_in = ops.pop_grad_event(dw, ctx.grad_key) if OVERLAP_PROP_BWD else None
         run_on = ops.side_stream(eu.device, 1) if ev_in is not None else main
         with torch.cuda.stream(run_on):
             if ev_in is not None:
@@ -215,14 +226,19 @@ class _PropLevelTc5(torch.autograd.Function):
             # for a later main-stream event.  No Tensor.record_stream: its deferred frees make the caching allocator fall
             # back to cudaMalloc (a device-wide sync) whenever the host runs several steps ahead of the GPU.
             main.wait_event(done)
-        return (None, None, None, dtable, None, None, None, dws[0], dbs[0], dws[1], dbs[1])
+        return (None, None, None, dtable, None, None, None, None, dws[0], dbs[0], dws[1], dbs[1])
 
 
 def prop_level_weights(origins, dirs, eu_bins, table, aabb, contract, grid: GridMeta, net: MlpMeta, prec,
                        weights: Sequence[Tensor], biases: Sequence[Tensor]) -> Tensor:
     if USE_TC5_PROP and tc5_prop_supported(grid, net, prec, eu_bins.shape[1] - 1) and all(b is not None for b in biases):
-        return _PropLevelTc5.apply(origins, dirs, eu_bins, table, aabb, contract, grid, weights[0], biases[0], weights[1],
-                                   biases[1])
+        # hand-off key: a loss that consumes this tensor publishes its gradient's completion event under it (ops.py)
+        key = ops.new_grad_key() if (OVERLAP_PROP_BWD and torch.is_grad_enabled()) else None
+        out = _PropLevelTc5.apply(origins, dirs, eu_bins, table, aabb, contract, grid, key, weights[0], biases[0],
+                                  weights[1], biases[1])
+        if key is not None:
+            out._ps_grad_key = key
+        return out
     return _PropLevel.apply(origins, dirs, eu_bins, table, aabb, contract, grid, net, prec, *weights, *biases)
 
 

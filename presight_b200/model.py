@@ -44,6 +44,9 @@ class NerfactoNuscMSModelConfig:
     num_nerf_samples_per_ray: int = 64
     proposal_update_every: int = 5
     proposal_warmup: int = 1000
+    use_proposal_weight_anneal: bool = True
+    proposal_weights_anneal_slope: float = 10.0
+    proposal_weights_anneal_max_num_iters: int = 1000
     num_proposal_iterations: int = 2
     use_same_proposal_network: bool = False
     proposal_net_args_list: List[Dict] = field(
@@ -86,6 +89,28 @@ class NerfactoNuscMSModelConfig:
     line_of_sight_end_step: int = 30000
     line_of_sight_max_sigma: float = 5.0
     line_of_sight_min_sigma: float = 2.0
+
+
+class TrainingCallbackLocation:
+    """engine/callbacks.py:48-53."""
+    BEFORE_TRAIN_ITERATION = "BEFORE_TRAIN_ITERATION"
+    AFTER_TRAIN_ITERATION = "AFTER_TRAIN_ITERATION"
+
+
+class TrainingCallback:
+    """The subset of engine/callbacks.py:56-117 the model's callbacks use: `func(step=...)` every
+    `update_every_num_iters` iterations at the listed locations."""
+
+    def __init__(self, where_to_run, func, update_every_num_iters: Optional[int] = 1) -> None:
+        self.where_to_run, self.func, self.update_every_num_iters = list(where_to_run), func, update_every_num_iters
+
+    def run_callback(self, step: int) -> None:
+        if self.update_every_num_iters is None or step % self.update_every_num_iters == 0:
+            self.func(step=step)
+
+    def run_callback_at_location(self, step: int, location) -> None:
+        if location in self.where_to_run:
+            self.run_callback(step=step)
 
 
 class _EmbeddingLookup(torch.autograd.Function):
@@ -190,6 +215,11 @@ class NerfactoNuscMSModel(nn.Module):
             num_proposal_network_iterations=c.num_proposal_iterations, single_jitter=c.use_single_jitter,
             update_sched=update_schedule, initial_sampler=initial_sampler)
         self.collider = NearFarCollider(near_plane=c.near_plane, far_plane=c.far_plane)
+        if c.background_color not in ("black", "last_sample"):
+            # the fused final level composites onto black and `get_loss_dict` does not blend a background into the
+            # targets (renderers.py:174-197); PreSight's configs all use black.  ("last_sample" equals black for the loss.)
+            raise NotImplementedError(f"background_color={c.background_color!r}: the model driver renders onto black only "
+                                      "(use RGBRenderer directly for white / random backgrounds)")
         self.renderer_rgb = RGBRenderer(background_color=c.background_color)
         self.renderer_accumulation = AccumulationRenderer()
         self.renderer_depth = DepthRenderer(method="threshold")
@@ -212,6 +242,28 @@ class NerfactoNuscMSModel(nn.Module):
             if hasattr(self, name):
                 groups["fields"] += list(getattr(self, name).parameters())
         return groups
+
+    def set_step(self, step: int) -> None:
+        """What the reference's BEFORE_TRAIN_ITERATION callback does (nerfacto_nusc_ms.py:425-434): remember the step (it
+        drives the line-of-sight schedules) and anneal the proposal weights (mip-NeRF 360 eq. 18)."""
+        c = self.config
+        self.step = int(step)
+        if c.use_proposal_weight_anneal:
+            train_frac = float(np.clip(step / c.proposal_weights_anneal_max_num_iters, 0, 1))
+            b = c.proposal_weights_anneal_slope
+            self.proposal_sampler.set_anneal(b * train_frac / ((b - 1) * train_frac + 1))
+
+    def get_training_callbacks(self, training_callback_attributes=None) -> List[TrainingCallback]:
+        """nerfacto_nusc_ms.py:405-450: with proposal-weight annealing on (the default) the trainer must run `set_step`
+        before and `proposal_sampler.step_cb` after every iteration — the latter drives the proposal networks' update
+        schedule; without these calls every step is an "update" step with anneal 1 and frozen line-of-sight schedules."""
+        callbacks: List[TrainingCallback] = []
+        if self.config.use_proposal_weight_anneal:
+            callbacks.append(TrainingCallback([TrainingCallbackLocation.BEFORE_TRAIN_ITERATION],
+                                              lambda step: self.set_step(step), 1))
+            callbacks.append(TrainingCallback([TrainingCallbackLocation.AFTER_TRAIN_ITERATION],
+                                              lambda step: self.proposal_sampler.step_cb(step), 1))
+        return callbacks
 
     # ------------------------------------------------------------------------------------------
     def _appearance(self, ray_samples: RaySamples) -> Optional[Tensor]:
@@ -252,6 +304,7 @@ class NerfactoNuscMSModel(nn.Module):
                     appearance: Optional[Tensor] = None) -> Dict[str, object]:
         """nerfacto_nusc_ms.py:452-546.  `jitters` (per-level [N,1] uniforms) and `appearance` ([N,A], already
         looked-up embeddings) are optional injection points so parity runs can share randomness and inputs."""
+        ops.clear_grad_events()          # cross-stream gradient hand-offs never outlive the step that published them
         ray_samples, weights_list, ray_samples_list = self.proposal_sampler(ray_bundle, density_fns=self.density_fns,
                                                                             jitters=jitters)
         N, S = ray_samples.shape

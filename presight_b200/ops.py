@@ -425,19 +425,43 @@ def composite(eu_bins: Tensor, density: Tensor, rgb: Optional[Tensor], sem: Opti
 # Cross-stream hand-off of gradients: a producer may publish "this gradient tensor is complete at event E" so that a
 # consumer running its backward on a side stream (presight_b200/fused.py: the proposal levels' backward overlaps the
 # final level's hash scatter) waits for E instead of for everything queued on the main stream.
+#
+# The hand-off is keyed by an explicit token, not by an address: the consumer's forward (`fused.prop_level_weights`)
+# creates a key and tags its output tensor with it (`_ps_grad_key`); a loss Function that receives that tensor remembers
+# the key and publishes under it in its backward; the consumer's backward pops ITS key and checks that the gradient it was
+# handed is the very tensor that was published (same address, shape and version counter — autograd's in-place
+# accumulation of a second consumer's gradient bumps the version, a summed gradient has another address).  Anything
+# else — no key, no entry, a mismatch — means "no hand-off": the consumer stays on the main stream, which is always
+# correct.  Entries of one step never survive into the next (`clear_grad_events`, called at the start of every forward).
 _GRAD_EVENTS = {}
+_GRAD_KEY_COUNTER = [0]
 
 
-def publish_grad_event(t: Tensor) -> None:
+def new_grad_key() -> int:
+    _GRAD_KEY_COUNTER[0] += 1
+    return _GRAD_KEY_COUNTER[0]
+
+
+def clear_grad_events() -> None:
+    _GRAD_EVENTS.clear()
+
+
+def publish_grad_event(t: Tensor, key) -> None:
+    if key is None:
+        return
     ev = torch.cuda.Event()
     ev.record(torch.cuda.current_stream())
-    if len(_GRAD_EVENTS) > 64:
-        _GRAD_EVENTS.clear()
-    _GRAD_EVENTS[t.data_ptr()] = ev
+    _GRAD_EVENTS[key] = (ev, t.data_ptr(), tuple(t.shape), t._version)
 
 
-def pop_grad_event(t: Tensor):
-    return _GRAD_EVENTS.pop(t.data_ptr(), None)
+def pop_grad_event(t: Tensor, key):
+    entry = _GRAD_EVENTS.pop(key, None) if key is not None else None
+    if entry is None:
+        return None
+    ev, addr, shape, version = entry
+    if t.data_ptr() != addr or tuple(t.shape) != shape or t._version != version:
+        return None
+    return ev
 
 
 _SIDE_STREAMS = {}
@@ -465,6 +489,8 @@ class _InterlevelLoss(torch.autograd.Function):
         with _probe("interlevel_loss"):
             call("ps_interlevel_loss", ptr(c), ptr(w), ptr(t_env), ptr(we), N, S, Sp, ptr(loss), ptr(grad), stream())
         ctx.scale = 1.0 / float(N * S)
+        ctx.grad_key = getattr(w_env, "_ps_grad_key", None)
+        ctx.wshape = w_env.shape
         if need:
             ctx.save_for_backward(grad)
         return loss[0] * ctx.scale
@@ -472,8 +498,8 @@ class _InterlevelLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (grad,) = ctx.saved_tensors
-        out = grad * (g * ctx.scale)
-        publish_grad_event(out)
+        out = (grad * (g * ctx.scale)).view(ctx.wshape)
+        publish_grad_event(out, ctx.grad_key)
         return None, None, None, out
 
 
@@ -495,6 +521,7 @@ class _ZaaInterlevelLoss(torch.autograd.Function):
                  ptr(loss), ptr(grad), stream())
         ctx.scale = 1.0 / float(N * Sp)
         ctx.wshape = w_env.shape
+        ctx.grad_key = getattr(w_env, "_ps_grad_key", None)
         if need:
             ctx.save_for_backward(grad)
         return loss[0] * ctx.scale
@@ -503,7 +530,7 @@ class _ZaaInterlevelLoss(torch.autograd.Function):
     def backward(ctx, g):
         (grad,) = ctx.saved_tensors
         out = (grad * (g * ctx.scale)).view(ctx.wshape)
-        publish_grad_event(out)
+        publish_grad_event(out, ctx.grad_key)
         return None, None, None, out, None
 
 

@@ -47,7 +47,8 @@ class FusedAdam(torch.optim.Optimizer):
                 grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 if grad.dtype != torch.float32:
                     grad = grad.float()
-                call("ps_adam_step", ptr(p), ptr(grad), ptr(state["exp_avg"]), ptr(state["exp_avg_sq"]), p.numel(),
-                     float(group["lr"]), float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"]),
-                     int(state["step"]), stream())
+                with torch.cuda.device(p.device):            # the launch goes to the parameter's device and its current stream
+                    call("ps_adam_step", ptr(p), ptr(grad), ptr(state["exp_avg"]), ptr(state["exp_avg_sq"]), p.numel(),
+                         float(group["lr"]), float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"]),
+                         int(state["step"]), stream())
         return loss

@@ -57,14 +57,9 @@ class GradSynchronizer:
         self._done = set()
         self._handles = []
         if self.world > 1 and overlap:
-            # Backward order on the main stream: final level (field kernels pipelined with the main hash scatter) ->
-            # proposal levels.  The 512 MiB main-table gradient is complete when the first block ends; its all-reduce
-            # (launched from the hook below onto NCCL's stream) can only hide under compute that runs AFTER that point, so
-            # with more than one rank the proposal levels' backward stays on the main stream instead of running early on
-            # the side stream the single-GPU path uses (presight_b200/fused.py: OVERLAP_PROP_BWD).  Measured on 2 B200:
-            # 13.7 ms/step either way (the longer all-reduce of larger worlds has more to gain from the later order).
-            from . import fused
-            fused.OVERLAP_PROP_BWD = False
+            # (Scheduling note: the main table's all-reduce can only hide under compute that runs after the final level's
+            # backward, so a data-parallel caller wants the proposal levels' backward on the main stream —
+            # `fused.set_overlap_prop_bwd(False)`, which bench.py calls for world > 1.  This class does not touch it.)
             for p in self.params:
                 if p.numel() >= min_async_numel:
                     self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad_ready))
