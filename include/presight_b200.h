@@ -382,6 +382,69 @@ int ps_prop_level_bwd(const ps_prop_net* net, const float* origins, const float*
                       int S, const float* aabb_host, int contract, const float* scalings_host, int L, int F, int log2_T,
                       const void* feat_bf16, const float* d_weights, float* dtable, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Sub-field routing and the sub-field mode of the fused levels.  Replace the nearest-centroid routers
+ * fields/PreSight/ingp_field_ms.py:80-126, prop_density_field_ms.py:86-105 (cdist().argmin, then per sub-field a
+ * boolean-mask gather, a field call, a masked scatter and a `torch.any` host sync) without any host synchronisation:
+ *
+ *   ps_ms_route    every point (positions [P,3], or ray sample mid-points from origins / dirs [N,3] + eu_bins [N,S+1] with
+ *                  P = N*S) -> sf_out [P] = index of the nearest centroid (first minimum), counts [nf] += points per
+ *                  sub-field (caller-zeroed).  centroids [nf,3] on the device.
+ *   ps_ms_plan     counts -> seg_start [nf+1] (segments padded to multiples of `pad` rows), cursors [nf] = seg_start,
+ *                  tile_sf [max_rows / tile_rows] = sub-field of every tile of `tile_rows` rows, 255 past the last segment.
+ *   ps_ms_scatter  every point -> a row of its sub-field's segment (order inside a segment is arbitrary):
+ *                  perm[row] = point (caller presets perm to -1 = padding), x01_sorted [max_rows,3] = unit-cube position
+ *                  normalised by THAT sub-field's aabb (aabbs [nf,6] on the device: min xyz, max xyz;
+ *                  fields/PreSight/utils.py:6-10 + the L-inf contraction), sel_sorted [max_rows] = inside-the-cube flag.
+ *   max_rows >= P + nf * pad is a static bound, so nothing has to be read back.
+ *
+ *   ps_hash_fwd_ms / ps_hash_bwd_ms    the hash encoding over those rows (level-major features [L][rows][F]); tables /
+ *                  dtables = device arrays of one table pointer per sub-field.
+ *   ps_prop_level_fwd_ms / _bwd_ms     PropNetDensityField.density_fn per row with the row's sub-field's table and MLP
+ *                  (nets_dev: device array of ps_prop_net_dev): density [P] written at the point's own index /
+ *                  d_density [P] -> dtables and the sub-fields' dW0 / db0 / dW1 / db1 (accumulated).
+ *   ps_field_level_fwd_ms / _bwd_ms    iNGPField (density, colour head, semantic head) per row from the sorted hash features
+ *                  (nets_dev: device array of ps_field_net_dev): density [P], rgb [P,3], sem [P,64] at the point's own
+ *                  index / their gradients -> dfeat (sorted), dapp [N,A] and the sub-fields' dW / dB (accumulated).
+ *   Weights along the rays and their backward then run in ps_composite_fwd / ps_composite_bwd.  rows: multiple of 128
+ *   (proposal) / 256 (field) — use pad = 256. */
+typedef struct ps_prop_net_dev {
+    const float* W0; const float* b0; const float* W1; const float* b1;
+    float* dW0; float* db0; float* dW1; float* db1;
+} ps_prop_net_dev;
+typedef struct ps_field_net_dev {
+    const float* W[8]; const float* B[8];
+    float* dW[8]; float* dB[8];
+    int in_dim;   /* L * F */
+    int app_dim;
+} ps_field_net_dev;
+int ps_ms_route(const float* positions, const float* origins, const float* dirs, const float* eu_bins, int64_t P, int S,
+                const float* centroids, int nf, uint8_t* sf_out, int32_t* counts, void* stream);
+int ps_ms_plan(const int32_t* counts, int nf, int pad, int tile_rows, int64_t max_rows, int32_t* seg_start, int32_t* cursors,
+               uint8_t* tile_sf, void* stream);
+int ps_ms_scatter(const float* positions, const float* origins, const float* dirs, const float* eu_bins, int64_t P, int S,
+                  const uint8_t* sf, const float* aabbs, int nf, int contract, int32_t* cursors, int32_t* perm,
+                  float* x01_sorted, uint8_t* sel_sorted, void* stream);
+int ps_hash_fwd_ms(const float* x01_sorted, int64_t rows, const float* const* tables, const uint8_t* tile_sf,
+                   const float* scalings_host, int L, int F, int log2_T, float* out, void* stream);
+int ps_hash_bwd_ms(const float* x01_sorted, int64_t rows, float* const* dtables, const uint8_t* tile_sf, const int32_t* perm,
+                   const float* scalings_host, int L, int F, int log2_T, const float* dout, void* stream);
+int ps_prop_level_fwd_ms(const ps_prop_net_dev* nets_dev, int hidden, const float* x01_sorted, const uint8_t* sel_sorted,
+                         const int32_t* perm, const uint8_t* tile_sf, int64_t rows, const float* const* tables_dev,
+                         const float* scalings_host, int L, int F, int log2_T, float* density, void* feat_bf16,
+                         void* stream);
+int ps_prop_level_bwd_ms(const ps_prop_net_dev* nets_dev, int hidden, const float* x01_sorted, const uint8_t* sel_sorted,
+                         const int32_t* perm, const uint8_t* tile_sf, int64_t rows, float* const* dtables_dev,
+                         const float* scalings_host, int L, int F, int log2_T, const void* feat_bf16,
+                         const float* d_density, void* stream);
+int ps_field_level_fwd_ms(const ps_field_net_dev* nets_dev, int app_dim, const float* feat_lm_sorted, int L, int F,
+                          const uint8_t* sel_sorted, const int32_t* perm, const uint8_t* tile_sf, int64_t rows, int S,
+                          const float* dirs, const float* app, float* density, float* rgb, float* sem, void* stream);
+int ps_field_level_bwd_ms(const ps_field_net_dev* nets_dev, int app_dim, const float* feat_lm_sorted, int L, int F,
+                          const uint8_t* sel_sorted, const int32_t* perm, const uint8_t* tile_sf, int64_t rows, int S,
+                          const float* dirs, const float* app, const float* d_density, const float* d_rgb,
+                          const float* d_sem, float* dfeat_lm_sorted, float* dapp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

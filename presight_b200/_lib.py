@@ -59,6 +59,15 @@ SIGNATURES = {
     "ps_sky_blend_bwd": [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p],
     "ps_render_losses": [_p, _p, _p, _p, _p, _p, _i64, _i, _f, _p, _p, _p, _p, _p],
     "ps_depth_losses": [_p, _p, _p, _p, _p, _p, _i64, _i, _f, _p, _f, _f, _i, _p, _p, _p, _p],
+    "ps_ms_route": [_p, _p, _p, _p, _i64, _i, _p, _i, _p, _p, _p],
+    "ps_ms_plan": [_p, _i, _i, _i, _i64, _p, _p, _p, _p],
+    "ps_ms_scatter": [_p, _p, _p, _p, _i64, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p],
+    "ps_hash_fwd_ms": [_p, _i64, _p, _p, _fp, _i, _i, _i, _p, _p],
+    "ps_hash_bwd_ms": [_p, _i64, _p, _p, _p, _fp, _i, _i, _i, _p, _p],
+    "ps_prop_level_fwd_ms": [_p, _i, _p, _p, _p, _p, _i64, _p, _fp, _i, _i, _i, _p, _p, _p],
+    "ps_prop_level_bwd_ms": [_p, _i, _p, _p, _p, _p, _i64, _p, _fp, _i, _i, _i, _p, _p, _p],
+    "ps_field_level_fwd_ms": [_p, _i, _p, _i, _i, _p, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _p],
+    "ps_field_level_bwd_ms": [_p, _i, _p, _i, _i, _p, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "ps_voxel_min_bound": [_p, _p, _i64, _p, _p],
     "ps_voxel_accumulate": [_p, _p, _p, _p, _i64, _i, _p, C.c_double, _p, _i64, _p, _p, _p, _p, _p, _p],
     "ps_voxel_finalize": [_p, _i64, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p],
@@ -192,6 +201,45 @@ def host_prop_net(ws, bs, dws=None, dbs=None):
         net.dW0, net.db0, net.dW1, net.db1 = ptr(dws[0]), ptr(dbs[0]), ptr(dws[1]), ptr(dbs[1])
     net.hidden = int(ws[0].shape[0])
     return net
+
+
+class PropNetDev(C.Structure):
+    """ps_prop_net_dev of include/presight_b200.h (arrays of these live in device memory)."""
+    _fields_ = [("W0", C.c_void_p), ("b0", C.c_void_p), ("W1", C.c_void_p), ("b1", C.c_void_p), ("dW0", C.c_void_p),
+                ("db0", C.c_void_p), ("dW1", C.c_void_p), ("db1", C.c_void_p)]
+
+
+class FieldNetDev(C.Structure):
+    """ps_field_net_dev of include/presight_b200.h."""
+    _fields_ = [("W", C.c_void_p * 8), ("B", C.c_void_p * 8), ("dW", C.c_void_p * 8), ("dB", C.c_void_p * 8),
+                ("in_dim", C.c_int), ("app_dim", C.c_int)]
+
+
+_DEV_TABLES = {}
+
+
+def _device_table(slot, signature, build):
+    """Small device-side tables (pointer arrays, network descriptors) are uploaded only when their content changes: the
+    upload is a pageable-memory copy, i.e. a stream synchronisation, and in steady state the parameters never move and
+    the caching allocator hands the per-step gradient buffers back at the same addresses."""
+    hit = _DEV_TABLES.get(slot)
+    if hit is None or hit[0] != signature:
+        hit = (signature, build())
+        _DEV_TABLES[slot] = hit
+    return hit[1]
+
+
+def device_struct_array(structs, device, slot) -> torch.Tensor:
+    """ctypes structures -> one uint8 CUDA tensor holding them back to back (cached per `slot`, see _device_table)."""
+    raw = b"".join(bytes(st) for st in structs)
+    return _device_table((slot, str(device)), raw,
+                         lambda: torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device))
+
+
+def device_ptr_array(tensors, device, slot) -> torch.Tensor:
+    """Device array of the tensors' data pointers (int64), cached per `slot`."""
+    sig = tuple(t.data_ptr() for t in tensors)
+    return _device_table((slot, str(device)), sig, lambda: torch.tensor(sig, dtype=torch.int64).to(device))
 
 
 def host_ints(vals: Sequence[int]):

@@ -221,6 +221,75 @@ __device__ __forceinline__ void load_row_inputs(const FieldArgs& a, int64_t P, i
     if (a.d_w) in.gw = __ldg(a.d_w + p);
 }
 
+// ---- sub-field mode (router: fields/PreSight/ingp_field_ms.py:80-126) -------------------------------------
+// The level's points arrive grouped by sub-field (ms_route.cu): row i is point perm[i] (-1 = padding), tiles of 128 rows
+// are sub-field-homogeneous (segments padded to 256 rows), hash features were gathered from each tile's own table in
+// row order.  Rays are not contiguous in a tile any more, so these kernels stop at the per-point field outputs
+// (density, rgb, semantics) and start from their gradients; compositing runs in ps_composite_fwd / _bwd.
+struct FieldMsArgs {
+    const FieldNet* nets;        // one per sub-field, array in device memory (dW / dB used by the backward)
+    const float* feat;           // level-major hash features [L][rows][F] in row order
+    float* dfeat;                // backward: same layout (written)
+    int L, F;
+    const uint8_t* sels;         // [rows]
+    const int32_t* perm;         // [rows]
+    const uint8_t* tile_sf;      // [rows / 128], 255 = unused
+    int64_t rows;
+    int S;                       // samples per ray: ray of point p = p / S
+    const float* dirs;           // [N, 3]
+    const float* app;            // [N, A] (nullable)
+    float* dapp;                 // backward: [N, A] accumulated (nullable)
+    // forward outputs, written at the point's own index
+    float* density;              // [P]
+    float* rgb;                  // [P, 3]
+    float* sem;                  // [P, 64]
+    // backward inputs
+    const float* d_density;      // [P]
+    const float* d_rgb;          // [P, 3]
+    const float* d_sem;          // [P, 64]
+};
+
+template <int K0>
+__device__ __forceinline__ void load_row_inputs_ms(const FieldMsArgs& a, const FieldNet& net, int64_t i, int32_t p,
+                                                   bool want_feat, bool want_ray, RowInputs<K0>& in) {
+#pragma unroll
+    for (int c = 0; c < K0; ++c) in.feat[c] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) in.app[c] = 0.f;
+    in.dir[0] = in.dir[1] = in.dir[2] = 0.f;
+    in.t0 = in.t1 = in.selv = in.gw = 0.f;
+    if (p < 0) return;
+    if (want_feat) {
+        if (a.F == 2) {
+#pragma unroll
+            for (int l = 0; l < K0 / 2; ++l)
+                if (l < a.L) {
+                    const float2 q = __ldg(reinterpret_cast<const float2*>(a.feat + ((int64_t)l * a.rows + i) * 2));
+                    in.feat[2 * l] = q.x;
+                    in.feat[2 * l + 1] = q.y;
+                }
+        } else {  // F == 4
+#pragma unroll
+            for (int l = 0; l < K0 / 4; ++l)
+                if (l < a.L) {
+                    const float4 q = __ldg(reinterpret_cast<const float4*>(a.feat + ((int64_t)l * a.rows + i) * 4));
+                    in.feat[4 * l] = q.x; in.feat[4 * l + 1] = q.y; in.feat[4 * l + 2] = q.z; in.feat[4 * l + 3] = q.w;
+                }
+        }
+    }
+    if (want_ray) {
+        const int64_t ray = p / a.S;
+        in.dir[0] = __ldg(a.dirs + 3 * ray);
+        in.dir[1] = __ldg(a.dirs + 3 * ray + 1);
+        in.dir[2] = __ldg(a.dirs + 3 * ray + 2);
+        if (a.app)
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+                if (c < net.app_dim) in.app[c] = __ldg(a.app + ray * net.app_dim + c);
+    }
+    in.selv = (float)a.sels[i];
+}
+
 // per-ray inputs only (view direction, appearance embedding)
 template <int K0>
 __device__ __forceinline__ void load_ray_inputs(const FieldArgs& a, int64_t ray, bool valid, RowInputs<K0>& in) {

@@ -582,6 +582,428 @@ static int launch_field_bwd(const FieldArgs& a, cudaStream_t stream) {
     return check_launch("field_level_bwd");
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Sub-field mode backward (see FieldMsArgs in field_tc5.cuh): the same recompute + dgrad + wgrad chain per 128-row tile,
+// driven by per-point gradients of density / rgb / semantics (the compositing backward runs in ps_composite_bwd).  The CTA
+// walks a contiguous range of tiles; when the sub-field changes it flushes the TMEM-resident weight / bias gradient
+// accumulators into the finished sub-field's buffers and restages the next sub-field's weights.
+template <int K0>
+__global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_ms_kernel(FieldMsArgs a) {
+    using WL = WLayout<K0>;
+    using SM = BwdSmem<K0>;
+    using TM = BwdTmem<K0>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, half = tid >> 7, r = tid & 127, warp = r >> 5, lane = tid & 31;
+    unsigned char* wbase = smem;
+    unsigned char* DZb = smem + SM::dzb;
+    unsigned char* DZa = smem + SM::dza;
+    unsigned char* A2 = smem + SM::a2;
+    unsigned char* A1 = smem + SM::a1;
+    unsigned char* X0 = smem + SM::x0;
+    unsigned char* H1 = smem + SM::h1;
+    unsigned char* Ht = smem + SM::h;
+    unsigned char* SHAPPt = smem + SM::shapp;
+    float* raws = reinterpret_cast<float*>(smem + SM::raw);
+    uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(smem + SM::bars);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::bars + 24);
+
+    for (uint32_t k = SM::dzb + tid * 16; k < SM::rayc; k += kBwdThreads * 16)
+        *reinterpret_cast<uint4*>(smem + k) = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < 32) tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        mbar_init(smem_u32(bar_ptr), 1);
+        mbar_init(smem_u32(bar_ptr + 1), 1);
+        mbar_init(smem_u32(bar_ptr + 2), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t bar = smem_u32(bar_ptr), barB0 = smem_u32(bar_ptr + 1), barB1 = smem_u32(bar_ptr + 2);
+    const uint32_t wb = smem_u32(wbase), ones = wb + WL::ones, onehot = wb + WL::onehot;
+    const uint32_t aDZa = smem_u32(DZa), aDZb = smem_u32(DZb), aA1 = smem_u32(A1), aA2 = smem_u32(A2),
+                   aX0 = smem_u32(X0), aH1 = smem_u32(H1), aH = smem_u32(Ht), aSH = smem_u32(SHAPPt);
+    constexpr uint32_t CH = kRows * 16;
+    uint32_t phase = 0, phaseB0 = 0, phaseB1 = 0;
+    const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int64_t ntiles = a.rows / kRows;
+    const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const int64_t t_begin = (int64_t)blockIdx.x * per, t_end = t_begin + per < ntiles ? t_begin + per : ntiles;
+    bool first = true;
+    float db_r2 = 0.f;
+    int cur = -1;
+    FieldNet net{};
+
+    // weight and bias gradients of the sub-field just finished: TMEM accumulators -> its gradient buffers (atomics)
+    auto flush_all = [&]() {
+        const int A = net.app_dim;
+        if (!first) {
+            fence_after();
+            auto flush = [&](int col0, int n_real, int ncols, float* dW, int k_real, int kind) {
+                const int n = warp * 32 + lane;
+                if (warp * 32 >= n_real) return;
+                for (int blk = 0; blk < ncols / 16; ++blk) {
+                    if ((blk & 1) != half) continue;
+                    float u[16];
+                    tmem_ld16_nowait(trow + col0 + 16 * blk, u);
+                    tmem_wait_ld();
+                    if (n < n_real) {
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            int k = 16 * blk + q;
+                            if (kind == 1) {
+                                if (k < 16) {}
+                                else if (k == 16) k = -1;
+                                else if (k < 32) k -= 1;
+                                else k = (k - 32 < A) ? k - 1 : -1;
+                            }
+                            if (kind == 2) {
+                                if (k < 3) atomicAdd(dW + (size_t)k * k_real + n, u[q]);
+                                continue;
+                            }
+                            if (k >= 0 && k < k_real && u[q] != 0.f) atomicAdd(dW + (size_t)n * k_real + k, u[q]);
+                        }
+                    }
+                }
+            };
+            flush(TM::b0, kHid, K0, net.dW[B0], net.in_dim, 0);
+            flush(TM::b1, kBaseOut, kHid, net.dW[B1], kHid, 0);
+            flush(TM::s0, kHid, kSem, net.dW[S0], kSem, 0);
+            flush(TM::s1, kHid, kHid, net.dW[S1], kHid, 0);
+            flush(TM::s2, kSem, kHid, net.dW[S2], kHid, 0);
+            flush(TM::r0, kHid, kRgbIn, net.dW[R0], 16 + kGeo + A, 1);
+            flush(TM::r1, kHid, kHid, net.dW[R1], kHid, 0);
+            flush(TM::r2, kHid, kRgbOut, net.dW[R2], kHid, 2);
+            if (half == 0) {
+                float u[16];
+                tmem_ld16_nowait(trow + TM::r2, u);
+                tmem_wait_ld();
+                const int n = warp * 32 + lane;
+#pragma unroll
+                for (int l = 0; l < kLayers; ++l) {
+                    if (l == R2) continue;
+                    if (n < WL::rows(l) && net.dB[l]) atomicAdd(net.dB[l] + n, u[kBiasCol0 + l]);
+                }
+                if (lane < 3 && net.dB[R2]) atomicAdd(net.dB[R2] + lane, db_r2);
+            }
+            fence_before();
+        }
+        db_r2 = 0.f;
+        first = true;
+    };
+
+#define FB_SYNC_ISSUE(...)     \
+    fence_async_smem();        \
+    fence_before();            \
+    __syncthreads();           \
+    if (warp_u == 0) {         \
+        if (elect_one()) {     \
+            fence_after();     \
+            __VA_ARGS__;       \
+        }                      \
+        __syncwarp();          \
+    }
+#define FB_WAIT()           \
+    mbar_wait(bar, phase);  \
+    phase ^= 1;             \
+    fence_after();
+#define FB_SYNC_ISSUE2(A_LIST, B_LIST, KB) \
+    fence_async_smem();                    \
+    fence_before();                        \
+    __syncthreads();                       \
+    if (warp_u == 0) {                     \
+        if (elect_one()) {                 \
+            fence_after();                 \
+            A_LIST;                        \
+            umma_commit(bar);              \
+        }                                  \
+        __syncwarp();                      \
+    } else if (warp_u == 4) {              \
+        if (elect_one()) {                 \
+            fence_after();                 \
+            B_LIST;                        \
+            umma_commit(KB ? barB1 : barB0); \
+        }                                  \
+        __syncwarp();                      \
+    }
+#define FB_WAIT_B(KB)                  \
+    if (KB) {                          \
+        mbar_wait(barB1, phaseB1);     \
+        phaseB1 ^= 1;                  \
+    } else {                           \
+        mbar_wait(barB0, phaseB0);     \
+        phaseB0 ^= 1;                  \
+    }
+
+    for (int64_t tile = t_begin; tile < t_end; ++tile) {
+        const int sf = a.tile_sf[tile];
+        if (sf == 255) break;
+        if (sf != cur) {
+            if (cur >= 0) flush_all();
+            __syncthreads();
+            net = a.nets[sf];
+            load_all_weights<K0>(net, wbase, tid, kBwdThreads);
+            fence_async_smem();
+            __syncthreads();
+            cur = sf;
+        }
+        const int A = net.app_dim;
+        const bool acc_dw = !first;
+        first = false;
+        const int64_t i = tile * kRows + r;
+        const int32_t p = a.perm[i];
+        const bool valid = p >= 0;
+        const int64_t ray = valid ? p / a.S : 0;
+        float selv;
+        {
+            RowInputs<K0> in;
+            load_row_inputs_ms<K0>(a, net, i, p, half == 0, half == 1, in);
+            if (half == 0) stage_features<K0>(in, X0, r);
+            else stage_shapp<K0>(in, valid, SHAPPt, r);
+            selv = in.selv;
+        }
+        // per-point upstream gradients (this thread's share): density, rgb (half 0), 32 semantic channels
+        const float g_den = valid ? __ldg(a.d_density + p) : 0.f;
+        float g_rgb[3] = {0.f, 0.f, 0.f};
+        if (valid && half == 0) {
+            g_rgb[0] = __ldg(a.d_rgb + (int64_t)p * 3);
+            g_rgb[1] = __ldg(a.d_rgb + (int64_t)p * 3 + 1);
+            g_rgb[2] = __ldg(a.d_rgb + (int64_t)p * 3 + 2);
+        }
+        // ---- base network, forward --------------------------------------------------------------------------
+        FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(B0), kHid, kHid);
+                      gemm_kk(tmem + TM::acc, aX0, kRows, wb + WL::b0, kHid, kHid, K0, true); umma_commit(bar))
+        FB_WAIT()
+        relu_epilogue32(trow + TM::acc, 32 * half, H1, r);
+        FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(B1), kBaseOut, kBaseOut);
+                      gemm_kk(tmem + TM::acc, aH1, kRows, wb + WL::b1, kBaseOut, kBaseOut, kHid, true); umma_commit(bar))
+        FB_WAIT()
+        {
+            float v[32];
+            const int c0 = half == 0 ? 0 : 48;
+            tmem_ld32_nowait(trow + TM::acc + c0, v);
+            tmem_wait_ld();
+            if (half == 0) raws[r] = v[0];
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) store_chunk(Ht, kRows, r, c0 + k, v + k);
+            if (half == 0) {
+                float u[16];
+                tmem_ld16_nowait(trow + TM::acc + 32, u);
+                tmem_wait_ld();
+                store_chunk(Ht, kRows, r, 32, u);
+                store_chunk(Ht, kRows, r, 40, u + 8);
+            }
+        }
+        // ---- colour head, forward ---------------------------------------------------------------------------
+        FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(R0), kHid, kHid);
+                      gemm_kk(tmem + TM::acc, aSH, kRows, wb + WL::r0, kHid, kHid, 16, true);
+                      gemm_kk(tmem + TM::acc, aH, kRows, wb + WL::r0 + 2 * kHid * 16, kHid, kHid, 16, true);
+                      gemm_kk(tmem + TM::acc, aSH + 2 * CH, kRows, wb + WL::r0 + 4 * kHid * 16, kHid, kHid, 16, true);
+                      umma_commit(bar))
+        const float raw = raws[r];
+        // density = exp(raw) * sel; gradient through the clamped exponential (activations.py:28-41)
+        const float d_raw = valid ? g_den * selv * expf(fminf(fmaxf(raw, -15.f), 15.f)) : 0.f;
+        FB_WAIT()
+        relu_epilogue32(trow + TM::acc, 32 * half, A1, r);
+        FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(R1), kHid, kHid);
+                      gemm_kk(tmem + TM::acc, aA1, kRows, wb + WL::r1, kHid, kHid, kHid, true); umma_commit(bar))
+        FB_WAIT()
+        relu_epilogue32(trow + TM::acc, 32 * half, A2, r);
+        FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(R2), kRgbOut, kRgbOut);
+                      gemm_kk(tmem + TM::acc, aA2, kRows, wb + WL::r2, kRgbOut, kRgbOut, kHid, true); umma_commit(bar))
+        FB_WAIT()
+        // ---- colour head, backward --------------------------------------------------------------------------
+        float dz3[3] = {0.f, 0.f, 0.f};
+        if (half == 0) {
+            float u[16];
+            tmem_ld16_nowait(trow + TM::acc, u);
+            tmem_wait_ld();
+            float dz[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) dz[k] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float y = sigmoid_f(u[k]);
+                dz[k] = g_rgb[k] * y * (1.f - y);
+            }
+            store_chunk(DZa, kRows, r, 0, dz);
+            store_chunk(DZa, kRows, r, 8, dz + 8);
+            dz3[0] = dz[0]; dz3[1] = dz[1]; dz3[2] = dz[2];
+        }
+        FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::r2, kRgbOut, kHid, 16, false),
+                       gemm_wgrad(tmem + TM::r2, aA2, aDZa, 16, acc_dw), 0)
+        if (half == 0) {
+            const float s0 = warp_sum(dz3[0]), s1 = warp_sum(dz3[1]), s2 = warp_sum(dz3[2]);
+            db_r2 += lane == 0 ? s0 : (lane == 1 ? s1 : s2);
+        }
+        FB_WAIT()
+        dgrad_epilogue32(trow + TM::acc, 32 * half, A2, DZb, r);
+        FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::r1, kHid, kHid, kHid, false),
+                       gemm_wgrad(tmem + TM::r1, aDZb, aA1, kHid, acc_dw);
+                       gemm_bias_grad(tmem + TM::r2, aDZb, onehot + R1 * 256), 1)
+        FB_WAIT()
+        FB_WAIT_B(0)
+        dgrad_epilogue32(trow + TM::acc, 32 * half, A1, DZa, r);
+        FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::r0, kHid, kRgbIn, kHid, false),
+                       gemm_wgrad(tmem + TM::r0, aDZa, aSH, 16, acc_dw);
+                       gemm_wgrad(tmem + TM::r0 + 16, aDZa, aH, 16, acc_dw);
+                       gemm_wgrad(tmem + TM::r0 + 32, aDZa, aSH + 2 * CH, 16, acc_dw);
+                       gemm_bias_grad(tmem + TM::r2, aDZa, onehot + R0 * 256), 0)
+        FB_WAIT()
+        FB_WAIT_B(1)
+        float d_h01[16];
+        {
+            float u[16];
+            tmem_ld16_nowait(trow + TM::acc + (half == 0 ? 16 : 32), u);
+            tmem_wait_ld();
+            if (half == 0) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) d_h01[k] = u[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) d_h01[k] = 0.f;
+                // appearance gradient: rows of a tile belong to different rays here -> one atomic per (row, channel)
+                if (a.dapp && A > 0 && valid)
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        if (k < A) atomicAdd(a.dapp + ray * A + k, u[k]);
+            }
+        }
+        // ---- semantic head, forward -------------------------------------------------------------------------
+        FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(S0), kHid, kHid);
+                      gemm_kk(tmem + TM::acc, aH + 2 * CH, kRows, wb + WL::s0, kHid, kHid, kSem, true); umma_commit(bar))
+        FB_WAIT()
+        FB_WAIT_B(0)
+        relu_epilogue32(trow + TM::acc, 32 * half, A1, r);
+        FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(S1), kHid, kHid);
+                      gemm_kk(tmem + TM::acc, aA1, kRows, wb + WL::s1, kHid, kHid, kHid, true); umma_commit(bar))
+        FB_WAIT()
+        relu_epilogue32(trow + TM::acc, 32 * half, A2, r);
+        // ---- semantic head, backward: dZ of the (linear) output layer = the per-point gradient itself ----------------
+        {
+            float v[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = 0.f;
+            if (valid) {
+                const float4* src = reinterpret_cast<const float4*>(a.d_sem + (int64_t)p * kSem + 32 * half);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4 q = __ldg(src + k);
+                    v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) store_chunk(DZb, kRows, r, 32 * half + k, v + k);
+        }
+        FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::s2, kSem, kHid, kSem, false),
+                       gemm_wgrad(tmem + TM::s2, aDZb, aA2, kHid, acc_dw);
+                       gemm_bias_grad(tmem + TM::r2, aDZb, onehot + S2 * 256), 1)
+        FB_WAIT()
+        dgrad_epilogue32(trow + TM::acc, 32 * half, A2, DZa, r);
+        FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::s1, kHid, kHid, kHid, false),
+                       gemm_wgrad(tmem + TM::s1, aDZa, aA1, kHid, acc_dw);
+                       gemm_bias_grad(tmem + TM::r2, aDZa, onehot + S1 * 256), 0)
+        FB_WAIT()
+        FB_WAIT_B(1)
+        dgrad_epilogue32(trow + TM::acc, 32 * half, A1, DZb, r);
+        FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::s0, kHid, kSem, kHid, false),
+                       gemm_wgrad(tmem + TM::s0, aDZb, aH + 2 * CH, kSem, acc_dw);
+                       gemm_bias_grad(tmem + TM::r2, aDZb, onehot + S0 * 256), 1)
+        FB_WAIT()
+        FB_WAIT_B(0)
+        // ---- base network, backward ---------------------------------------------------------------------------
+        {
+            float v[32];
+            tmem_ld32_nowait(trow + TM::acc + 32 * half, v);
+            tmem_wait_ld();
+            if (!valid) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) v[k] = 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) store_chunk(DZa, kRows, r, 16 + 32 * half + k, v + k);
+            if (half == 0) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) d_h01[k] = valid ? d_h01[k] : 0.f;
+                d_h01[0] = d_raw;
+                store_chunk(DZa, kRows, r, 0, d_h01);
+                store_chunk(DZa, kRows, r, 8, d_h01 + 8);
+            }
+        }
+        FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZa, kRows, wb + WL::b1, kBaseOut, kHid, kBaseOut, false),
+                       gemm_wgrad(tmem + TM::b1, aDZa, aH1, kHid, acc_dw);
+                       gemm_bias_grad(tmem + TM::r2, aDZa, onehot + B1 * 256), 0)
+        FB_WAIT()
+        FB_WAIT_B(1)
+        dgrad_epilogue32(trow + TM::acc, 32 * half, H1, DZb, r);
+        FB_SYNC_ISSUE2(gemm_dgrad(tmem + TM::acc, aDZb, kRows, wb + WL::b0, kHid, K0, kHid, false),
+                       gemm_wgrad(tmem + TM::b0, aDZb, aX0, K0, acc_dw);
+                       gemm_bias_grad(tmem + TM::r2, aDZb, onehot + B0 * 256), 1)
+        FB_WAIT()
+        FB_WAIT_B(0)
+        FB_WAIT_B(1)
+        // ---- hash-feature gradient (level-major [L][rows][F], row order) ---------------------------------------
+        if (a.dfeat) {
+#pragma unroll
+            for (int blk = 0; blk < K0 / 16; ++blk) {
+                if ((blk & 1) != half) continue;
+                float u[16];
+                tmem_ld16_nowait(trow + TM::acc + 16 * blk, u);
+                tmem_wait_ld();
+                if (a.F == 2) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int l = 8 * blk + k;
+                        if (l < a.L)
+                            *reinterpret_cast<float2*>(a.dfeat + ((int64_t)l * a.rows + i) * 2) =
+                                valid ? make_float2(u[2 * k], u[2 * k + 1]) : make_float2(0.f, 0.f);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int l = 4 * blk + k;
+                        if (l < a.L)
+                            *reinterpret_cast<float4*>(a.dfeat + ((int64_t)l * a.rows + i) * 4) =
+                                valid ? make_float4(u[4 * k], u[4 * k + 1], u[4 * k + 2], u[4 * k + 3])
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+#undef FB_SYNC_ISSUE
+#undef FB_SYNC_ISSUE2
+#undef FB_WAIT
+#undef FB_WAIT_B
+    if (cur >= 0) flush_all();
+    fence_before();
+    __syncthreads();
+    if (tid < 32) tmem_dealloc(tmem, 512);
+}
+
+template <int K0>
+static int launch_field_bwd_ms(const FieldMsArgs& a, cudaStream_t stream) {
+    constexpr size_t smem = BwdSmem<K0>::total;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(field_bwd_ms_kernel<K0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess) {
+            set_error("field_level_bwd_ms: cannot reserve %zu bytes of shared memory", smem);
+            return 2;
+        }
+        configured = true;
+    }
+    const int64_t ntiles = a.rows / kRows;
+    const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+    field_bwd_ms_kernel<K0><<<grid, kBwdThreads, smem, stream>>>(a);
+    return check_launch("field_level_bwd_ms");
+}
+
 }  // namespace ftc5
 }  // namespace ps
 
@@ -614,4 +1036,24 @@ extern "C" int ps_field_level_bwd(const ps_field_net* net, const float* feat_lm,
     a.d_w = d_weights; a.d_rgb = d_rgb_out; a.d_acc = d_acc; a.d_dexp = d_depth_exp; a.d_sem = d_sem_out;
     if (L * F <= 32) return launch_field_bwd<32>(a, (cudaStream_t)stream);
     return launch_field_bwd<48>(a, (cudaStream_t)stream);
+}
+
+int ps_field_ms_check(const ps_field_net_dev* nets_dev, int L, int F, int64_t rows, int S, int app_dim, const char* what);
+
+extern "C" int ps_field_level_bwd_ms(const ps_field_net_dev* nets_dev, int app_dim, const float* feat_lm_sorted, int L,
+                                     int F, const uint8_t* sel_sorted, const int32_t* perm, const uint8_t* tile_sf,
+                                     int64_t rows, int S, const float* dirs, const float* app, const float* d_density,
+                                     const float* d_rgb, const float* d_sem, float* dfeat_lm_sorted, float* dapp,
+                                     void* stream) {
+    if (int e = ps_field_ms_check(nets_dev, L, F, rows, S, app_dim, "field_level_bwd_ms")) return e;
+    PS_REQUIRE(feat_lm_sorted && sel_sorted && perm && tile_sf && dirs && d_density && d_rgb && d_sem && dfeat_lm_sorted,
+               "field_level_bwd_ms: null pointer");
+    PS_REQUIRE(app_dim == 0 || app != nullptr, "field_level_bwd_ms: appearance is null");
+    FieldMsArgs a{};
+    a.nets = reinterpret_cast<const FieldNet*>(nets_dev);
+    a.feat = feat_lm_sorted; a.dfeat = dfeat_lm_sorted; a.L = L; a.F = F; a.sels = sel_sorted; a.perm = perm;
+    a.tile_sf = tile_sf; a.rows = rows; a.S = S; a.dirs = dirs; a.app = app; a.dapp = dapp;
+    a.d_density = d_density; a.d_rgb = d_rgb; a.d_sem = d_sem;
+    if (L * F <= 32) return launch_field_bwd_ms<32>(a, (cudaStream_t)stream);
+    return launch_field_bwd_ms<48>(a, (cudaStream_t)stream);
 }

@@ -316,6 +316,177 @@ static int launch_field_fwd(const FieldArgs& a, cudaStream_t stream) {
     return check_launch("field_level_fwd");
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Sub-field mode forward (see FieldMsArgs in field_tc5.cuh): the same five GEMM -> epilogue phases per 128-row tile, two
+// tiles (one per thread group) in lock step so that both always belong to the same sub-field; the CTA walks a contiguous
+// range of tile pairs and restages the 54 KB of weights only when the sub-field changes.  Outputs per point.
+template <int K0>
+__global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_ms_kernel(FieldMsArgs a) {
+    using WL = WLayout<K0>;
+    using SM = FwdSmem<K0>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, g = tid >> 7, t = tid & 127, warp = t >> 5;
+    unsigned char* wbase = smem;
+    unsigned char* gs = smem + SM::groups + g * SM::group_bytes;
+    unsigned char* Ht = gs + SM::h;
+    unsigned char* SHAPPt = gs + SM::shapp;
+    unsigned char* BufA = gs + SM::bufa;
+    unsigned char* BufB = gs + SM::bufb;
+    uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(smem + SM::bars);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::bars + 16);
+    if (tid < 32) tmem_alloc(tmem_slot, 256);
+    if (tid == 0) {
+        mbar_init(smem_u32(bar_ptr), 1);
+        mbar_init(smem_u32(bar_ptr + 1), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot + g * 128;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t bar = smem_u32(bar_ptr + g);
+    const uint32_t wb = smem_u32(wbase), ones = wb + WL::ones;
+    const uint32_t aH = smem_u32(Ht), aSH = smem_u32(SHAPPt), aA = smem_u32(BufA), aB = smem_u32(BufB);
+    const int barid = 1 + g;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    uint32_t phase = 0;
+    const int64_t npairs = a.rows / (2 * kRows);
+    const int64_t per = (npairs + gridDim.x - 1) / gridDim.x;
+    const int64_t p_begin = (int64_t)blockIdx.x * per, p_end = p_begin + per < npairs ? p_begin + per : npairs;
+    int cur = -1;
+    FieldNet net{};
+
+#define FT_SYNC_ISSUE(...)                 \
+    fence_async_smem();                    \
+    fence_before();                        \
+    bar_sync(barid, 128);                  \
+    if (warp_u == 0) {                     \
+        if (elect_one()) {                 \
+            fence_after();                 \
+            __VA_ARGS__;                   \
+            umma_commit(bar);              \
+        }                                  \
+        __syncwarp();                      \
+    }
+#define FT_WAIT()           \
+    mbar_wait(bar, phase);  \
+    phase ^= 1;             \
+    fence_after();
+
+    for (int64_t pair = p_begin; pair < p_end; ++pair) {
+        const int sf = a.tile_sf[2 * pair];
+        if (sf == 255) break;                                   // the used tiles are a prefix
+        if (sf != cur) {
+            __syncthreads();                                    // both groups are done with the previous weights
+            net = a.nets[sf];
+            load_all_weights<K0>(net, wbase, tid, kFwdThreads);
+            fence_async_smem();
+            __syncthreads();
+            cur = sf;
+        }
+        const int64_t i = (2 * pair + g) * kRows + t;
+        const int32_t p = a.perm[i];
+        const bool valid = p >= 0;
+        float selv;
+        {
+            RowInputs<K0> in;
+            load_row_inputs_ms<K0>(a, net, i, p, true, true, in);
+            stage_features<K0>(in, BufA, t);
+            stage_shapp<K0>(in, valid, SHAPPt, t);
+            selv = in.selv;
+        }
+        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(B0), kHid, kHid);
+                      gemm_kk(tmem, aA, kRows, wb + WL::b0, kHid, kHid, K0, true))
+        FT_WAIT()
+        hidden_epilogue64(trow, BufB, t);
+        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(B1), kBaseOut, kBaseOut);
+                      gemm_kk(tmem, aB, kRows, wb + WL::b1, kBaseOut, kBaseOut, kHid, true))
+        FT_WAIT()
+        float raw;
+        {
+            float v[32];
+            tmem_ld32_nowait(trow, v);
+            tmem_wait_ld();
+            raw = v[0];
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) store_chunk(Ht, kRows, t, k, v + k);
+            tmem_ld32_nowait(trow + 32, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) store_chunk(Ht, kRows, t, 32 + k, v + k);
+            float u[16];
+            tmem_ld16_nowait(trow + 64, u);
+            tmem_wait_ld();
+            store_chunk(Ht, kRows, t, 64, u);
+            store_chunk(Ht, kRows, t, 72, u + 8);
+        }
+        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(R0), kHid, kHid);
+                      gemm_kk(tmem, aSH, kRows, wb + WL::r0, kHid, kHid, 16, true);
+                      gemm_kk(tmem, aH, kRows, wb + WL::r0 + 2 * kHid * 16, kHid, kHid, 16, true);
+                      gemm_kk(tmem, aSH + 2 * kRows * 16, kRows, wb + WL::r0 + 4 * kHid * 16, kHid, kHid, 16, true);
+                      gemm_bias(tmem + 64, ones, wb + WL::bt(S0), kHid, kHid);
+                      gemm_kk(tmem + 64, aH + 2 * kRows * 16, kRows, wb + WL::s0, kHid, kHid, kSem, true))
+        if (valid) a.density[p] = expf(raw) * selv;               // ingp_field.py:185-190
+        FT_WAIT()
+        hidden_epilogue64(trow, BufA, t);
+        hidden_epilogue64(trow + 64, BufB, t);
+        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(R1), kHid, kHid);
+                      gemm_kk(tmem, aA, kRows, wb + WL::r1, kHid, kHid, kHid, true);
+                      gemm_bias(tmem + 64, ones, wb + WL::bt(S1), kHid, kHid);
+                      gemm_kk(tmem + 64, aB, kRows, wb + WL::s1, kHid, kHid, kHid, true))
+        FT_WAIT()
+        hidden_epilogue64(trow, BufA, t);
+        hidden_epilogue64(trow + 64, BufB, t);
+        FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(R2), kRgbOut, kRgbOut);
+                      gemm_kk(tmem, aA, kRows, wb + WL::r2, kRgbOut, kRgbOut, kHid, true);
+                      gemm_bias(tmem + 64, ones, wb + WL::bt(S2), kSem, kSem);
+                      gemm_kk(tmem + 64, aB, kRows, wb + WL::s2, kSem, kSem, kHid, true))
+        FT_WAIT()
+        {
+            float v[64];
+            tmem_ld32_nowait(trow + 64, *reinterpret_cast<float(*)[32]>(v));
+            tmem_ld32_nowait(trow + 96, *reinterpret_cast<float(*)[32]>(v + 32));
+            float u[16];
+            tmem_ld16_nowait(trow, u);
+            tmem_wait_ld();
+            if (valid) {
+                float4* dst = reinterpret_cast<float4*>(a.sem + (int64_t)p * kSem);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) a.rgb[(int64_t)p * 3 + k] = sigmoid_f(u[k]);
+            }
+        }
+        fence_before();
+        bar_sync(barid, 128);          // every thread of the group is done with the accumulators and tiles
+    }
+#undef FT_SYNC_ISSUE
+#undef FT_WAIT
+    fence_before();
+    __syncthreads();
+    if (tid < 32) tmem_dealloc(*tmem_slot, 256);
+}
+
+template <int K0>
+static int launch_field_fwd_ms(const FieldMsArgs& a, cudaStream_t stream) {
+    constexpr size_t smem = FwdSmem<K0>::total;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(field_fwd_ms_kernel<K0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess) {
+            set_error("field_level_fwd_ms: cannot reserve %zu bytes of shared memory", smem);
+            return 2;
+        }
+        configured = true;
+    }
+    const int64_t npairs = a.rows / (2 * kRows);
+    const int grid = (int)(npairs < kNumSMs ? npairs : kNumSMs);
+    field_fwd_ms_kernel<K0><<<grid, kFwdThreads, smem, stream>>>(a);
+    return check_launch("field_level_fwd_ms");
+}
+
 }  // namespace ftc5
 }  // namespace ps
 
@@ -354,4 +525,32 @@ int ps_field_check_common(const ps_field_net* net, int L, int F, int64_t N, int 
     PS_REQUIRE(net->app_dim >= 0 && net->app_dim <= 16, "%s: appearance dim %d exceeds 16", what, net->app_dim);
     for (int l = 0; l < kLayers; ++l) PS_REQUIRE(net->W[l] != nullptr, "%s: weight %d is null", what, l);
     return 0;
+}
+
+int ps_field_ms_check(const ps_field_net_dev* nets_dev, int L, int F, int64_t rows, int S, int app_dim, const char* what) {
+    PS_REQUIRE(nets_dev != nullptr, "%s: nets is null", what);
+    PS_REQUIRE(F == 2 || F == 4, "%s: features_per_level %d not in {2,4}", what, F);
+    PS_REQUIRE(L >= 1 && L * F <= 48, "%s: L*F = %d exceeds 48", what, L * F);
+    PS_REQUIRE(rows > 0 && rows % 256 == 0 && rows < (1ll << 31), "%s: rows must be a positive multiple of 256", what);
+    PS_REQUIRE(S >= 1, "%s: samples per ray %d < 1", what, S);
+    PS_REQUIRE(app_dim >= 0 && app_dim <= 16, "%s: appearance dim %d exceeds 16", what, app_dim);
+    return 0;
+}
+
+static_assert(sizeof(ps_field_net_dev) == sizeof(ps::ftc5::FieldNet), "ps_field_net_dev layout");
+
+extern "C" int ps_field_level_fwd_ms(const ps_field_net_dev* nets_dev, int app_dim, const float* feat_lm_sorted, int L, int F,
+                                     const uint8_t* sel_sorted, const int32_t* perm, const uint8_t* tile_sf, int64_t rows,
+                                     int S, const float* dirs, const float* app, float* density, float* rgb, float* sem,
+                                     void* stream) {
+    if (int e = ps_field_ms_check(nets_dev, L, F, rows, S, app_dim, "field_level_fwd_ms")) return e;
+    PS_REQUIRE(feat_lm_sorted && sel_sorted && perm && tile_sf && dirs && density && rgb && sem,
+               "field_level_fwd_ms: null pointer");
+    PS_REQUIRE(app_dim == 0 || app != nullptr, "field_level_fwd_ms: appearance is null");
+    FieldMsArgs a{};
+    a.nets = reinterpret_cast<const FieldNet*>(nets_dev);
+    a.feat = feat_lm_sorted; a.L = L; a.F = F; a.sels = sel_sorted; a.perm = perm; a.tile_sf = tile_sf; a.rows = rows;
+    a.S = S; a.dirs = dirs; a.app = app; a.density = density; a.rgb = rgb; a.sem = sem;
+    if (L * F <= 32) return launch_field_fwd_ms<32>(a, (cudaStream_t)stream);
+    return launch_field_fwd_ms<48>(a, (cudaStream_t)stream);
 }

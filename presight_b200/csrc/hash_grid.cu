@@ -13,12 +13,26 @@
 
 namespace ps {
 
+// Sub-field mode (ms_route.cu): rows are grouped by sub-field in tiles of 128; tile -> sub-field -> that sub-field's table
+// (forward) or gradient table (backward).  All null = the ordinary single-table call.
+struct MsTables {
+    const float* const* tables;
+    float* const* dtables;
+    const uint8_t* tile_sf;
+    const int32_t* perm;
+};
+
 template <int F, int LPT>
 __global__ void __launch_bounds__(256) hash_fwd_kernel(const float* __restrict__ x, int64_t P,
                                                        const float* __restrict__ table, HashParams hp,
-                                                       float* __restrict__ out, int level_major) {
+                                                       float* __restrict__ out, int level_major, MsTables ms) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
+    if (ms.tile_sf) {                      // sub-field-homogeneous tiles of 128 rows: this tile's table (255 = unused tile)
+        const int sf = ms.tile_sf[p >> 7];
+        if (sf == 255) return;
+        table = ms.tables[sf];
+    }
     const int l0 = blockIdx.y * LPT;
     const float px = __ldg(x + 3 * p), py = __ldg(x + 3 * p + 1), pz = __ldg(x + 3 * p + 2);
     const uint32_t mask = (1u << hp.log2_T) - 1u;
@@ -75,10 +89,16 @@ template <int F, int LPT, bool WITH_DX>
 __global__ void __launch_bounds__(256) hash_bwd_kernel(const float* __restrict__ x, int64_t P,
                                                        const float* __restrict__ table, HashParams hp,
                                                        const float* __restrict__ dout, float* __restrict__ dtable,
-                                                       float* __restrict__ dx, int level_major) {
+                                                       float* __restrict__ dx, int level_major, MsTables ms) {
     // every lane stays alive (full-mask shuffles below); out-of-range lanes carry zero gradient
     const int64_t pi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = pi < P;
+    bool valid = pi < P;
+    if (ms.tile_sf) {                      // (warp-uniform: a warp lies inside one 128-row tile)
+        const int sf = ms.tile_sf[(valid ? pi : P - 1) >> 7];
+        if (sf == 255) return;
+        dtable = ms.dtables[sf];
+        valid = valid && ms.perm[pi] >= 0; // padding rows of a sub-field's segment carry no point
+    }
     const int64_t p = valid ? pi : P - 1;
     const int lane = threadIdx.x & 31;
     const int l0 = blockIdx.y * LPT;
@@ -242,33 +262,34 @@ using namespace ps;
     }
 
 static int hash_fwd_impl(const float* x01, int64_t P, const float* table, const float* scalings_host, int L, int F,
-                         int log2_T, float* out, int level_major, void* stream) {
+                         int log2_T, float* out, int level_major, void* stream, MsTables ms = MsTables{}) {
     HashParams hp;
     if (int e = fill_params(hp, scalings_host, L, log2_T)) return e;
     PS_REQUIRE(F == 1 || F == 2 || F == 4 || F == 8, "hash_fwd: features_per_level %d not in {1,2,4,8}", F);
     PS_REQUIRE(P >= 0, "hash_fwd: negative P");
     if (P == 0) return 0;
-    PS_REQUIRE(x01 && table && out, "hash_fwd: null pointer");
+    PS_REQUIRE(x01 && (table || ms.tables) && out, "hash_fwd: null pointer");
     const int threads = 256;
     const int64_t blocks = cdiv(P, threads);
     PS_REQUIRE(blocks < (1ll << 31), "hash_fwd: too many points");
     cudaStream_t s = (cudaStream_t)stream;
     const int lpt = pick_lpt(L, F, log2_T);
     const dim3 grid((unsigned)blocks, (unsigned)(L / lpt));
-#define PS_FWD(FF, LL) hash_fwd_kernel<FF, LL><<<grid, threads, 0, s>>>(x01, P, table, hp, out, level_major);
+#define PS_FWD(FF, LL) hash_fwd_kernel<FF, LL><<<grid, threads, 0, s>>>(x01, P, table, hp, out, level_major, ms);
     PS_DISPATCH_F_LPT(F, lpt, PS_FWD)
 #undef PS_FWD
     return check_launch("hash_fwd");
 }
 
 static int hash_bwd_impl(const float* x01, int64_t P, const float* table, const float* scalings_host, int L, int F,
-                         int log2_T, const float* dout, float* dtable, float* dx, int level_major, void* stream) {
+                         int log2_T, const float* dout, float* dtable, float* dx, int level_major, void* stream,
+                         MsTables ms = MsTables{}) {
     HashParams hp;
     if (int e = fill_params(hp, scalings_host, L, log2_T)) return e;
     PS_REQUIRE(F == 1 || F == 2 || F == 4 || F == 8, "hash_bwd: features_per_level %d not in {1,2,4,8}", F);
     PS_REQUIRE(P >= 0, "hash_bwd: negative P");
     if (P == 0) return 0;
-    PS_REQUIRE(x01 && dout && dtable, "hash_bwd: null pointer");
+    PS_REQUIRE(x01 && dout && (dtable || ms.dtables), "hash_bwd: null pointer");
     PS_REQUIRE(dx == nullptr || table != nullptr, "hash_bwd: dx requested but table is null");
     const int threads = 256;
     const int64_t blocks = cdiv(P, threads);
@@ -278,9 +299,9 @@ static int hash_bwd_impl(const float* x01, int64_t P, const float* table, const 
     const dim3 grid((unsigned)blocks, (unsigned)(L / lpt));
 #define PS_BWD(FF, LL)                                                                                  \
     if (dx)                                                                                             \
-        hash_bwd_kernel<FF, LL, true><<<grid, threads, 0, s>>>(x01, P, table, hp, dout, dtable, dx, level_major); \
+        hash_bwd_kernel<FF, LL, true><<<grid, threads, 0, s>>>(x01, P, table, hp, dout, dtable, dx, level_major, ms); \
     else                                                                                                \
-        hash_bwd_kernel<FF, LL, false><<<grid, threads, 0, s>>>(x01, P, table, hp, dout, dtable, dx, level_major);
+        hash_bwd_kernel<FF, LL, false><<<grid, threads, 0, s>>>(x01, P, table, hp, dout, dtable, dx, level_major, ms);
     PS_DISPATCH_F_LPT(F, lpt, PS_BWD)
 #undef PS_BWD
     return check_launch("hash_bwd");
@@ -302,6 +323,22 @@ extern "C" int ps_hash_fwd_lm(const float* x01, int64_t P, const float* table, c
 extern "C" int ps_hash_bwd_lm(const float* x01, int64_t P, const float* table, const float* scalings_host, int L,
                               int F, int log2_T, const float* dout, float* dtable, float* dx, void* stream) {
     return hash_bwd_impl(x01, P, table, scalings_host, L, F, log2_T, dout, dtable, dx, 1, stream);
+}
+
+// sub-field mode (level-major features [L][rows][F] over the rows of ms_route.cu's segments; rows a multiple of 128):
+// tables / dtables = device arrays of one pointer per sub-field
+extern "C" int ps_hash_fwd_ms(const float* x01_sorted, int64_t rows, const float* const* tables, const uint8_t* tile_sf,
+                              const float* scalings_host, int L, int F, int log2_T, float* out, void* stream) {
+    PS_REQUIRE(tables && tile_sf && rows % 128 == 0, "hash_fwd_ms: null pointer or rows not a multiple of 128");
+    MsTables ms{tables, nullptr, tile_sf, nullptr};
+    return hash_fwd_impl(x01_sorted, rows, nullptr, scalings_host, L, F, log2_T, out, 1, stream, ms);
+}
+extern "C" int ps_hash_bwd_ms(const float* x01_sorted, int64_t rows, float* const* dtables, const uint8_t* tile_sf,
+                              const int32_t* perm, const float* scalings_host, int L, int F, int log2_T, const float* dout,
+                              void* stream) {
+    PS_REQUIRE(dtables && tile_sf && perm && rows % 128 == 0, "hash_bwd_ms: null pointer or rows not a multiple of 128");
+    MsTables ms{nullptr, dtables, tile_sf, perm};
+    return hash_bwd_impl(x01_sorted, rows, nullptr, scalings_host, L, F, log2_T, dout, nullptr, nullptr, 1, stream, ms);
 }
 
 // how many consecutive levels one thread handles for this grid shape (callers use it to choose the feature layout:

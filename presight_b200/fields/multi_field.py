@@ -73,12 +73,59 @@ class iNGPFieldMS(nn.Module):
         return {k: v.reshape(*output_shape, -1) for k, v in res.items()}
 
     def supports_fused(self) -> bool:
-        return len(self.fields) == 1
+        """One sub-field: the ray-tile fused kernels.  Several: the sub-field mode of the same kernels (routing on the
+        device, presight_b200/fused.py) when every sub-field has the reference field's architecture."""
+        if len(self.fields) == 1:
+            return True
+        return self._ms_meta() is not None
+
+    def _ms_meta(self):
+        from .. import fused
+        f0 = self.fields[0]
+        if not f0.use_semantics:
+            return None
+        enc = f0.mlp_base_grid
+        grid = fused.GridMeta(enc._scalings_host, enc.log2_hashmap_size, enc.features_per_level)
+
+        def dims(mlp):
+            ls = list(mlp.layers)
+            return (ls[0].weight.shape[1],) + tuple(l.weight.shape[0] for l in ls)
+        A = f0.appearance_embedding_dim
+        base = fused.MlpMeta(dims(f0.mlp_base_mlp), f0.mlp_base_mlp._out_act)
+        sem = fused.MlpMeta(dims(f0.semantic_head), f0.semantic_head._out_act)
+        rgb = fused.MlpMeta(dims(f0.rgb_head), f0.rgb_head._out_act)
+        if not (fused.USE_TC5_FIELD and fused.tc5_field_supported(grid, base, sem, rgb, f0.geo_feat_dim,
+                                                                    f0.mlp_base_mlp.precision, 64, A)):
+            return None
+        for f in self.fields[1:]:
+            e = f.mlp_base_grid
+            if (tuple(e._scalings_host) != tuple(enc._scalings_host) or e.log2_hashmap_size != enc.log2_hashmap_size
+                    or e.features_per_level != enc.features_per_level or dims(f.mlp_base_mlp) != base.dims
+                    or dims(f.semantic_head) != sem.dims or dims(f.rgb_head) != rgb.dims
+                    or (f.spatial_distortion is None) != (f0.spatial_distortion is None)):
+                return None
+        return grid
 
     def fused_level(self, origins: Tensor, directions: Tensor, eu_bins: Tensor, appearance: Optional[Tensor],
                     threshold: float = 0.5):
-        """Single-sub-field fast path: see iNGPField.fused_level."""
-        return self.fields[0].fused_level(origins, directions, eu_bins, appearance, threshold)
+        """Fast path of forward() + compositing: see iNGPField.fused_level (one sub-field) / fused.field_level_ms."""
+        if len(self.fields) == 1:
+            return self.fields[0].fused_level(origins, directions, eu_bins, appearance, threshold)
+        from .. import fused
+        grid = self._ms_meta()
+        params = []
+        for f in self.fields:
+            layers = [*f.mlp_base_mlp.layers, *f.semantic_head.layers, *f.rgb_head.layers]
+            params.append((f.mlp_base_grid.hash_table, [l.weight for l in layers], [l.bias for l in layers]))
+        return fused.field_level_ms(origins, directions, eu_bins, appearance, self.centroids,
+                                    self._aabbs_host(), self.fields[0].spatial_distortion is not None, grid, threshold,
+                                    params)
+
+    def _aabbs_host(self):
+        key = tuple(f.aabb.data_ptr() for f in self.fields) + tuple(f.aabb._version for f in self.fields)
+        if getattr(self, "_aabbs_cache", None) is None or self._aabbs_cache[0] != key:
+            self._aabbs_cache = (key, [list(f.aabb_host()) for f in self.fields])
+        return self._aabbs_cache[1]
 
     def density_fn(self, positions: Tensor) -> Tuple[Tensor, Tensor]:
         """ingp_field_ms.py:128-153."""
@@ -112,11 +159,48 @@ class PropNetDensityFieldMS(nn.Module):
         return self.density_fn(ray_samples.frustums.get_positions()), None
 
     def supports_fused(self) -> bool:
-        return len(self.fields) == 1
+        if len(self.fields) == 1:
+            return True
+        return self._ms_meta() is not None
+
+    def _ms_meta(self):
+        from .. import fused
+        f0 = self.fields[0]
+        if f0.use_linear:
+            return None
+        enc = f0.encoding
+        grid = fused.GridMeta(enc._scalings_host, enc.log2_hashmap_size, enc.features_per_level)
+        layers = list(f0.mlp_base[1].layers)
+        if not (fused.USE_TC5_PROP and len(layers) == 2 and layers[1].weight.shape[0] == 1
+                and all(l.bias is not None for l in layers)
+                and fused.tc5_ms_prop_supported(grid, layers[0].weight.shape[0], f0._precision)):
+            return None
+        for f in self.fields[1:]:
+            e = f.encoding
+            ls = None if f.use_linear else list(f.mlp_base[1].layers)
+            if (ls is None or tuple(e._scalings_host) != tuple(enc._scalings_host) or e.log2_hashmap_size != enc.log2_hashmap_size
+                    or e.features_per_level != enc.features_per_level or len(ls) != 2
+                    or ls[0].weight.shape != layers[0].weight.shape
+                    or (f.spatial_distortion is None) != (f0.spatial_distortion is None)):
+                return None
+        return grid
 
     def level_weights(self, origins: Tensor, directions: Tensor, eu_bins: Tensor) -> Tensor:
-        """Single-sub-field fast path (no routing needed): see PropNetDensityField.level_weights."""
-        return self.fields[0].level_weights(origins, directions, eu_bins)
+        """Fast path of `get_weights(density_fn(positions))`: PropNetDensityField.level_weights for one sub-field, the
+        sub-field mode of the fused proposal kernels (routing on the device) for several."""
+        if len(self.fields) == 1:
+            return self.fields[0].level_weights(origins, directions, eu_bins)
+        from .. import fused
+        grid = self._ms_meta()
+        params = []
+        for f in self.fields:
+            l0, l1 = list(f.mlp_base[1].layers)
+            params.append((f.encoding.hash_table, l0.weight, l0.bias, l1.weight, l1.bias))
+        key = tuple(f.aabb.data_ptr() for f in self.fields) + tuple(f.aabb._version for f in self.fields)
+        if getattr(self, "_aabbs_cache", None) is None or self._aabbs_cache[0] != key:
+            self._aabbs_cache = (key, [list(f.aabb_host()) for f in self.fields])
+        return fused.prop_level_weights_ms(origins, directions, eu_bins, self.centroids, self._aabbs_cache[1],
+                                           self.fields[0].spatial_distortion is not None, grid, params)
 
     def density_fn(self, positions: Tensor) -> Tensor:
         """prop_density_field_ms.py:86-105."""

@@ -543,6 +543,233 @@ def field_level(origins, dirs, eu_bins, app, table, aabb, contract, grid: GridMe
                              threshold, *flat)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# Sub-field mode: nearest-centroid routing folded into the level, on the device.  Reference routers:
+# fields/PreSight/ingp_field_ms.py:80-126, prop_density_field_ms.py:86-105.  One `route_points` per level groups the
+# level's points by sub-field (csrc/ms_route.cu, no host sync, static bounds); the fused tcgen05 kernels then run on
+# sub-field-homogeneous tiles with per-tile hash tables and per-sub-field weights (csrc/prop_tc5.cu, field_tc5_*.cu),
+# and the weights along the rays come from the one-pass compositing kernel.
+# ---------------------------------------------------------------------------------------------------------------
+MS_PAD = 256       # a sub-field's rows are padded to whole pairs of 128-row tiles
+
+
+@dataclass
+class Routing:
+    """A level's points in sub-field order."""
+    rows: int                 # static bound: P rounded up + nf * MS_PAD
+    perm: Tensor              # [rows] int32: row -> point, -1 = padding
+    tile_sf: Tensor           # [rows / 128] uint8: sub-field of each tile, 255 = unused
+    x01: Tensor               # [rows, 3] unit-cube positions (normalised by the row's sub-field's aabb)
+    sel: Tensor               # [rows] uint8 inside-the-cube flag
+    sf: Tensor                # [P] uint8 nearest centroid of every point (original order)
+
+
+def route_points(centroids: Tensor, aabbs_host: Sequence[Sequence[float]], contract: bool, origins: Optional[Tensor],
+                 dirs: Optional[Tensor], eu: Optional[Tensor], positions: Optional[Tensor] = None) -> Routing:
+    """Group the sample points of a level (ray mid-points of `eu`, or explicit `positions` [P,3]) by nearest centroid."""
+    nf = centroids.shape[0]
+    if positions is not None:
+        pos = _f32c(positions.detach()).view(-1, 3)
+        P, S, dev = pos.shape[0], 1, pos.device
+    else:
+        pos = None
+        N, S = eu.shape[0], eu.shape[1] - 1
+        P, dev = N * S, eu.device
+    rows = (P + MS_PAD - 1) // MS_PAD * MS_PAD + nf * MS_PAD
+    cen = _f32c(centroids.detach())
+    from ._lib import _device_table
+    sig = tuple(float(v) for b in aabbs_host for v in b)
+    boxes = _device_table((("aabbs", id(aabbs_host)), str(dev)), sig,
+                          lambda: torch.tensor(sig, dtype=torch.float32).view(nf, 6).to(dev))
+    counts = torch.zeros(2 * nf + 1 + nf, device=dev, dtype=torch.int32)      # counts | seg_start | cursors, one fill
+    seg_start, cursors = counts[nf:2 * nf + 1], counts[2 * nf + 1:]
+    sf = torch.empty(P, device=dev, dtype=torch.uint8)
+    perm = torch.full((rows,), -1, device=dev, dtype=torch.int32)
+    tile_sf = torch.empty(rows // 128, device=dev, dtype=torch.uint8)
+    x01 = torch.zeros(rows, 3, device=dev, dtype=torch.float32)
+    sel = torch.zeros(rows, device=dev, dtype=torch.uint8)
+    o, d, e = (None, None, None) if pos is not None else (ptr(origins), ptr(dirs), ptr(eu))
+    call("ps_ms_route", ptr(pos), o, d, e, P, S, ptr(cen), nf, ptr(sf), ptr(counts), stream())
+    call("ps_ms_plan", ptr(counts), nf, MS_PAD, 128, rows, ptr(seg_start), ptr(cursors), ptr(tile_sf), stream())
+    call("ps_ms_scatter", ptr(pos), o, d, e, P, S, ptr(sf), ptr(boxes), nf, 1 if contract else 0, ptr(cursors), ptr(perm),
+         ptr(x01), ptr(sel), stream())
+    return Routing(rows, perm, tile_sf, x01, sel, sf)
+
+
+def tc5_ms_prop_supported(grid: GridMeta, hidden: int, prec) -> bool:
+    return prec == ops.PREC_BF16 and grid.F in (1, 2) and grid.L * grid.F <= 16 and hidden in (16, 64)
+
+
+class _PropLevelMS(torch.autograd.Function):
+    """weights of one proposal level whose points are routed to nf sub-fields (prop_density_field_ms.py:86-105 +
+    rays.py:128-150).  params = per sub-field (table, W0, b0, W1, b1), flattened."""
+
+    @staticmethod
+    def forward(ctx, origins, dirs, eu_bins, centroids, aabbs_host, contract, grid: GridMeta, nf, *params):
+        from ._lib import PropNetDev, device_ptr_array, device_struct_array, load
+        o, d, eu = _f32c(origins.detach()), _f32c(dirs.detach()), _f32c(eu_bins.detach())
+        N, S = eu.shape[0], eu.shape[1] - 1
+        dev = eu.device
+        subs = [[t.detach() for t in params[5 * k:5 * k + 5]] for k in range(nf)]
+        rt = route_points(centroids, aabbs_host, contract, o, d, eu)
+        need_grad = any(ctx.needs_input_grad)
+        stride = int(load().ps_prop_level_feat_stride(grid.L, grid.F))
+        feat = torch.empty(rt.rows, stride, device=dev, dtype=torch.bfloat16) if need_grad else None
+        slot = ("prop", subs[0][0].data_ptr())
+        tables = device_ptr_array([s[0] for s in subs], dev, (slot, "tables"))
+        nets = device_struct_array([PropNetDev(s[1].data_ptr(), s[2].data_ptr(), s[3].data_ptr(), s[4].data_ptr(), 0, 0, 0, 0)
+                                    for s in subs], dev, (slot, "nets_fwd"))
+        hidden = subs[0][1].shape[0]
+        density = torch.zeros(N * S, device=dev, dtype=torch.float32)
+        with ops._probe(f"prop_level_fwd_ms_S{S}"):
+            call("ps_prop_level_fwd_ms", ptr(nets), hidden, ptr(rt.x01), ptr(rt.sel), ptr(rt.perm), ptr(rt.tile_sf), rt.rows,
+                 ptr(tables), host_floats(grid.scalings), grid.L, grid.F, grid.log2_T, ptr(density), ptr(feat), stream())
+        w = torch.empty(N, S, device=dev, dtype=torch.float32)
+        call("ps_composite_fwd", ptr(eu), ptr(density), None, None, N, S, 0, 0.5, ptr(w), None, None, None, None, None,
+             None, stream())
+        if need_grad:
+            ctx.save_for_backward(eu, density, feat, rt.perm, rt.tile_sf, rt.x01, rt.sel, *params)
+        ctx.meta = (grid, N, S, nf, rt.rows, hidden)
+        return w.view(N, S, 1)
+
+    @staticmethod
+    def backward(ctx, dw):
+        from ._lib import PropNetDev, device_ptr_array, device_struct_array
+        grid, N, S, nf, rows, hidden = ctx.meta
+        eu, density, feat, perm, tile_sf, x01, sel, *params = ctx.saved_tensors
+        dev = eu.device
+        subs = [[t.detach() for t in params[5 * k:5 * k + 5]] for k in range(nf)]
+        d_density = torch.empty(N * S, device=dev, dtype=torch.float32)
+        call("ps_composite_bwd", ptr(eu), ptr(density), None, None, None, None, None, N, S, 0,
+             ptr(_f32c(dw).view(N, S)), None, None, None, None, ptr(d_density), None, None, stream())
+        grads = _zeros_like_many([t for s in subs for t in s])            # one fill for every table / weight gradient
+        gsub = [grads[5 * k:5 * k + 5] for k in range(nf)]
+        slot = ("prop", subs[0][0].data_ptr())
+        dtables = device_ptr_array([g[0] for g in gsub], dev, (slot, "dtables"))
+        nets = device_struct_array([PropNetDev(s[1].data_ptr(), s[2].data_ptr(), s[3].data_ptr(), s[4].data_ptr(),
+                                               g[1].data_ptr(), g[2].data_ptr(), g[3].data_ptr(), g[4].data_ptr())
+                                    for s, g in zip(subs, gsub)], dev, (slot, "nets_bwd"))
+        with ops._probe(f"prop_level_bwd_ms_S{S}"):
+            call("ps_prop_level_bwd_ms", ptr(nets), hidden, ptr(x01), ptr(sel), ptr(perm), ptr(tile_sf), rows, ptr(dtables),
+                 host_floats(grid.scalings), grid.L, grid.F, grid.log2_T, ptr(feat), ptr(d_density), stream())
+        return (None, None, None, None, None, None, None, None, *grads)
+
+
+def prop_level_weights_ms(origins, dirs, eu_bins, centroids, aabbs_host, contract, grid: GridMeta, fields_params) -> Tensor:
+    """fields_params: per sub-field (table, W0, b0, W1, b1)."""
+    flat = [t for fp in fields_params for t in fp]
+    return _PropLevelMS.apply(origins, dirs, eu_bins, centroids, aabbs_host, contract, grid, len(fields_params), *flat)
+
+
+class _FieldLevelMS(torch.autograd.Function):
+    """Final level with nf routed sub-fields (ingp_field_ms.py:80-126 + nerfacto_nusc_ms.py:497-530): route -> per-tile
+    hash gather -> ONE fused field kernel (per-point density / rgb / semantics) -> one-pass compositing; backward:
+    compositing backward -> ONE fused field backward kernel -> per-tile hash scatter.
+    params = per sub-field (table, 8 weights, 8 biases), flattened."""
+
+    PER = 17
+
+    @staticmethod
+    def forward(ctx, origins, dirs, eu_bins, app, centroids, aabbs_host, contract, grid: GridMeta, threshold, nf, *params):
+        from ._lib import FieldNetDev, device_ptr_array, device_struct_array
+        o, d, eu = _f32c(origins.detach()), _f32c(dirs.detach()), _f32c(eu_bins.detach())
+        N, S = eu.shape[0], eu.shape[1] - 1
+        P, dev = N * S, eu.device
+        PER = _FieldLevelMS.PER
+        subs = [[t.detach() for t in params[PER * k:PER * (k + 1)]] for k in range(nf)]
+        A = 0 if app is None else app.shape[1]
+        app_c = None if app is None else _f32c(app.detach())
+        rt = route_points(centroids, aabbs_host, contract, o, d, eu)
+        slot = ("field", subs[0][0].data_ptr())
+        tables = device_ptr_array([s[0] for s in subs], dev, (slot, "tables"))
+        feat = torch.empty(rt.rows * grid.L * grid.F, device=dev, dtype=torch.float32)
+        with ops._probe(f"hash_fwd_ms_L{grid.L}F{grid.F}T{grid.log2_T}"):
+            call("ps_hash_fwd_ms", ptr(rt.x01), rt.rows, ptr(tables), ptr(rt.tile_sf), host_floats(grid.scalings), grid.L,
+                 grid.F, grid.log2_T, ptr(feat), stream())
+
+        def net_of(s, g=None):
+            n = FieldNetDev()
+            for i in range(8):
+                n.W[i], n.B[i] = s[1 + i].data_ptr(), s[9 + i].data_ptr()
+                n.dW[i] = 0 if g is None else g[1 + i].data_ptr()
+                n.dB[i] = 0 if g is None else g[9 + i].data_ptr()
+            n.in_dim, n.app_dim = grid.L * grid.F, A
+            return n
+        nets = device_struct_array([net_of(s) for s in subs], dev, (slot, "nets_fwd"))
+        density = torch.zeros(P, device=dev, dtype=torch.float32)
+        rgb_s = torch.empty(P, 3, device=dev, dtype=torch.float32)
+        sem_s = torch.empty(P, 64, device=dev, dtype=torch.float32)
+        with ops._probe("field_level_fwd_ms"):
+            call("ps_field_level_fwd_ms", ptr(nets), A, ptr(feat), grid.L, grid.F, ptr(rt.sel), ptr(rt.perm), ptr(rt.tile_sf),
+                 rt.rows, S, ptr(d), ptr(app_c), ptr(density), ptr(rgb_s), ptr(sem_s), stream())
+        w = torch.empty(N, S, device=dev, dtype=torch.float32)
+        rgb_out = torch.empty(N, 3, device=dev, dtype=torch.float32)
+        acc = torch.empty(N, 1, device=dev, dtype=torch.float32)
+        dexp = torch.empty(N, 1, device=dev, dtype=torch.float32)
+        dthr = torch.empty(N, 1, device=dev, dtype=torch.float32)
+        sem_out = torch.empty(N, 64, device=dev, dtype=torch.float32)
+        tmm = ops.new_tminmax(dev)
+        with ops._probe("composite_fwd"):
+            call("ps_composite_fwd", ptr(eu), ptr(density), ptr(rgb_s), ptr(sem_s), N, S, 64, float(threshold), ptr(w),
+                 ptr(rgb_out), ptr(acc), ptr(dexp), ptr(dthr), ptr(sem_out), ptr(tmm), stream())
+        saved = [eu, d, density, rgb_s, sem_s, acc, dexp, feat, rt.perm, rt.tile_sf, rt.x01, rt.sel]
+        if app_c is not None:
+            saved.append(app_c)
+        ctx.n_fixed = len(saved)
+        ctx.save_for_backward(*saved, *params)
+        ctx.meta = (grid, N, S, A, nf, rt.rows, app is not None and app.requires_grad)
+        ctx.net_of = net_of
+        ctx.mark_non_differentiable(dthr, tmm)
+        ctx.set_materialize_grads(False)
+        return w.view(N, S, 1), rgb_out, acc, dexp, dthr, sem_out, tmm
+
+    @staticmethod
+    def backward(ctx, dw, drgb, dacc, ddexp, _dthr, dsem, _dtmm):
+        from ._lib import device_ptr_array, device_struct_array
+        grid, N, S, A, nf, rows, app_grad = ctx.meta
+        saved = list(ctx.saved_tensors)
+        eu, d, density, rgb_s, sem_s, acc, dexp, feat, perm, tile_sf, x01, sel = saved[:12]
+        app_c = saved[12] if A else None
+        params = saved[ctx.n_fixed:]
+        PER = _FieldLevelMS.PER
+        P, dev = N * S, eu.device
+        subs = [[t.detach() for t in params[PER * k:PER * (k + 1)]] for k in range(nf)]
+
+        def opt(t, shape=None):
+            if t is None:
+                return None
+            t = _f32c(t)
+            return t if shape is None else t.view(shape)
+        d_density = torch.empty(P, device=dev, dtype=torch.float32)
+        d_rgb_s = torch.empty(P, 3, device=dev, dtype=torch.float32)
+        d_sem_s = torch.empty(P, 64, device=dev, dtype=torch.float32)
+        with ops._probe("composite_bwd"):
+            call("ps_composite_bwd", ptr(eu), ptr(density), ptr(rgb_s), ptr(sem_s), None, ptr(acc), ptr(dexp), N, S, 64,
+                 ptr(opt(dw, (N, S))), ptr(opt(drgb)), ptr(opt(dacc)), ptr(opt(ddexp)), ptr(opt(dsem)), ptr(d_density),
+                 ptr(d_rgb_s), ptr(d_sem_s), stream())
+        grads = _zeros_like_many([t for s in subs for t in s])
+        gsub = [grads[PER * k:PER * (k + 1)] for k in range(nf)]
+        slot = ("field", subs[0][0].data_ptr())
+        nets = device_struct_array([ctx.net_of(s, g) for s, g in zip(subs, gsub)], dev, (slot, "nets_bwd"))
+        dapp = torch.zeros(N, A, device=dev, dtype=torch.float32) if (A and app_grad) else None
+        dfeat = torch.empty_like(feat)
+        with ops._probe("field_level_bwd_ms"):
+            call("ps_field_level_bwd_ms", ptr(nets), A, ptr(feat), grid.L, grid.F, ptr(sel), ptr(perm), ptr(tile_sf), rows, S,
+                 ptr(d), ptr(app_c), ptr(d_density), ptr(d_rgb_s), ptr(d_sem_s), ptr(dfeat), ptr(dapp), stream())
+        dtables = device_ptr_array([g[0] for g in gsub], dev, (slot, "dtables"))
+        with ops._probe(f"hash_bwd_ms_L{grid.L}F{grid.F}T{grid.log2_T}"):
+            call("ps_hash_bwd_ms", ptr(x01), rows, ptr(dtables), ptr(tile_sf), ptr(perm), host_floats(grid.scalings), grid.L,
+                 grid.F, grid.log2_T, ptr(dfeat), stream())
+        return (None, None, None, dapp, None, None, None, None, None, None, *grads)
+
+
+def field_level_ms(origins, dirs, eu_bins, app, centroids, aabbs_host, contract, grid: GridMeta, threshold, fields_params):
+    """fields_params: per sub-field (table, [8 weights], [8 biases]) in the layer order base0, base1, sem0..2, rgb0..2."""
+    flat = [t for (tab, ws, bs) in fields_params for t in (tab, *ws, *bs)]
+    return _FieldLevelMS.apply(origins, dirs, eu_bins, app, centroids, aabbs_host, contract, grid, threshold,
+                               len(fields_params), *flat)
+
+
 @torch.no_grad()
 def query_priors(points_scaled: Tensor, prop_fields, field) -> Tuple[Tensor, Tensor]:
     """Dense prior query for one sub-field (scripts/extract_priors.py:130-138): mean of the proposal and field

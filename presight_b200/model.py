@@ -443,7 +443,7 @@ class NerfactoNuscMSModel(nn.Module):
     @torch.no_grad()
     def query_priors(self, points_scaled: Tensor) -> Tuple[Tensor, Tensor]:
         """scripts/extract_priors.py:130-138: mean density over proposal nets + field, clipped fp16 semantics."""
-        if self.use_fused and self.field.supports_fused() and self.config.use_semantics:
+        if self.use_fused and len(self.field.fields) == 1 and self.field.supports_fused() and self.config.use_semantics:
             from . import fused
             return fused.query_priors(points_scaled, [p.fields[0] for p in self.proposal_networks],
                                       self.field.fields[0])

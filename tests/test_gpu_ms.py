@@ -1,0 +1,165 @@
+"""Sub-field mode: nearest-centroid routing on the device and the fused tcgen05 level kernels on
+sub-field-homogeneous tiles, with 16 sub-fields (PreSight's `num_aabbs`), against the oracle's restatement of the
+reference routers (fields/PreSight/ingp_field_ms.py:80-126, prop_density_field_ms.py:86-105) and against the modular
+path (device sort + one launch set per sub-field).  Through the C-ABI."""
+import os
+import sys
+
+import pytest
+import torch
+
+import oracle as O
+from helpers import assert_close
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+NF = 16
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def test_routing_kernels_partition_points():
+    """ps_ms_route / ps_ms_plan / ps_ms_scatter: sub-field = nearest centroid (first minimum), every point appears in
+    exactly one row of its own sub-field's segment, segments are padded to whole 256-row pairs, and the sorted unit-cube
+    positions / selectors are bit-identical to ps_normalize_positions with the row's sub-field's aabb."""
+    from presight_b200 import fused, ops, synthetic
+    cen, aabbs = synthetic.sub_field_layout(NF)
+    host = synthetic.make_rays(777, seed=3)
+    g = torch.Generator().manual_seed(0)
+    S = 48
+    eu = torch.sort(torch.rand(777, S + 1, generator=g) * 30.0, dim=1).values.to(DEV)
+    o, d = host["origins"].to(DEV), host["directions"].to(DEV)
+    aabbs_host = [[float(v) for v in b.reshape(-1)] for b in aabbs]
+    rt = fused.route_points(cen.to(DEV), aabbs_host, True, o, d, eu)
+    P = 777 * S
+    pos = ops.sample_positions(o, d, eu).view(-1, 3)
+    want_sf = O.nearest_centroid(pos.cpu(), cen)
+    assert torch.equal(rt.sf.cpu().long(), want_sf.long())
+    perm = rt.perm.cpu().long()
+    used = perm >= 0
+    assert int(used.sum()) == P and torch.equal(torch.sort(perm[used]).values, torch.arange(P))      # a permutation
+    tile_sf = rt.tile_sf.cpu().long()
+    row_sf = tile_sf.repeat_interleave(128)
+    assert torch.equal(row_sf[used], want_sf.long()[perm[used]])                         # rows sit in their own segment
+    assert bool((row_sf[~used] == 255).logical_or(row_sf[~used] < NF).all())
+    live = tile_sf[tile_sf != 255]
+    assert bool((live[1:] >= live[:-1]).all()) and len(live) % 2 == 0                    # ascending, whole pairs
+    assert rt.rows % 256 == 0 and rt.rows >= P
+    for k in range(NF):
+        rows_k = torch.nonzero(used & (row_sf == k)).flatten()
+        if len(rows_k) == 0:
+            continue
+        x01, sel = ops.normalize_positions(pos[perm[rows_k].to(DEV)], aabbs_host[k], True)
+        assert torch.equal(rt.x01[rows_k.to(DEV)], x01) and torch.equal(rt.sel[rows_k.to(DEV)], sel.view(-1))
+
+
+def build(n_rays, log2_T=14, impl="b200"):
+    from presight_b200 import synthetic
+    from presight_b200.model import NerfactoNuscMSModel
+    cfg = synthetic.config_presight(impl)
+    cfg.log2_hashmap_size = log2_T                         # small tables: the CPU oracle runs 16 sub-fields
+    for a in cfg.proposal_net_args_list:
+        a["log2_hashmap_size"] = log2_T
+    torch.manual_seed(1)
+    host = synthetic.make_rays(n_rays, seed=5)
+    cen, aabbs = synthetic.sub_field_layout(NF)
+    model = NerfactoNuscMSModel(cfg, cen, aabbs, host["n_cameras"], host["n_videos"])
+    with torch.no_grad():
+        for f in model.field.fields:
+            f.mlp_base_grid.hash_table.mul_(300.0)
+        for p in model.proposal_networks:
+            for f in p.fields:
+                f.encoding.hash_table.mul_(300.0)
+    return model.to(DEV).train(), cfg, host
+
+
+def forward_backward(model, cfg, host, jit):
+    from presight_b200 import losses
+    from presight_b200.cameras.rays import RayBundle
+    from presight_b200.model import VIDEO_ID
+    for p in model.parameters():
+        p.grad = None
+    rb = RayBundle(origins=host["origins"].to(DEV), directions=host["directions"].to(DEV),
+                   camera_indices=host["camera_indices"].to(DEV), metadata={VIDEO_ID: host["video_ids"].to(DEV)})
+    model.proposal_sampler._step = 0
+    out = model(rb, jitters=[j.to(DEV) for j in jit])
+    loss = ((out["rgb"] - host["rgb"].to(DEV)) ** 2).mean() \
+        + 0.5 * ((out["semantics"] - host["features"].to(DEV).clip(0, 1)) ** 2).mean() \
+        + losses.interlevel_loss(out["weights_list"], [rs.sp_bins for rs in out["ray_samples_list"]])
+    loss.backward()
+    return out, loss
+
+
+def test_presight_shape_fused_matches_oracle_and_modular():
+    """16 sub-fields, L10 F4 main grids, 128/64/64 samples: the model on the sub-field mode of the fused kernels (asserted)
+    against (a) the CPU oracle on the same weights / rays / jitters at the bf16 tolerances and (b) the modular path."""
+    from presight_b200 import fused, ops
+    n = 384
+    model, cfg, host = build(n)
+    assert len(model.field.fields) == NF and model.field.supports_fused() and model.proposal_networks[0].supports_fused()
+    g = torch.Generator().manual_seed(3)
+    jit = [torch.rand(n, 1, generator=g) for _ in range(3)]
+    ops.PROBE = ops.KernelProbe()
+    out, loss = forward_backward(model, cfg, host, jit)
+    names = set(ops.PROBE.summary())
+    ops.PROBE = None
+    assert {"field_level_fwd_ms", "field_level_bwd_ms", "prop_level_fwd_ms_S128", "prop_level_bwd_ms_S64"} <= names, names
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+
+    # (a) oracle
+    omodel, emb = bench.oracle_model_from(model, cfg)
+    app = torch.cat([emb["appearance_embedding.embedding.weight"][host["camera_indices"][:, 0]],
+                     emb["video_embedding.embedding.weight"][host["video_ids"][:, 0]]], dim=-1)
+    oo = O.model_outputs(omodel, host["origins"], host["directions"], app, jit)
+    oloss = O.rgb_loss(host["rgb"], oo["rgb"]) + 0.5 * O.semantic_loss(oo["semantics"], host["features"]) \
+        + O.interlevel_loss(oo["weights_list"], [b[0] for b in oo["bins_list"]])
+    oloss.backward()
+    assert_close(loss.detach().cpu(), oloss.detach(), 1e-2, "loss")
+    for k in ("rgb", "accumulation", "expected_depth", "semantics"):
+        assert_close(out[k].detach().cpu(), oo[k], 1e-2, k)
+    assert_close(out["weights_list"][0].detach().cpu(), oo["weights_list"][0], 1e-2, "weights 0")
+    checked = 0
+    for i in range(NF):
+        gt = omodel.fields[i].grid.table.grad
+        if gt is not None and float(gt.abs().max()) > 0:
+            assert rel_l2(grads[f"field.fields.{i}.mlp_base_grid.hash_table"].cpu(), gt) < 5e-2, f"main table {i}"
+            checked += 1
+        gp = omodel.props[0][i].grid.table.grad
+        if gp is not None and float(gp.abs().max()) > 0:
+            assert rel_l2(grads[f"proposal_networks.0.fields.{i}.encoding.hash_table"].cpu(), gp) < 5e-2, f"prop table {i}"
+        gw = omodel.fields[i].rgb.weights[0].grad
+        if gw is not None and float(gw.abs().max()) > 0:
+            assert rel_l2(grads[f"field.fields.{i}.rgb_head.layers.0.weight"].cpu(), gw) < 5e-2, f"rgb weight {i}"
+            assert rel_l2(grads[f"field.fields.{i}.semantic_head.layers.2.bias"].cpu(), omodel.fields[i].sem.biases[2].grad) < 5e-2
+    assert checked >= 4, "the synthetic rays should reach several sub-fields"
+
+    # (b) modular path (device sort, per-sub-field launches): same model, fused paths off
+    model.use_fused = False
+    model.proposal_sampler.use_fused = False
+    out_m, loss_m = forward_backward(model, cfg, host, jit)
+    assert_close(loss.detach(), loss_m.detach(), 1e-2, "loss vs modular")
+    for k in ("rgb", "accumulation", "semantics"):
+        assert_close(out[k].detach(), out_m[k].detach(), 1e-2, k + " vs modular")
+
+
+def test_sub_field_mode_is_sync_free_in_steady_state():
+    """After the first steps have uploaded the pointer tables, a training step makes no pageable host->device copy for
+    them (the tables are cached by address) — the routing itself never reads anything back."""
+    from presight_b200 import _lib
+    n = 256
+    model, cfg, host = build(n, log2_T=12)
+    g = torch.Generator().manual_seed(3)
+    jit = [torch.rand(n, 1, generator=g) for _ in range(3)]
+    for _ in range(3):
+        forward_backward(model, cfg, host, jit)
+    before = {k: v[0] for k, v in _lib._DEV_TABLES.items()}
+    forward_backward(model, cfg, host, jit)
+    after = {k: v[0] for k, v in _lib._DEV_TABLES.items()}
+    changed = [k for k in after if before.get(k) != after[k]]
+    assert len(changed) <= 2, f"device tables re-uploaded in steady state: {changed}"
