@@ -388,12 +388,13 @@ int ps_prop_level_bwd(const ps_prop_net* net, const float* origins, const float*
  * boolean-mask gather, a field call, a masked scatter and a `torch.any` host sync) without any host synchronisation:
  *
  *   ps_ms_route    every point (positions [P,3], or ray sample mid-points from origins / dirs [N,3] + eu_bins [N,S+1] with
- *                  P = N*S) -> sf_out [P] = index of the nearest centroid (first minimum), counts [nf] += points per
- *                  sub-field (caller-zeroed).  centroids [nf,3] on the device.
- *   ps_ms_plan     counts -> seg_start [nf+1] (segments padded to multiples of `pad` rows), cursors [nf] = seg_start,
- *                  tile_sf [max_rows / tile_rows] = sub-field of every tile of `tile_rows` rows, 255 past the last segment.
- *   ps_ms_scatter  every point -> a row of its sub-field's segment (order inside a segment is arbitrary):
- *                  perm[row] = point (caller presets perm to -1 = padding), x01_sorted [max_rows,3] = unit-cube position
+ *                  P = N*S) -> sf_out [P] = index of the nearest centroid (first minimum), block_hist [ceil(P/256), nf] =
+ *                  points per sub-field of every block of 256 consecutive points.  centroids [nf,3] on the device.
+ *   ps_ms_plan     block_hist -> (in place) first row of every (block, sub-field); seg_start [nf+1] (segments padded to
+ *                  multiples of `pad` rows); tile_sf [max_rows / tile_rows] = sub-field of every tile of `tile_rows` rows,
+ *                  255 past the last segment.
+ *   ps_ms_scatter  every point -> its row of its sub-field's segment (a STABLE counting sort: the original order is kept
+ *                  inside a segment, the result is deterministic): perm[row] = point (caller presets perm to -1 = padding), x01_sorted [max_rows,3] = unit-cube position
  *                  normalised by THAT sub-field's aabb (aabbs [nf,6] on the device: min xyz, max xyz;
  *                  fields/PreSight/utils.py:6-10 + the L-inf contraction), sel_sorted [max_rows] = inside-the-cube flag.
  *   max_rows >= P + nf * pad is a static bound, so nothing has to be read back.
@@ -419,11 +420,11 @@ typedef struct ps_field_net_dev {
     int app_dim;
 } ps_field_net_dev;
 int ps_ms_route(const float* positions, const float* origins, const float* dirs, const float* eu_bins, int64_t P, int S,
-                const float* centroids, int nf, uint8_t* sf_out, int32_t* counts, void* stream);
-int ps_ms_plan(const int32_t* counts, int nf, int pad, int tile_rows, int64_t max_rows, int32_t* seg_start, int32_t* cursors,
+                const float* centroids, int nf, uint8_t* sf_out, int32_t* block_hist, void* stream);
+int ps_ms_plan(int32_t* block_hist, int64_t P, int nf, int pad, int tile_rows, int64_t max_rows, int32_t* seg_start,
                uint8_t* tile_sf, void* stream);
 int ps_ms_scatter(const float* positions, const float* origins, const float* dirs, const float* eu_bins, int64_t P, int S,
-                  const uint8_t* sf, const float* aabbs, int nf, int contract, int32_t* cursors, int32_t* perm,
+                  const uint8_t* sf, const float* aabbs, int nf, int contract, const int32_t* block_off, int32_t* perm,
                   float* x01_sorted, uint8_t* sel_sorted, void* stream);
 int ps_hash_fwd_ms(const float* x01_sorted, int64_t rows, const float* const* tables, const uint8_t* tile_sf,
                    const float* scalings_host, int L, int F, int log2_T, float* out, void* stream);

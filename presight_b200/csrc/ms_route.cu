@@ -3,10 +3,14 @@
 //   masked scatter per sub-field, a `torch.any` host sync each), prop_density_field_ms.py:86-105
 // as three small kernels with no host synchronisation, feeding the sub-field-homogeneous point tiles of the fused level
 // kernels (prop_tc5_ms.cu / field_tc5_ms.cu):
-//   1. route    every sample point -> nearest centroid (uint8) + per-sub-field counts
-//   2. plan     counts -> segment starts padded to whole tiles, write cursors, tile -> sub-field table
-//   3. scatter  every point -> its slot in its sub-field's segment: perm[slot] = point, unit-cube position normalised
+//   1. route    every sample point -> nearest centroid (uint8) + a histogram per block of 256 points
+//   2. plan     block histograms -> segment starts padded to whole tiles, the first row of every (block, sub-field),
+//               tile -> sub-field table
+//   3. scatter  every point -> its row in its sub-field's segment: perm[row] = point, unit-cube position normalised
 //               with THAT sub-field's aabb (fields/PreSight/utils.py:6-10 + contraction) and the in-box selector
+// The sort is STABLE (a counting sort with per-block offsets and in-block ranks): inside a sub-field's segment the
+// points keep their original order, so consecutive samples of a ray stay neighbours — that is what the warp
+// pre-aggregation of the hash scatter-add and the gather's cache locality live on — and the result is deterministic.
 // A level's points are then P_pad <= P + nf * pad rows in sub-field order; row -> point through perm (-1 = padding).
 #include "position.cuh"
 
@@ -28,22 +32,31 @@ __device__ __forceinline__ void point_of(const float* __restrict__ positions, co
     frustum_midpoint(o, d, __ldg(eu + ray * (S + 1) + s), __ldg(eu + ray * (S + 1) + s + 1), x);
 }
 
-// warp-aggregated counter increment: lanes that hit the same counter send one atomic; returns this lane's slot
-__device__ __forceinline__ int aggregated_inc(int32_t* counters, int key, bool active) {
-    const unsigned peers = __match_any_sync(0xffffffffu, active ? key : -1 - (int)(threadIdx.x & 31));
-    int base = 0;
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(peers) - 1;
-    if (active && lane == leader) base = atomicAdd(counters + key, __popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    return base + __popc(peers & ((1u << lane) - 1u));
+constexpr int kRouteThreads = 256;
+
+// rank of this thread among the threads of its block with the same key, in thread order (all threads must call);
+// also returns the block's count of that key through `hist` (shared, [kMaxSub], zeroed by the caller before the call)
+__device__ __forceinline__ int block_rank(int key, bool active, int32_t (*warp_hist)[kMaxSub], int nf) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned peers = __match_any_sync(0xffffffffu, active ? key : -1 - lane);
+    const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+    for (int k = lane; k < nf; k += 32) warp_hist[warp][k] = 0;
+    __syncwarp();
+    if (active && rank_in_warp == 0) warp_hist[warp][key] = __popc(peers);
+    __syncthreads();
+    int before = 0;
+    if (active)
+        for (int w = 0; w < warp; ++w) before += warp_hist[w][key];
+    return before + rank_in_warp;
 }
 
-__global__ void __launch_bounds__(256) ms_route_kernel(const float* __restrict__ positions, const float* __restrict__ origins,
-                                                       const float* __restrict__ dirs, const float* __restrict__ eu,
-                                                       int64_t P, int S, const float* __restrict__ cent, int nf,
-                                                       uint8_t* __restrict__ sf_out, int32_t* __restrict__ counts) {
+__global__ void __launch_bounds__(kRouteThreads) ms_route_kernel(const float* __restrict__ positions,
+                                                                 const float* __restrict__ origins,
+                                                                 const float* __restrict__ dirs, const float* __restrict__ eu,
+                                                                 int64_t P, int S, const float* __restrict__ cent, int nf,
+                                                                 uint8_t* __restrict__ sf_out, int32_t* __restrict__ block_hist) {
     __shared__ float c[kMaxSub][3];
+    __shared__ int32_t warp_hist[kRouteThreads / 32][kMaxSub];
     for (int i = threadIdx.x; i < nf * 3; i += blockDim.x) c[i / 3][i % 3] = cent[i];
     __syncthreads();
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,27 +73,50 @@ __global__ void __launch_bounds__(256) ms_route_kernel(const float* __restrict__
         }
         sf_out[p] = (uint8_t)arg;
     }
-    aggregated_inc(counts, arg, on);
+    block_rank(arg, on, warp_hist, nf);
+    for (int k = threadIdx.x; k < nf; k += blockDim.x) {
+        int32_t tot = 0;
+        for (int w = 0; w < kRouteThreads / 32; ++w) tot += warp_hist[w][k];
+        block_hist[(int64_t)blockIdx.x * nf + k] = tot;
+    }
 }
 
-// one CTA: padded segment starts, cursors, tile -> sub-field table (255 = beyond the last segment)
-__global__ void __launch_bounds__(256) ms_plan_kernel(const int32_t* __restrict__ counts, int nf, int pad, int tile_rows,
-                                                      int64_t max_rows, int32_t* __restrict__ seg_start,
-                                                      int32_t* __restrict__ cursors, uint8_t* __restrict__ tile_sf) {
+// one CTA: per-sub-field totals and the exclusive scan of the block histograms (block_hist is overwritten by the first
+// row of every (block, sub-field)), padded segment starts, tile -> sub-field table (255 = beyond the last segment)
+__global__ void __launch_bounds__(1024) ms_plan_kernel(int32_t* __restrict__ block_hist, int64_t nblocks, int nf, int pad,
+                                                       int tile_rows, int64_t max_rows, int32_t* __restrict__ seg_start,
+                                                       uint8_t* __restrict__ tile_sf) {
+    __shared__ int32_t part[1024];
     __shared__ int32_t start[kMaxSub + 1];
-    if (threadIdx.x == 0) {
-        int32_t acc = 0;
-        for (int k = 0; k < nf; ++k) {
-            start[k] = acc;
-            acc += (counts[k] + pad - 1) / pad * pad;
+    const int tid = threadIdx.x;
+    const int64_t chunk = (nblocks + blockDim.x - 1) / blockDim.x;
+    const int64_t b0 = (int64_t)tid * chunk, b1 = b0 + chunk < nblocks ? b0 + chunk : nblocks;
+    if (tid == 0) start[0] = 0;
+    for (int k = 0; k < nf; ++k) {
+        int32_t sum = 0;
+        for (int64_t b = b0; b < b1; ++b) sum += block_hist[b * nf + k];
+        part[tid] = sum;
+        __syncthreads();
+        // inclusive scan of the per-thread partial sums (Hillis-Steele over 1024 entries)
+        for (int o = 1; o < 1024; o <<= 1) {
+            const int32_t v = tid >= o ? part[tid - o] : 0;
+            __syncthreads();
+            part[tid] += v;
+            __syncthreads();
         }
-        start[nf] = acc;
-        for (int k = 0; k <= nf; ++k) seg_start[k] = start[k];
-        for (int k = 0; k < nf; ++k) cursors[k] = start[k];
+        const int32_t total = part[1023];
+        int32_t run = start[k] + part[tid] - sum;                   // first row of this thread's first block
+        for (int64_t b = b0; b < b1; ++b) {
+            const int32_t cnt = block_hist[b * nf + k];
+            block_hist[b * nf + k] = run;
+            run += cnt;
+        }
+        if (tid == 0) start[k + 1] = start[k] + (total + pad - 1) / pad * pad;
+        __syncthreads();
     }
-    __syncthreads();
+    for (int k = tid; k <= nf; k += blockDim.x) seg_start[k] = start[k];
     const int64_t ntiles = max_rows / tile_rows;
-    for (int64_t t = threadIdx.x; t < ntiles; t += blockDim.x) {
+    for (int64_t t = tid; t < ntiles; t += blockDim.x) {
         const int64_t row = t * tile_rows;
         int sf = 255;
         for (int k = 0; k < nf; ++k)
@@ -93,13 +129,14 @@ struct SubBoxes {
     Aabb box[kMaxSub];
 };
 
-__global__ void __launch_bounds__(256) ms_scatter_kernel(const float* __restrict__ positions, const float* __restrict__ origins,
+__global__ void __launch_bounds__(kRouteThreads) ms_scatter_kernel(const float* __restrict__ positions, const float* __restrict__ origins,
                                                          const float* __restrict__ dirs, const float* __restrict__ eu,
                                                          int64_t P, int S, const uint8_t* __restrict__ sf_in,
                                                          const float* __restrict__ aabbs, int nf, int contract,
-                                                         int32_t* __restrict__ cursors, int32_t* __restrict__ perm,
+                                                         const int32_t* __restrict__ block_off, int32_t* __restrict__ perm,
                                                          float* __restrict__ x01s, uint8_t* __restrict__ sels) {
     __shared__ Aabb boxes[kMaxSub];
+    __shared__ int32_t warp_hist[kRouteThreads / 32][kMaxSub];
     for (int i = threadIdx.x; i < nf * 6; i += blockDim.x) {
         const int k = i / 6, j = i % 6;
         if (j < 3) boxes[k].lo[j] = aabbs[i]; else boxes[k].hi[j - 3] = aabbs[i];
@@ -108,8 +145,9 @@ __global__ void __launch_bounds__(256) ms_scatter_kernel(const float* __restrict
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool on = p < P;
     const int sf = on ? sf_in[p] : 0;
-    const int slot = aggregated_inc(cursors, sf, on);
+    const int rank = block_rank(sf, on, warp_hist, nf);
     if (!on) return;
+    const int slot = block_off[(int64_t)blockIdx.x * nf + sf] + rank;
     float x[3];
     point_of(positions, origins, dirs, eu, p, S, x);
     const bool inside = normalize_point(x, boxes[sf], contract != 0);
@@ -125,35 +163,38 @@ __global__ void __launch_bounds__(256) ms_scatter_kernel(const float* __restrict
 using namespace ps;
 
 extern "C" int ps_ms_route(const float* positions, const float* origins, const float* dirs, const float* eu_bins, int64_t P,
-                           int S, const float* centroids, int nf, uint8_t* sf_out, int32_t* counts, void* stream) {
+                           int S, const float* centroids, int nf, uint8_t* sf_out, int32_t* block_hist, void* stream) {
     if (P == 0) return 0;
     PS_REQUIRE(nf >= 1 && nf <= kMaxSub, "ms_route: %d sub-fields outside [1, %d]", nf, kMaxSub);
-    PS_REQUIRE(centroids && sf_out && counts, "ms_route: null pointer");
+    PS_REQUIRE(centroids && sf_out && block_hist, "ms_route: null pointer");
     PS_REQUIRE(positions != nullptr || (origins && dirs && eu_bins && S >= 1), "ms_route: give positions or rays + bins");
     PS_REQUIRE(P < (1ll << 31), "ms_route: too many points");
-    ms_route_kernel<<<(unsigned)cdiv(P, 256), 256, 0, (cudaStream_t)stream>>>(positions, origins, dirs, eu_bins, P, S,
-                                                                            centroids, nf, sf_out, counts);
+    ms_route_kernel<<<(unsigned)cdiv(P, kRouteThreads), kRouteThreads, 0, (cudaStream_t)stream>>>(
+        positions, origins, dirs, eu_bins, P, S, centroids, nf, sf_out, block_hist);
     return check_launch("ms_route");
 }
 
-extern "C" int ps_ms_plan(const int32_t* counts, int nf, int pad, int tile_rows, int64_t max_rows, int32_t* seg_start,
-                          int32_t* cursors, uint8_t* tile_sf, void* stream) {
-    PS_REQUIRE(counts && seg_start && cursors && tile_sf, "ms_plan: null pointer");
+extern "C" int ps_ms_plan(int32_t* block_hist, int64_t P, int nf, int pad, int tile_rows, int64_t max_rows,
+                          int32_t* seg_start, uint8_t* tile_sf, void* stream) {
+    PS_REQUIRE(block_hist && seg_start && tile_sf, "ms_plan: null pointer");
     PS_REQUIRE(nf >= 1 && nf <= kMaxSub, "ms_plan: %d sub-fields outside [1, %d]", nf, kMaxSub);
     PS_REQUIRE(tile_rows >= 1 && pad >= tile_rows && pad % tile_rows == 0 && max_rows % tile_rows == 0,
                "ms_plan: pad %d must be a multiple of the tile (%d rows) and max_rows a multiple of the tile", pad, tile_rows);
-    ms_plan_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(counts, nf, pad, tile_rows, max_rows, seg_start, cursors, tile_sf);
+    PS_REQUIRE(max_rows >= (P + pad - 1) / pad * pad + (int64_t)nf * pad, "ms_plan: max_rows %lld too small for %lld points",
+               (long long)max_rows, (long long)P);
+    ms_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(block_hist, cdiv(P, kRouteThreads), nf, pad, tile_rows, max_rows,
+                                                        seg_start, tile_sf);
     return check_launch("ms_plan");
 }
 
 extern "C" int ps_ms_scatter(const float* positions, const float* origins, const float* dirs, const float* eu_bins, int64_t P,
-                             int S, const uint8_t* sf, const float* aabbs, int nf, int contract, int32_t* cursors,
+                             int S, const uint8_t* sf, const float* aabbs, int nf, int contract, const int32_t* block_off,
                              int32_t* perm, float* x01_sorted, uint8_t* sel_sorted, void* stream) {
     if (P == 0) return 0;
-    PS_REQUIRE(sf && aabbs && cursors && perm && x01_sorted && sel_sorted, "ms_scatter: null pointer");
+    PS_REQUIRE(sf && aabbs && block_off && perm && x01_sorted && sel_sorted, "ms_scatter: null pointer");
     PS_REQUIRE(nf >= 1 && nf <= kMaxSub, "ms_scatter: %d sub-fields outside [1, %d]", nf, kMaxSub);
     PS_REQUIRE(positions != nullptr || (origins && dirs && eu_bins && S >= 1), "ms_scatter: give positions or rays + bins");
-    ms_scatter_kernel<<<(unsigned)cdiv(P, 256), 256, 0, (cudaStream_t)stream>>>(
-        positions, origins, dirs, eu_bins, P, S, sf, aabbs, nf, contract, cursors, perm, x01_sorted, sel_sorted);
+    ms_scatter_kernel<<<(unsigned)cdiv(P, kRouteThreads), kRouteThreads, 0, (cudaStream_t)stream>>>(
+        positions, origins, dirs, eu_bins, P, S, sf, aabbs, nf, contract, block_off, perm, x01_sorted, sel_sorted);
     return check_launch("ms_scatter");
 }

@@ -581,17 +581,17 @@ def route_points(centroids: Tensor, aabbs_host: Sequence[Sequence[float]], contr
     sig = tuple(float(v) for b in aabbs_host for v in b)
     boxes = _device_table((("aabbs", id(aabbs_host)), str(dev)), sig,
                           lambda: torch.tensor(sig, dtype=torch.float32).view(nf, 6).to(dev))
-    counts = torch.zeros(2 * nf + 1 + nf, device=dev, dtype=torch.int32)      # counts | seg_start | cursors, one fill
-    seg_start, cursors = counts[nf:2 * nf + 1], counts[2 * nf + 1:]
+    block_hist = torch.empty((P + 255) // 256 * nf, device=dev, dtype=torch.int32)
+    seg_start = torch.empty(nf + 1, device=dev, dtype=torch.int32)
     sf = torch.empty(P, device=dev, dtype=torch.uint8)
     perm = torch.full((rows,), -1, device=dev, dtype=torch.int32)
     tile_sf = torch.empty(rows // 128, device=dev, dtype=torch.uint8)
     x01 = torch.zeros(rows, 3, device=dev, dtype=torch.float32)
     sel = torch.zeros(rows, device=dev, dtype=torch.uint8)
     o, d, e = (None, None, None) if pos is not None else (ptr(origins), ptr(dirs), ptr(eu))
-    call("ps_ms_route", ptr(pos), o, d, e, P, S, ptr(cen), nf, ptr(sf), ptr(counts), stream())
-    call("ps_ms_plan", ptr(counts), nf, MS_PAD, 128, rows, ptr(seg_start), ptr(cursors), ptr(tile_sf), stream())
-    call("ps_ms_scatter", ptr(pos), o, d, e, P, S, ptr(sf), ptr(boxes), nf, 1 if contract else 0, ptr(cursors), ptr(perm),
+    call("ps_ms_route", ptr(pos), o, d, e, P, S, ptr(cen), nf, ptr(sf), ptr(block_hist), stream())
+    call("ps_ms_plan", ptr(block_hist), P, nf, MS_PAD, 128, rows, ptr(seg_start), ptr(tile_sf), stream())
+    call("ps_ms_scatter", ptr(pos), o, d, e, P, S, ptr(sf), ptr(boxes), nf, 1 if contract else 0, ptr(block_hist), ptr(perm),
          ptr(x01), ptr(sel), stream())
     return Routing(rows, perm, tile_sf, x01, sel, sf)
 
@@ -768,6 +768,68 @@ def field_level_ms(origins, dirs, eu_bins, app, centroids, aabbs_host, contract,
     flat = [t for (tab, ws, bs) in fields_params for t in (tab, *ws, *bs)]
     return _FieldLevelMS.apply(origins, dirs, eu_bins, app, centroids, aabbs_host, contract, grid, threshold,
                                len(fields_params), *flat)
+
+
+@torch.no_grad()
+def query_priors_ms(points_scaled: Tensor, prop_routers, field_router) -> Tuple[Tensor, Tensor]:
+    """The prior query (scripts/extract_priors.py:130-138) for a model with several routed sub-fields: ONE routing of the
+    points (the proposal networks and the field share centroids and aabbs), then the sub-field mode of the fused kernels —
+    each proposal level's density, the field's density and semantics (its colour head's output is ignored) — and the
+    finalising kernel.  prop_routers: PropNetDensityFieldMS list; field_router: iNGPFieldMS."""
+    from ._lib import FieldNetDev, PropNetDev, device_ptr_array, device_struct_array
+    pts = _f32c(points_scaled).view(-1, 3)
+    M, dev = pts.shape[0], pts.device
+    nf = len(field_router.fields)
+    f0 = field_router.fields[0]
+    rt = route_points(field_router.centroids, field_router._aabbs_host(), f0.spatial_distortion is not None, None, None,
+                      None, positions=pts)
+    dens = []
+    for lvl, pr in enumerate(prop_routers):
+        grid = pr._ms_meta()
+        subs = []
+        for f in pr.fields:
+            l0, l1 = list(f.mlp_base[1].layers)
+            subs.append([f.encoding.hash_table.detach(), l0.weight.detach(), l0.bias.detach(), l1.weight.detach(),
+                         l1.bias.detach()])
+        slot = ("prop", subs[0][0].data_ptr())
+        tables = device_ptr_array([s_[0] for s_ in subs], dev, (slot, "tables"))
+        nets = device_struct_array([PropNetDev(s_[1].data_ptr(), s_[2].data_ptr(), s_[3].data_ptr(), s_[4].data_ptr(),
+                                               0, 0, 0, 0) for s_ in subs], dev, (slot, "nets_fwd"))
+        d = torch.zeros(M, device=dev, dtype=torch.float32)
+        call("ps_prop_level_fwd_ms", ptr(nets), subs[0][1].shape[0], ptr(rt.x01), ptr(rt.sel), ptr(rt.perm),
+             ptr(rt.tile_sf), rt.rows, ptr(tables), host_floats(grid.scalings), grid.L, grid.F, grid.log2_T, ptr(d), None,
+             stream())
+        dens.append(d)
+    grid = field_router._ms_meta()
+    subs = []
+    for f in field_router.fields:
+        layers = [*f.mlp_base_mlp.layers, *f.semantic_head.layers, *f.rgb_head.layers]
+        subs.append([f.mlp_base_grid.hash_table.detach(), *[l.weight.detach() for l in layers],
+                     *[l.bias.detach() for l in layers]])
+    slot = ("field", subs[0][0].data_ptr())
+    tables = device_ptr_array([s_[0] for s_ in subs], dev, (slot, "tables"))
+    feat = torch.empty(rt.rows * grid.L * grid.F, device=dev, dtype=torch.float32)
+    call("ps_hash_fwd_ms", ptr(rt.x01), rt.rows, ptr(tables), ptr(rt.tile_sf), host_floats(grid.scalings), grid.L, grid.F,
+         grid.log2_T, ptr(feat), stream())
+
+    def net_of(s_):
+        n = FieldNetDev()
+        for i in range(8):
+            n.W[i], n.B[i], n.dW[i], n.dB[i] = s_[1 + i].data_ptr(), s_[9 + i].data_ptr(), 0, 0
+        n.in_dim, n.app_dim = grid.L * grid.F, 0          # no appearance: the colour head's output is not used here
+        return n
+    nets = device_struct_array([net_of(s_) for s_ in subs], dev, (slot, "nets_query"))
+    d = torch.zeros(M, device=dev, dtype=torch.float32)
+    rgb = torch.empty(M, 3, device=dev, dtype=torch.float32)
+    sem = torch.zeros(M, 64, device=dev, dtype=torch.float32)
+    zdir = torch.zeros(1, 3, device=dev, dtype=torch.float32)
+    call("ps_field_level_fwd_ms", ptr(nets), 0, ptr(feat), grid.L, grid.F, ptr(rt.sel), ptr(rt.perm), ptr(rt.tile_sf),
+         rt.rows, max(M, 1), ptr(zdir), None, ptr(d), ptr(rgb), ptr(sem), stream())        # S = M: every point is "ray 0"
+    dens.append(d)
+    mean = torch.empty(M, device=dev, dtype=torch.float32)
+    feats = torch.empty(M, 64, device=dev, dtype=torch.float16)
+    call("ps_prior_finalize", host_ptrs(dens), len(dens), ptr(sem), M, 64, ptr(mean), ptr(feats), stream())
+    return mean, feats
 
 
 @torch.no_grad()

@@ -447,6 +447,10 @@ class NerfactoNuscMSModel(nn.Module):
             from . import fused
             return fused.query_priors(points_scaled, [p.fields[0] for p in self.proposal_networks],
                                       self.field.fields[0])
+        if (self.use_fused and len(self.field.fields) > 1 and self.config.use_semantics and self.field.supports_fused()
+                and all(p.supports_fused() for p in self.proposal_networks)):
+            from . import fused
+            return fused.query_priors_ms(points_scaled, list(self.proposal_networks), self.field)
         dens = [p.density_fn(points_scaled).squeeze(-1) for p in self.proposal_networks]
         dens.append(self.field.density_fn(points_scaled)[0].squeeze(-1))
         densities_mean = torch.stack(dens, dim=0).mean(dim=0)

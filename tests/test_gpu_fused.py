@@ -382,7 +382,7 @@ def test_tc5_prop_level_matches_modular(n, S, L, F, H, log2T):
     aabb = [-1.0, -1.0, -0.5, 1.0, 1.0, 0.5]
     assert fused.tc5_prop_supported(grid, meta, ops.PREC_BF16, S)
     leaves = [table, *ws, *bs]
-    w_t = fused._PropLevelTc5.apply(o, d, eu, table, aabb, True, grid, ws[0], bs[0], ws[1], bs[1])
+    w_t = fused._PropLevelTc5.apply(o, d, eu, table, aabb, True, grid, None, ws[0], bs[0], ws[1], bs[1])
     g_t = torch.autograd.grad((w_t * gw).sum(), leaves)
     w_m = fused._PropLevel.apply(o, d, eu, table, aabb, True, grid, meta, ops.PREC_BF16, *ws, *bs)
     g_m = torch.autograd.grad((w_m * gw).sum(), leaves)
@@ -395,5 +395,5 @@ def test_tc5_prop_level_matches_modular(n, S, L, F, H, log2T):
         assert e < (1e-1 if name == "b1" else 2e-2), f"{name}: rel-L2 {e:.3e}"
     # no-grad forward (eval / non-update steps) takes the same kernel without saving features
     with torch.no_grad():
-        w_n = fused._PropLevelTc5.apply(o, d, eu, table, aabb, True, grid, ws[0], bs[0], ws[1], bs[1])
+        w_n = fused._PropLevelTc5.apply(o, d, eu, table, aabb, True, grid, None, ws[0], bs[0], ws[1], bs[1])
     assert torch.equal(w_n, w_t)

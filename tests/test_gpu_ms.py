@@ -51,6 +51,13 @@ def test_routing_kernels_partition_points():
     live = tile_sf[tile_sf != 255]
     assert bool((live[1:] >= live[:-1]).all()) and len(live) % 2 == 0                    # ascending, whole pairs
     assert rt.rows % 256 == 0 and rt.rows >= P
+    # stable: inside a sub-field's segment the points keep their original order (and the result is deterministic)
+    seg = row_sf[used]
+    pv = perm[used]
+    same = seg[1:] == seg[:-1]
+    assert bool((pv[1:][same] > pv[:-1][same]).all())
+    rt2 = fused.route_points(cen.to(DEV), aabbs_host, True, o, d, eu)
+    assert torch.equal(rt2.perm, rt.perm) and torch.equal(rt2.tile_sf, rt.tile_sf)
     for k in range(NF):
         rows_k = torch.nonzero(used & (row_sf == k)).flatten()
         if len(rows_k) == 0:
@@ -227,6 +234,25 @@ def test_presight_shape_fused_matches_oracle_and_modular():
     # bins; the kernel-level comparison on identical bins is test_levels_match_modular_on_identical_bins)
     tables = {k: v for k, v in worst.items() if k.endswith("hash_table")}
     assert len(tables) >= 8 and max(tables.values()) < 0.2, sorted(tables.items(), key=lambda kv: -kv[1])[:5]
+
+
+def test_prior_query_with_sub_fields_matches_oracle():
+    """`query_priors` on a model with 16 routed sub-fields (the shape PreSight extracts priors from): sub-field mode of the
+    fused kernels vs the oracle's restatement of extract_priors.py:130-138 and vs the modular routers."""
+    from presight_b200 import synthetic
+    model, cfg, host = build(64, log2_T=14)
+    model.eval()
+    pts = synthetic.prior_tile_grid(3)[::37][:20000].contiguous().to(DEV)
+    mean, feats = model.query_priors(pts)
+    omodel, _ = bench.oracle_model_from(model, cfg)
+    want_mean, want_feats = O.prior_query(omodel, pts.cpu())
+    assert feats.dtype == torch.float16 and feats.shape == (pts.shape[0], 64)
+    assert_close(mean.cpu(), want_mean, 1e-2, "mean density")
+    assert_close(feats.float().cpu(), want_feats.float(), 1e-2, "semantic features")
+    model.use_fused = False
+    mean_m, feats_m = model.query_priors(pts)
+    assert_close(mean, mean_m, 3e-3, "mean density vs modular")
+    assert_close(feats.float(), feats_m.float(), 3e-3, "features vs modular")
 
 
 def test_sub_field_mode_is_sync_free_in_steady_state():

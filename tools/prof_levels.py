@@ -51,7 +51,7 @@ def main():
             gw = torch.randn(n, S, 1, generator=g).to(dev) * 1e-3
 
             def run():
-                w = fused._PropLevelTc5.apply(o, d, eu, table, aabb, True, grid, ws[0], bs[0], ws[1], bs[1])
+                w = fused._PropLevelTc5.apply(o, d, eu, table, aabb, True, grid, None, ws[0], bs[0], ws[1], bs[1])
                 torch.autograd.grad((w * gw).sum(), [table, *ws, *bs])
             print(f"prop S={S}: {timeit(run, args.iters):.3f} ms fwd+bwd", flush=True)
     if "field" in args.what:
