@@ -585,8 +585,8 @@ static int launch_field_bwd(const FieldArgs& a, cudaStream_t stream) {
 
 // ------------------------------------------------------------------------------------------------------------------
 // Sub-field mode backward (see FieldMsArgs in field_tc5.cuh): the same recompute + dgrad + wgrad chain per 128-row tile,
-// driven by per-point gradients of density / rgb / semantics (the compositing backward runs in ps_composite_bwd).  The CTA
-// walks a contiguous range of tiles; when the sub-field changes it flushes the TMEM-resident weight / bias gradient
+// driven by per-point gradients of density / rgb / semantics (the compositing backward runs in ps_composite_bwd).  CTAs take
+// tiles round-robin; when the sub-field changes it flushes the TMEM-resident weight / bias gradient
 // accumulators into the finished sub-field's buffers and restages the next sub-field's weights.
 template <int K0>
 __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_ms_kernel(FieldMsArgs a) {
@@ -630,9 +630,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_ms_kernel(FieldMsArg
     constexpr uint32_t CH = kRows * 16;
     uint32_t phase = 0, phaseB0 = 0, phaseB1 = 0;
     const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    // Tiles are taken round-robin, so at any moment all CTAs work on neighbouring tiles, i.e. (mostly) on the SAME sub-field:
+    // the live hash-table working set is one sub-field's tables, which fit the 126 MB L2, instead of all of them.
     const int64_t ntiles = a.rows / kRows;
-    const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
-    const int64_t t_begin = (int64_t)blockIdx.x * per, t_end = t_begin + per < ntiles ? t_begin + per : ntiles;
     bool first = true;
     float db_r2 = 0.f;
     int cur = -1;
@@ -739,7 +739,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_ms_kernel(FieldMsArg
         phaseB0 ^= 1;                  \
     }
 
-    for (int64_t tile = t_begin; tile < t_end; ++tile) {
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int sf = a.tile_sf[tile];
         if (sf == 255) break;
         if (sf != cur) {

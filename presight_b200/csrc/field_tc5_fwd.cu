@@ -319,8 +319,8 @@ static int launch_field_fwd(const FieldArgs& a, cudaStream_t stream) {
 
 // ------------------------------------------------------------------------------------------------------------------
 // Sub-field mode forward (see FieldMsArgs in field_tc5.cuh): the same five GEMM -> epilogue phases per 128-row tile, two
-// tiles (one per thread group) in lock step so that both always belong to the same sub-field; the CTA walks a contiguous
-// range of tile pairs and restages the 54 KB of weights only when the sub-field changes.  Outputs per point.
+// tiles (one per thread group) in lock step so that both always belong to the same sub-field; CTAs take tile pairs
+// round-robin and restage the 54 KB of weights when the sub-field changes.  Outputs per point.
 template <int K0>
 __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_ms_kernel(FieldMsArgs a) {
     using WL = WLayout<K0>;
@@ -352,9 +352,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_ms_kernel(FieldMsArg
     const int barid = 1 + g;
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
     uint32_t phase = 0;
-    const int64_t npairs = a.rows / (2 * kRows);
-    const int64_t per = (npairs + gridDim.x - 1) / gridDim.x;
-    const int64_t p_begin = (int64_t)blockIdx.x * per, p_end = p_begin + per < npairs ? p_begin + per : npairs;
+    const int64_t npairs = a.rows / (2 * kRows);       // taken round-robin: all CTAs stay on (mostly) the same sub-field
     int cur = -1;
     FieldNet net{};
 
@@ -375,7 +373,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_ms_kernel(FieldMsArg
     phase ^= 1;             \
     fence_after();
 
-    for (int64_t pair = p_begin; pair < p_end; ++pair) {
+    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
         const int sf = a.tile_sf[2 * pair];
         if (sf == 255) break;                                   // the used tiles are a prefix
         if (sf != cur) {

@@ -522,7 +522,7 @@ static int dispatch(const PropArgs& a, int H, bool bwd, cudaStream_t s) {
 // Sub-field mode (routers: fields/PreSight/prop_density_field_ms.py:86-105).  The level's points arrive
 // grouped by sub-field (ms_route.cu): row i of tile t is point perm[i] (-1 = padding) with its unit-cube position already
 // normalised by its sub-field's aabb; every 128-row tile belongs to ONE sub-field (tile_sf), whose hash table and MLP the
-// tile uses.  A CTA walks a contiguous range of tiles, so it restages the (tiny) network only when the sub-field
+// tile uses.  CTAs take tiles round-robin and restage the (tiny) network when the sub-field
 // changes — in the backward it then also flushes the TMEM-resident weight-gradient accumulators to that sub-field's
 // gradient buffers.  Rays are no longer contiguous in a tile, so the kernels stop at the density (forward) and start
 // from d loss / d density (backward); weights and their backward run in ps_composite_fwd / ps_composite_bwd.
@@ -573,14 +573,14 @@ __global__ void __launch_bounds__(kThreads) prop_fwd_ms_kernel(PropMsArgs a) {
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     const uint32_t bar = smem_u32(bar_ptr);
     uint32_t phase = 0;
+    // Tiles are taken round-robin, so at any moment all CTAs work on neighbouring tiles, i.e. (mostly) on the SAME sub-field:
+    // the live hash-table working set is one sub-field's tables, which fit the 126 MB L2, instead of all of them.
     const int64_t ntiles = a.rows / kRows;
-    const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
-    const int64_t t_begin = (int64_t)blockIdx.x * per, t_end = t_begin + per < ntiles ? t_begin + per : ntiles;
     const uint32_t mask_t = (1u << a.hp.log2_T) - 1u;
     const int L = a.hp.L;
     int cur = -1;
 
-    for (int64_t tile = t_begin; tile < t_end; ++tile) {
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int sf = a.tile_sf[tile];
         if (sf == 255) break;                                   // the used tiles are a prefix
         if (sf != cur) {
@@ -698,9 +698,9 @@ __global__ void __launch_bounds__(kThreads) prop_bwd_ms_kernel(PropMsArgs a) {
     const uint32_t aH1 = smem_u32(H1), aDZ0 = smem_u32(DZ0), aX0 = smem_u32(X0), aDZ1 = smem_u32(DZ1),
                    aONES = smem_u32(ONES), aW0 = smem_u32(smem + SM::w0);
     uint32_t phase = 0;
+    // Tiles are taken round-robin, so at any moment all CTAs work on neighbouring tiles, i.e. (mostly) on the SAME sub-field:
+    // the live hash-table working set is one sub-field's tables, which fit the 126 MB L2, instead of all of them.
     const int64_t ntiles = a.rows / kRows;
-    const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
-    const int64_t t_begin = (int64_t)blockIdx.x * per, t_end = t_begin + per < ntiles ? t_begin + per : ntiles;
     const uint32_t mask_t = (1u << a.hp.log2_T) - 1u;
     const int L = a.hp.L;
     float db1 = 0.f;
@@ -736,7 +736,7 @@ __global__ void __launch_bounds__(kThreads) prop_bwd_ms_kernel(PropMsArgs a) {
         first = true;
     };
 
-    for (int64_t tile = t_begin; tile < t_end; ++tile) {
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int sf = a.tile_sf[tile];
         if (sf == 255) break;
         if (sf != cur) {

@@ -215,6 +215,7 @@ class SkyFieldMS(nn.Module):
         super().__init__()
         self.register_buffer("centroids", deepcopy(centroids))
         self.fields = nn.ModuleList(fields)
+        self.batched = True      # several sub-fields: one batched evaluation + selection instead of the routed loop
 
     def forward(self, ray_samples: RaySamples, appearance_embedding: Optional[Tensor]) -> Dict[str, Tensor]:
         """sky_field_ms.py:81-117 (routed by ray origin)."""
@@ -223,6 +224,35 @@ class SkyFieldMS(nn.Module):
         # reference layout [N,S,A] (sample 0 is used) or per-ray [N,A]
         app = None if appearance_embedding is None else (
             appearance_embedding if appearance_embedding.dim() == 2 else appearance_embedding[:, 0, :])
+        if len(self.fields) > 1 and self.batched and origins.is_cuda:
+            return self._forward_batched(origins.contiguous(), directions.contiguous(), app)
         res = _dispatch(origins.contiguous(), self.centroids, len(self.fields),
                         lambda i, o, d, a: self.fields[i].get_outputs(d, a), (directions, app))
         return {k: v.contiguous() for k, v in res.items()}
+
+    def _forward_batched(self, origins: Tensor, directions: Tensor, app: Optional[Tensor]) -> Dict[str, Tensor]:
+        """Several sub-fields, no host synchronisation: the sky networks are per-RAY and tiny (32-wide, 3 layers), so all
+        nf of them are evaluated on every ray as batched matrix products (fp32) and each ray keeps the output of the
+        sub-field nearest to its origin — the same values the routed loop of the reference computes, and, through the
+        selection's gradient, the same parameter gradients (a sub-field only sees the rays routed to it).  The routed
+        loop (`batched = False`) needs one device->host read of the bucket sizes per call."""
+        sf = ops.nearest_centroid(origins, self.centroids).long()                     # [N]
+        d = self.fields[0].direction_encoding.forward_raw(directions)                 # [N,16], no gradient
+        rows = torch.arange(origins.shape[0], device=origins.device)
+
+        def run(heads, x):
+            nl = len(heads[0].layers)
+            h = x[None].expand(len(heads), *x.shape)
+            for li in range(nl):
+                W = torch.stack([hd.layers[li].weight for hd in heads])               # [nf, out, in]
+                b = torch.stack([hd.layers[li].bias for hd in heads])                 # [nf, out]
+                h = torch.baddbmm(b[:, None, :], h, W.transpose(1, 2))
+                if li + 1 < nl:
+                    h = torch.relu(h)
+            return h[sf, rows]                                                        # [N, out]
+        f0 = self.fields[0]
+        x = d if app is None else torch.cat([d, app], dim=-1)
+        out = {FieldHeadNames.RGB: torch.sigmoid(run([f.rgb_head for f in self.fields], x))}
+        if f0.use_semantics:
+            out[FieldHeadNames.SEMANTICS] = run([f.semantic_head for f in self.fields], d)
+        return out

@@ -255,6 +255,41 @@ def test_prior_query_with_sub_fields_matches_oracle():
     assert_close(feats.float(), feats_m.float(), 3e-3, "features vs modular")
 
 
+def test_sky_batched_matches_routed_loop():
+    """SkyFieldMS with several sub-fields: the batched, synchronisation-free evaluation against the routed loop (the
+    reference's structure, sky_field_ms.py:81-117) — outputs and parameter gradients of every sub-field."""
+    model, cfg, host = build(300, log2_T=10, impl="b200+fp32")
+    sky = model.sky_model
+    from presight_b200.cameras.rays import RayBundle
+    n = 300
+    rb = RayBundle(origins=host["origins"].to(DEV), directions=host["directions"].to(DEV))
+    eu = torch.linspace(0.1, 1.0, 5, device=DEV).repeat(n, 1)
+    rs = RayBundle.samples_from_bins(rb, eu, eu, None)
+    g = torch.Generator().manual_seed(2)
+    app = torch.randn(n, 16, generator=g).to(DEV)
+    t_rgb, t_sem = torch.rand(n, 3, generator=g).to(DEV), torch.rand(n, 64, generator=g).to(DEV)
+    res = {}
+    for batched in (True, False):
+        sky.batched = batched
+        for p in sky.parameters():
+            p.grad = None
+        out = sky(rs, appearance_embedding=app)
+        (((out["rgb"] - t_rgb) ** 2).mean() + ((out["semantics"] - t_sem) ** 2).mean()).backward()
+        res[batched] = (out["rgb"].detach(), out["semantics"].detach(),
+                        {k: (None if p.grad is None else p.grad.clone()) for k, p in sky.named_parameters()})
+    assert_close(res[True][0], res[False][0], 1e-3, "sky rgb")
+    assert_close(res[True][1], res[False][1], 1e-3, "sky semantics")
+    n_checked = 0
+    for k, gb in res[False][2].items():
+        ga = res[True][2][k]
+        if gb is None or float(gb.abs().max()) == 0.0:
+            assert ga is None or float(ga.abs().max()) == 0.0, k
+            continue
+        assert rel_l2(ga, gb) < 5e-3, k
+        n_checked += 1
+    assert n_checked >= 12
+
+
 def test_sub_field_mode_is_sync_free_in_steady_state():
     """After the first steps have uploaded the pointer tables, a training step makes no pageable host->device copy for
     them (the tables are cached by address) — the routing itself never reads anything back."""
