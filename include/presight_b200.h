@@ -388,10 +388,11 @@ int ps_prop_level_bwd(const ps_prop_net* net, const float* origins, const float*
  * boolean-mask gather, a field call, a masked scatter and a `torch.any` host sync) without any host synchronisation:
  *
  *   ps_ms_route    every point (positions [P,3], or ray sample mid-points from origins / dirs [N,3] + eu_bins [N,S+1] with
- *                  P = N*S) -> sf_out [P] = index of the nearest centroid (first minimum), block_hist [ceil(P/256), nf] =
+ *                  P = N*S) -> sf_out [P] = index of the nearest centroid (first minimum), block_hist [nf, ceil(P/256)] =
  *                  points per sub-field of every block of 256 consecutive points.  centroids [nf,3] on the device.
- *   ps_ms_plan     block_hist -> (in place) first row of every (block, sub-field); seg_start [nf+1] (segments padded to
- *                  multiples of `pad` rows); tile_sf [max_rows / tile_rows] = sub-field of every tile of `tile_rows` rows,
+ *   ps_ms_plan     block_hist -> (in place) first row of every block relative to its sub-field's segment; seg_start
+ *                  [2*nf+1] = nf+1 segment starts (segments padded to multiples of `pad` rows) followed by the nf
+ *                  sub-field totals; tile_sf [max_rows / tile_rows] = sub-field of every tile of `tile_rows` rows,
  *                  255 past the last segment.
  *   ps_ms_scatter  every point -> its row of its sub-field's segment (a STABLE counting sort: the original order is kept
  *                  inside a segment, the result is deterministic): perm[row] = point (caller presets perm to -1 = padding), x01_sorted [max_rows,3] = unit-cube position
@@ -424,8 +425,8 @@ int ps_ms_route(const float* positions, const float* origins, const float* dirs,
 int ps_ms_plan(int32_t* block_hist, int64_t P, int nf, int pad, int tile_rows, int64_t max_rows, int32_t* seg_start,
                uint8_t* tile_sf, void* stream);
 int ps_ms_scatter(const float* positions, const float* origins, const float* dirs, const float* eu_bins, int64_t P, int S,
-                  const uint8_t* sf, const float* aabbs, int nf, int contract, const int32_t* block_off, int32_t* perm,
-                  float* x01_sorted, uint8_t* sel_sorted, void* stream);
+                  const uint8_t* sf, const float* aabbs, int nf, int contract, const int32_t* block_off,
+                  const int32_t* seg_start, int32_t* perm, float* x01_sorted, uint8_t* sel_sorted, void* stream);
 int ps_hash_fwd_ms(const float* x01_sorted, int64_t rows, const float* const* tables, const uint8_t* tile_sf,
                    const float* scalings_host, int L, int F, int log2_T, float* out, void* stream);
 int ps_hash_bwd_ms(const float* x01_sorted, int64_t rows, float* const* dtables, const uint8_t* tile_sf, const int32_t* perm,

@@ -61,7 +61,7 @@ SIGNATURES = {
     "ps_depth_losses": [_p, _p, _p, _p, _p, _p, _i64, _i, _f, _p, _f, _f, _i, _p, _p, _p, _p],
     "ps_ms_route": [_p, _p, _p, _p, _i64, _i, _p, _i, _p, _p, _p],
     "ps_ms_plan": [_p, _i64, _i, _i, _i, _i64, _p, _p, _p],
-    "ps_ms_scatter": [_p, _p, _p, _p, _i64, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p],
+    "ps_ms_scatter": [_p, _p, _p, _p, _i64, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p],
     "ps_hash_fwd_ms": [_p, _i64, _p, _p, _fp, _i, _i, _i, _p, _p],
     "ps_hash_bwd_ms": [_p, _i64, _p, _p, _p, _fp, _i, _i, _i, _p, _p],
     "ps_prop_level_fwd_ms": [_p, _i, _p, _p, _p, _p, _i64, _p, _fp, _i, _i, _i, _p, _p, _p],

@@ -4,8 +4,8 @@
 // as three small kernels with no host synchronisation, feeding the sub-field-homogeneous point tiles of the fused level
 // kernels (prop_tc5_ms.cu / field_tc5_ms.cu):
 //   1. route    every sample point -> nearest centroid (uint8) + a histogram per block of 256 points
-//   2. plan     block histograms -> segment starts padded to whole tiles, the first row of every (block, sub-field),
-//               tile -> sub-field table
+//   2. plan     block histograms -> (one CTA per sub-field) the first row of every block inside its sub-field's segment and
+//               the sub-field totals; then segment starts padded to whole tiles and the tile -> sub-field table
 //   3. scatter  every point -> its row in its sub-field's segment: perm[row] = point, unit-cube position normalised
 //               with THAT sub-field's aabb (fields/PreSight/utils.py:6-10 + contraction) and the in-box selector
 // The sort is STABLE (a counting sort with per-block offsets and in-block ranks): inside a sub-field's segment the
@@ -77,46 +77,55 @@ __global__ void __launch_bounds__(kRouteThreads) ms_route_kernel(const float* __
     for (int k = threadIdx.x; k < nf; k += blockDim.x) {
         int32_t tot = 0;
         for (int w = 0; w < kRouteThreads / 32; ++w) tot += warp_hist[w][k];
-        block_hist[(int64_t)blockIdx.x * nf + k] = tot;
+        block_hist[(int64_t)k * gridDim.x + blockIdx.x] = tot;          // [nf][nblocks]: a sub-field's column is contiguous
     }
 }
 
-// one CTA: per-sub-field totals and the exclusive scan of the block histograms (block_hist is overwritten by the first
-// row of every (block, sub-field)), padded segment starts, tile -> sub-field table (255 = beyond the last segment)
-__global__ void __launch_bounds__(1024) ms_plan_kernel(int32_t* __restrict__ block_hist, int64_t nblocks, int nf, int pad,
-                                                       int tile_rows, int64_t max_rows, int32_t* __restrict__ seg_start,
-                                                       uint8_t* __restrict__ tile_sf) {
+// CTA k: exclusive scan of sub-field k's block counts (block_hist[k][*] is overwritten by each block's first row RELATIVE to
+// the segment start), total -> totals[k]
+__global__ void __launch_bounds__(1024) ms_scan_kernel(int32_t* __restrict__ block_hist, int64_t nblocks,
+                                                       int32_t* __restrict__ totals) {
     __shared__ int32_t part[1024];
-    __shared__ int32_t start[kMaxSub + 1];
     const int tid = threadIdx.x;
+    int32_t* col = block_hist + (int64_t)blockIdx.x * nblocks;
     const int64_t chunk = (nblocks + blockDim.x - 1) / blockDim.x;
     const int64_t b0 = (int64_t)tid * chunk, b1 = b0 + chunk < nblocks ? b0 + chunk : nblocks;
-    if (tid == 0) start[0] = 0;
-    for (int k = 0; k < nf; ++k) {
-        int32_t sum = 0;
-        for (int64_t b = b0; b < b1; ++b) sum += block_hist[b * nf + k];
-        part[tid] = sum;
+    int32_t sum = 0;
+    for (int64_t b = b0; b < b1; ++b) sum += col[b];
+    part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {                       // inclusive scan of the per-thread partial sums
+        const int32_t v = tid >= o ? part[tid - o] : 0;
         __syncthreads();
-        // inclusive scan of the per-thread partial sums (Hillis-Steele over 1024 entries)
-        for (int o = 1; o < 1024; o <<= 1) {
-            const int32_t v = tid >= o ? part[tid - o] : 0;
-            __syncthreads();
-            part[tid] += v;
-            __syncthreads();
-        }
-        const int32_t total = part[1023];
-        int32_t run = start[k] + part[tid] - sum;                   // first row of this thread's first block
-        for (int64_t b = b0; b < b1; ++b) {
-            const int32_t cnt = block_hist[b * nf + k];
-            block_hist[b * nf + k] = run;
-            run += cnt;
-        }
-        if (tid == 0) start[k + 1] = start[k] + (total + pad - 1) / pad * pad;
+        part[tid] += v;
         __syncthreads();
     }
-    for (int k = tid; k <= nf; k += blockDim.x) seg_start[k] = start[k];
+    int32_t run = part[tid] - sum;
+    for (int64_t b = b0; b < b1; ++b) {
+        const int32_t cnt = col[b];
+        col[b] = run;
+        run += cnt;
+    }
+    if (tid == 1023) totals[blockIdx.x] = part[1023];
+}
+
+// one CTA: padded segment starts, tile -> sub-field table (255 = beyond the last segment)
+__global__ void __launch_bounds__(1024) ms_plan_kernel(const int32_t* __restrict__ totals, int nf, int pad, int tile_rows,
+                                                       int64_t max_rows, int32_t* __restrict__ seg_start,
+                                                       uint8_t* __restrict__ tile_sf) {
+    __shared__ int32_t start[kMaxSub + 1];
+    if (threadIdx.x == 0) {
+        int32_t acc = 0;
+        for (int k = 0; k < nf; ++k) {
+            start[k] = acc;
+            acc += (totals[k] + pad - 1) / pad * pad;
+        }
+        start[nf] = acc;
+        for (int k = 0; k <= nf; ++k) seg_start[k] = start[k];
+    }
+    __syncthreads();
     const int64_t ntiles = max_rows / tile_rows;
-    for (int64_t t = tid; t < ntiles; t += blockDim.x) {
+    for (int64_t t = threadIdx.x; t < ntiles; t += blockDim.x) {
         const int64_t row = t * tile_rows;
         int sf = 255;
         for (int k = 0; k < nf; ++k)
@@ -133,7 +142,8 @@ __global__ void __launch_bounds__(kRouteThreads) ms_scatter_kernel(const float* 
                                                          const float* __restrict__ dirs, const float* __restrict__ eu,
                                                          int64_t P, int S, const uint8_t* __restrict__ sf_in,
                                                          const float* __restrict__ aabbs, int nf, int contract,
-                                                         const int32_t* __restrict__ block_off, int32_t* __restrict__ perm,
+                                                         const int32_t* __restrict__ block_off,
+                                                         const int32_t* __restrict__ seg_start, int32_t* __restrict__ perm,
                                                          float* __restrict__ x01s, uint8_t* __restrict__ sels) {
     __shared__ Aabb boxes[kMaxSub];
     __shared__ int32_t warp_hist[kRouteThreads / 32][kMaxSub];
@@ -147,7 +157,7 @@ __global__ void __launch_bounds__(kRouteThreads) ms_scatter_kernel(const float* 
     const int sf = on ? sf_in[p] : 0;
     const int rank = block_rank(sf, on, warp_hist, nf);
     if (!on) return;
-    const int slot = block_off[(int64_t)blockIdx.x * nf + sf] + rank;
+    const int slot = seg_start[sf] + block_off[(int64_t)sf * gridDim.x + blockIdx.x] + rank;
     float x[3];
     point_of(positions, origins, dirs, eu, p, S, x);
     const bool inside = normalize_point(x, boxes[sf], contract != 0);
@@ -182,19 +192,22 @@ extern "C" int ps_ms_plan(int32_t* block_hist, int64_t P, int nf, int pad, int t
                "ms_plan: pad %d must be a multiple of the tile (%d rows) and max_rows a multiple of the tile", pad, tile_rows);
     PS_REQUIRE(max_rows >= (P + pad - 1) / pad * pad + (int64_t)nf * pad, "ms_plan: max_rows %lld too small for %lld points",
                (long long)max_rows, (long long)P);
-    ms_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(block_hist, cdiv(P, kRouteThreads), nf, pad, tile_rows, max_rows,
-                                                        seg_start, tile_sf);
+    // totals live behind the nf + 1 segment starts (seg_start has room for 2 * nf + 1 ints)
+    int32_t* totals = seg_start + nf + 1;
+    ms_scan_kernel<<<nf, 1024, 0, (cudaStream_t)stream>>>(block_hist, cdiv(P, kRouteThreads), totals);
+    if (int e = check_launch("ms_plan(scan)")) return e;
+    ms_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(totals, nf, pad, tile_rows, max_rows, seg_start, tile_sf);
     return check_launch("ms_plan");
 }
 
 extern "C" int ps_ms_scatter(const float* positions, const float* origins, const float* dirs, const float* eu_bins, int64_t P,
                              int S, const uint8_t* sf, const float* aabbs, int nf, int contract, const int32_t* block_off,
-                             int32_t* perm, float* x01_sorted, uint8_t* sel_sorted, void* stream) {
+                             const int32_t* seg_start, int32_t* perm, float* x01_sorted, uint8_t* sel_sorted, void* stream) {
     if (P == 0) return 0;
-    PS_REQUIRE(sf && aabbs && block_off && perm && x01_sorted && sel_sorted, "ms_scatter: null pointer");
+    PS_REQUIRE(sf && aabbs && block_off && seg_start && perm && x01_sorted && sel_sorted, "ms_scatter: null pointer");
     PS_REQUIRE(nf >= 1 && nf <= kMaxSub, "ms_scatter: %d sub-fields outside [1, %d]", nf, kMaxSub);
     PS_REQUIRE(positions != nullptr || (origins && dirs && eu_bins && S >= 1), "ms_scatter: give positions or rays + bins");
     ms_scatter_kernel<<<(unsigned)cdiv(P, kRouteThreads), kRouteThreads, 0, (cudaStream_t)stream>>>(
-        positions, origins, dirs, eu_bins, P, S, sf, aabbs, nf, contract, block_off, perm, x01_sorted, sel_sorted);
+        positions, origins, dirs, eu_bins, P, S, sf, aabbs, nf, contract, block_off, seg_start, perm, x01_sorted, sel_sorted);
     return check_launch("ms_scatter");
 }

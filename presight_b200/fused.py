@@ -582,7 +582,7 @@ def route_points(centroids: Tensor, aabbs_host: Sequence[Sequence[float]], contr
     boxes = _device_table((("aabbs", id(aabbs_host)), str(dev)), sig,
                           lambda: torch.tensor(sig, dtype=torch.float32).view(nf, 6).to(dev))
     block_hist = torch.empty((P + 255) // 256 * nf, device=dev, dtype=torch.int32)
-    seg_start = torch.empty(nf + 1, device=dev, dtype=torch.int32)
+    seg_start = torch.empty(2 * nf + 1, device=dev, dtype=torch.int32)        # nf + 1 starts | nf totals
     sf = torch.empty(P, device=dev, dtype=torch.uint8)
     perm = torch.full((rows,), -1, device=dev, dtype=torch.int32)
     tile_sf = torch.empty(rows // 128, device=dev, dtype=torch.uint8)
@@ -591,8 +591,8 @@ def route_points(centroids: Tensor, aabbs_host: Sequence[Sequence[float]], contr
     o, d, e = (None, None, None) if pos is not None else (ptr(origins), ptr(dirs), ptr(eu))
     call("ps_ms_route", ptr(pos), o, d, e, P, S, ptr(cen), nf, ptr(sf), ptr(block_hist), stream())
     call("ps_ms_plan", ptr(block_hist), P, nf, MS_PAD, 128, rows, ptr(seg_start), ptr(tile_sf), stream())
-    call("ps_ms_scatter", ptr(pos), o, d, e, P, S, ptr(sf), ptr(boxes), nf, 1 if contract else 0, ptr(block_hist), ptr(perm),
-         ptr(x01), ptr(sel), stream())
+    call("ps_ms_scatter", ptr(pos), o, d, e, P, S, ptr(sf), ptr(boxes), nf, 1 if contract else 0, ptr(block_hist),
+         ptr(seg_start), ptr(perm), ptr(x01), ptr(sel), stream())
     return Routing(rows, perm, tile_sf, x01, sel, sf)
 
 

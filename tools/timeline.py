@@ -29,7 +29,7 @@ if world > 1:
 cfg = bench.build_config(args.config, "b200")
 torch.manual_seed(42)
 host = synthetic.make_rays(args.rays, seed=42)
-model = NerfactoNuscMSModel(cfg, torch.zeros(1, 3), synthetic.tile_aabb(), host["n_cameras"], host["n_videos"]).to(dev).train()
+model = bench.build_model(args.config, cfg, host, dev).train()
 params = [p for p in model.parameters() if p.requires_grad]
 if world > 1:
     sync = GradSynchronizer(params, overlap=True)
@@ -84,6 +84,15 @@ for e in gpu:
         gaps.append((e["ts"] - end_all, (end_all - t0) / 1e3, e["name"][:60]))
     end_all = max(end_all, e["ts"] + e["dur"])
     print(f"{(e['ts'] - t0) / 1e3:8.3f} {e['dur'] / 1e3:7.3f}  s{e['args'].get('stream', '?'):<3} {e['name'][:90]}")
+import collections
+by = collections.Counter()
+cnt = collections.Counter()
+for e in gpu:
+    by[e["name"][:70]] += e["dur"]
+    cnt[e["name"][:70]] += 1
+print("# device time by kernel (ms, launches):")
+for k, v in by.most_common(25):
+    print(f"#   {v / 1e3:8.3f} {cnt[k]:4d}  {k}")
 print(f"# device idle inside the step: {idle / 1e3:.3f} ms in {len(gaps)} gaps; largest:")
 for g, at, nm in sorted(gaps, reverse=True)[:15]:
     print(f"#   {g / 1e3:.3f} ms at {at:.3f} ms before {nm}")
