@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpresight_b200.so")
+LIB_PATH = os.path.join(_HERE, "lib", f"libpresight_b200{os.environ.get('PS_LIB_SUFFIX', '')}.so")
 
 _p = C.c_void_p
 _i64 = C.c_int64

@@ -15,12 +15,15 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-OBJDIR = os.path.join(HERE, "build")
-LIB = os.path.join(LIBDIR, "libpresight_b200.so")
+# debug variants (tools only): PS_LIB_SUFFIX=_dbg PS_NVCC_DEFS="-DPS_PHASE_CLOCKS" builds lib/libpresight_b200_dbg.so
+SUFFIX = os.environ.get("PS_LIB_SUFFIX", "")
+OBJDIR = os.path.join(HERE, "build" + SUFFIX)
+LIB = os.path.join(LIBDIR, f"libpresight_b200{SUFFIX}.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+CFLAGS += os.environ.get("PS_NVCC_DEFS", "").split()
 
 
 def _sources():

@@ -21,7 +21,25 @@
 // them in registers with a transposing shuffle butterfly per epilogue because each tcgen05.mma then cost ~100 issue
 // cycles; with the elected-lane issue an MMA is a handful of instructions and the butterflies — 30 % of the kernel's
 // executed instructions, profiles/r1_z — are gone.)
+#include <stdlib.h>
+
 #include "field_tc5.cuh"
+
+// Phase clocks (tools/phase_clocks.py, debug build only: PS_NVCC_DEFS=-DPS_PHASE_CLOCKS): thread 0 of CTA 0 stamps
+// clock64() at every barrier / issue / wait of one steady-state tile into a global buffer as (code, cycles) pairs.
+#ifdef PS_PHASE_CLOCKS
+__device__ long long* g_phase_buf_bwd = nullptr;
+#define PS_STAMP(code)                                     \
+    do {                                                   \
+        if (stamp_on && nstamp < 250) {                    \
+            g_phase_buf_bwd[2 * nstamp] = (code);          \
+            g_phase_buf_bwd[2 * nstamp + 1] = clock64();   \
+            ++nstamp;                                      \
+        }                                                  \
+    } while (0)
+#else
+#define PS_STAMP(code)
+#endif
 
 namespace ps {
 namespace ftc5 {
@@ -168,29 +186,36 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
     float db_r2 = 0.f;
 
 #define FB_SYNC_ISSUE(...)     \
+    PS_STAMP(0);               \
     fence_async_smem();        \
     fence_before();            \
     __syncthreads();           \
+    PS_STAMP(1);               \
     if (warp_u == 0) {         \
         if (elect_one()) {     \
             fence_after();     \
             __VA_ARGS__;       \
         }                      \
         __syncwarp();          \
-    }
+    }                          \
+    PS_STAMP(2);
 #define FB_WAIT()           \
+    PS_STAMP(5);            \
     mbar_wait(bar, phase);  \
     phase ^= 1;             \
-    fence_after();
+    fence_after();          \
+    PS_STAMP(3);
 // Two issuing threads.  A single thread pays ~100 cycles per tcgen05.mma it issues, and a tile needs ~220 of them: the
 // forward / input-gradient GEMMs (whose results the epilogues wait for) are issued by thread 0, the weight- and
 // bias-gradient GEMMs (results needed only at the end of the kernel) by thread 128, each with its own commit barrier.
 // The B groups are waited one phase late, just before the tiles they read can be rewritten; they alternate between two
 // mbarriers (KB = 0, 1) so that a barrier never completes two phases before every thread has observed the first.
 #define FB_SYNC_ISSUE2(A_LIST, B_LIST, KB) \
+    PS_STAMP(0);                           \
     fence_async_smem();                    \
     fence_before();                        \
     __syncthreads();                       \
+    PS_STAMP(1);                           \
     if (warp_u == 0) {                     \
         if (elect_one()) {                 \
             fence_after();                 \
@@ -205,7 +230,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
             umma_commit(KB ? barB1 : barB0); \
         }                                  \
         __syncwarp();                      \
-    }
+    }                                      \
+    PS_STAMP(2);
 #define FB_WAIT_B(KB)                  \
     if (KB) {                          \
         mbar_wait(barB1, phaseB1);     \
@@ -213,9 +239,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
     } else {                           \
         mbar_wait(barB0, phaseB0);     \
         phaseB0 ^= 1;                  \
-    }
+    }                                  \
+    PS_STAMP(4);
 
+#ifdef PS_PHASE_CLOCKS
+    int nstamp = 0, tile_iter = 0;
+#endif
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+#ifdef PS_PHASE_CLOCKS
+        const bool stamp_on = g_phase_buf_bwd != nullptr && blockIdx.x == 0 && tid == 0 && (tile_iter == 3 || tile_iter == 4);
+        ++tile_iter;
+        PS_STAMP(9);
+#endif
         const bool acc_dw = !first;
         first = false;
         const int q = r / S, s = r - q * S;
@@ -246,6 +281,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
             rayc[i] = v;
         }
         const float* rc = rayc + (q < rpt ? q : 0) * 72;
+        PS_STAMP(8);
         // ---- base network, forward --------------------------------------------------------------------------
         FB_SYNC_ISSUE(gemm_bias(tmem + TM::acc, ones, wb + WL::bt(B0), kHid, kHid);
                       gemm_kk(tmem + TM::acc, aX0, kRows, wb + WL::b0, kHid, kHid, K0, true); umma_commit(bar))
@@ -497,6 +533,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) field_bwd_kernel(FieldArgs a) 
         }
         // the staging of the next tile is ordered behind these TMEM reads by the next FB_SYNC_ISSUE barrier; the tiles
         // it overwrites (X0, SHAPP, rayc) were last read by GEMMs / epilogues that completed before the wait above
+        PS_STAMP(7);
         __syncthreads();
     }
 #undef FB_SYNC_ISSUE
@@ -1010,7 +1047,26 @@ static int launch_field_bwd_ms(const FieldMsArgs& a, cudaStream_t stream) {
 using namespace ps;
 using namespace ps::ftc5;
 
+#ifdef PS_PHASE_CLOCKS
+/* tools only (debug build) */
+extern "C" int ps_debug_phase_buf_bwd(long long* buf) {
+    return cudaMemcpyToSymbol(g_phase_buf_bwd, &buf, sizeof(buf)) == cudaSuccess ? 0 : 2;
+}
+#endif
+
 int ps_field_check_common(const ps_field_net* net, int L, int F, int64_t N, int S, const char* what);
+
+namespace ps {
+namespace ftc5 {
+int launch_field_bwd2(const FieldArgs& a, cudaStream_t stream);          // field_tc5_bwd2.cu
+int launch_field_bwd2_ms(const FieldMsArgs& a, cudaStream_t stream);
+}
+}
+// PS_FIELD_BWD_V1=1 selects the first (single-chain) backward kernels for A/B timing
+static bool use_v1() {
+    static const bool v = [] { const char* e = getenv("PS_FIELD_BWD_V1"); return e && e[0] == '1'; }();
+    return v;
+}
 
 extern "C" int ps_field_level_bwd(const ps_field_net* net, const float* feat_lm, int L, int F, const uint8_t* sel,
                                   const float* eu_bins, const float* dirs, const float* app, int64_t N, int S,
@@ -1034,6 +1090,7 @@ extern "C" int ps_field_level_bwd(const ps_field_net* net, const float* feat_lm,
     a.dapp = dapp; a.N = N; a.S = S;
     a.acc = const_cast<float*>(acc); a.dexp = const_cast<float*>(depth_exp);
     a.d_w = d_weights; a.d_rgb = d_rgb_out; a.d_acc = d_acc; a.d_dexp = d_depth_exp; a.d_sem = d_sem_out;
+    if (!use_v1()) return launch_field_bwd2(a, (cudaStream_t)stream);
     if (L * F <= 32) return launch_field_bwd<32>(a, (cudaStream_t)stream);
     return launch_field_bwd<48>(a, (cudaStream_t)stream);
 }
@@ -1054,6 +1111,7 @@ extern "C" int ps_field_level_bwd_ms(const ps_field_net_dev* nets_dev, int app_d
     a.feat = feat_lm_sorted; a.dfeat = dfeat_lm_sorted; a.L = L; a.F = F; a.sels = sel_sorted; a.perm = perm;
     a.tile_sf = tile_sf; a.rows = rows; a.S = S; a.dirs = dirs; a.app = app; a.dapp = dapp;
     a.d_density = d_density; a.d_rgb = d_rgb; a.d_sem = d_sem;
+    if (!use_v1()) return launch_field_bwd2_ms(a, (cudaStream_t)stream);
     if (L * F <= 32) return launch_field_bwd_ms<32>(a, (cudaStream_t)stream);
     return launch_field_bwd_ms<48>(a, (cudaStream_t)stream);
 }

@@ -11,6 +11,21 @@
 // its MMA the other runs its epilogue; the weights (54 KB bf16) are staged once per CTA and shared by both groups.
 #include "field_tc5.cuh"
 
+// phase clocks of the debug build: see field_tc5_bwd.cu / tools/phase_clocks.py
+#ifdef PS_PHASE_CLOCKS
+__device__ long long* g_phase_buf_fwd = nullptr;
+#define PS_STAMP(code)                                     \
+    do {                                                   \
+        if (stamp_on && nstamp < 250) {                    \
+            g_phase_buf_fwd[2 * nstamp] = (code);          \
+            g_phase_buf_fwd[2 * nstamp + 1] = clock64();   \
+            ++nstamp;                                      \
+        }                                                  \
+    } while (0)
+#else
+#define PS_STAMP(code)
+#endif
+
 namespace ps {
 namespace ftc5 {
 
@@ -33,6 +48,12 @@ struct FwdSmem {
     static constexpr uint32_t bars = groups + kGroups * group_bytes;    // 2 mbarriers + tmem slot
     static constexpr uint32_t total = bars + 32;
 };
+
+// named barrier of thread group g (immediate ids: tc5.cuh)
+__device__ __forceinline__ void group_sync(int g) {
+    if (g == 0) bar_sync<1, 128>();
+    else bar_sync<2, 128>();
+}
 
 // epilogue of a hidden layer: accumulator row (bias already added by the GEMM) -> ReLU -> bf16 -> columns [0, 64)
 __device__ __forceinline__ void hidden_epilogue64(uint32_t trow, unsigned char* tile, int r) {
@@ -101,7 +122,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
     const uint32_t bar = smem_u32(bar_ptr + g);
     const uint32_t wb = smem_u32(wbase), ones = wb + WL::ones;
     const uint32_t aH = smem_u32(Ht), aSH = smem_u32(SHAPPt), aA = smem_u32(BufA), aB = smem_u32(BufB);
-    const int barid = 1 + g;
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // provably warp-uniform copy (issue branch)
     uint32_t phase = 0;
 
@@ -114,9 +134,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
     float tmin = INFINITY, tmax = -INFINITY;
 
 #define FT_SYNC_ISSUE(...)                 \
+    PS_STAMP(0);                           \
     fence_async_smem();                    \
     fence_before();                        \
-    bar_sync(barid, 128);                  \
+    group_sync(g);                  \
+    PS_STAMP(1);                           \
     if (warp_u == 0) {                     \
         if (elect_one()) {                 \
             fence_after();                 \
@@ -124,13 +146,24 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
             umma_commit(bar);              \
         }                                  \
         __syncwarp();                      \
-    }
+    }                                      \
+    PS_STAMP(2);
 #define FT_WAIT()           \
+    PS_STAMP(5);            \
     mbar_wait(bar, phase);  \
     phase ^= 1;             \
-    fence_after();
+    fence_after();          \
+    PS_STAMP(3);
 
+#ifdef PS_PHASE_CLOCKS
+    int nstamp = 0, tile_iter = 0;
+#endif
     for (int64_t tile = (int64_t)blockIdx.x * kGroups + g; tile < ntiles; tile += (int64_t)gridDim.x * kGroups) {
+#ifdef PS_PHASE_CLOCKS
+        const bool stamp_on = g_phase_buf_fwd != nullptr && blockIdx.x == 0 && tid == 0 && (tile_iter == 3 || tile_iter == 4);
+        ++tile_iter;
+        PS_STAMP(9);
+#endif
         const int q = t / S;                                   // ray within the tile
         const int s = t - q * S;
         const int64_t ray = tile * rpt + q;
@@ -145,6 +178,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
             stage_shapp<K0>(in, valid, SHAPPt, t);
             t0 = in.t0; t1 = in.t1; selv = in.selv;
         }
+        PS_STAMP(8);
         // ---- base network ------------------------------------------------------------------------------
         FT_SYNC_ISSUE(gemm_bias(tmem, ones, wb + WL::bt(B0), kHid, kHid);
                       gemm_kk(tmem, aA, kRows, wb + WL::b0, kHid, kHid, K0, true))
@@ -184,7 +218,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
         const float dd = __fmul_rn(__fsub_rn(t1, t0), density);
         const double dd_incl = warp_scan_incl((double)dd, lane);
         if (lane == 31) tails[warp * 2] = dd_incl;
-        bar_sync(barid, 128);
+        group_sync(g);
         const int w_first = (warp / wpr) * wpr;                // first warp of this warp's ray
         double carry = 0.0;
         for (int k = w_first; k < warp; ++k) carry += tails[k * 2];
@@ -248,7 +282,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
             if (lane == 0) { red[warp * 72 + 66] = c3[0]; red[warp * 72 + 67] = c3[1]; red[warp * 72 + 68] = c3[2]; }
         }
         fence_before();
-        bar_sync(barid, 128);          // red[] / foundw[] complete; every thread is done with the accumulators and tiles
+        group_sync(g);          // red[] / foundw[] complete; every thread is done with the accumulators and tiles
         // per-ray semantics / colour / accumulation / depths
         for (int i = t; i < rpt * 64; i += 128) {
             const int qq = i >> 6, c = i & 63;
@@ -278,7 +312,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(FieldArgs a) 
                 }
             }
         }
-        bar_sync(barid, 128);          // red[] consumed before the next tile overwrites it
+        group_sync(g);          // red[] consumed before the next tile overwrites it
+        PS_STAMP(7);
     }
 #undef FT_SYNC_ISSUE
 #undef FT_WAIT
@@ -349,7 +384,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_ms_kernel(FieldMsArg
     const uint32_t bar = smem_u32(bar_ptr + g);
     const uint32_t wb = smem_u32(wbase), ones = wb + WL::ones;
     const uint32_t aH = smem_u32(Ht), aSH = smem_u32(SHAPPt), aA = smem_u32(BufA), aB = smem_u32(BufB);
-    const int barid = 1 + g;
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
     uint32_t phase = 0;
     const int64_t npairs = a.rows / (2 * kRows);       // taken round-robin: all CTAs stay on (mostly) the same sub-field
@@ -359,7 +393,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_ms_kernel(FieldMsArg
 #define FT_SYNC_ISSUE(...)                 \
     fence_async_smem();                    \
     fence_before();                        \
-    bar_sync(barid, 128);                  \
+    group_sync(g);                  \
     if (warp_u == 0) {                     \
         if (elect_one()) {                 \
             fence_after();                 \
@@ -458,7 +492,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_ms_kernel(FieldMsArg
             }
         }
         fence_before();
-        bar_sync(barid, 128);          // every thread of the group is done with the accumulators and tiles
+        group_sync(g);          // every thread of the group is done with the accumulators and tiles
     }
 #undef FT_SYNC_ISSUE
 #undef FT_WAIT
@@ -490,6 +524,13 @@ static int launch_field_fwd_ms(const FieldMsArgs& a, cudaStream_t stream) {
 
 using namespace ps;
 using namespace ps::ftc5;
+
+#ifdef PS_PHASE_CLOCKS
+/* tools only (debug build) */
+extern "C" int ps_debug_phase_buf_fwd(long long* buf) {
+    return cudaMemcpyToSymbol(g_phase_buf_fwd, &buf, sizeof(buf)) == cudaSuccess ? 0 : 2;
+}
+#endif
 
 int ps_field_check_common(const ps_field_net* net, int L, int F, int64_t N, int S, const char* what);
 

@@ -40,6 +40,16 @@ __host__ __device__ constexpr uint32_t make_idesc(int N, int a_mn, int b_mn) {
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
 }
 
+// the same with an explicit M (64 or 128).  Measured on B200 (tools/m64_probe.py): an M = 64 accumulator of cta_group::1 keeps
+// row m in TMEM lane 32 * (m / 16) + m % 16, i.e. the lower 16 lanes of every 32-lane quadrant; a lane offset of 16 in the
+// D address selects the upper 16 lanes, so two M = 64 accumulators share one set of columns.  16 MN-major N = 64
+// instructions take 785 cycles at M = 64 against 1040 at M = 128 (the A operand read from shared memory halves).
+__host__ __device__ constexpr uint32_t make_idesc_m(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+constexpr uint32_t kLaneHi = 16u << 16;   // D-address offset of the second M = 64 accumulator of a column pair
+
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
@@ -87,9 +97,21 @@ __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::be
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// named barrier over `count` threads (count a multiple of 32); id 0 is __syncthreads' barrier
-__device__ __forceinline__ void bar_sync(int id, int count) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+// Named barriers over COUNT threads (a multiple of 32); id 0 is __syncthreads' barrier.  The id is an IMMEDIATE: with a
+// register operand ptxas reserves all 16 hardware barriers for the CTA ("used 16 barriers"), and since the SM has 16 in
+// all, no other CTA — not even a kernel that uses none — can then share the SM (measured: the fused field kernels and
+// the hash kernels stopped overlapping, tools/overlap_probe.py).
+template <int ID, int COUNT>
+__device__ __forceinline__ void bar_sync() {
+    static_assert(ID >= 1 && ID < 16 && COUNT % 32 == 0, "named barrier");
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
+}
+
+// producer side of a named barrier shared with bar_sync callers: does not wait (count = arriving + waiting threads)
+template <int ID, int COUNT>
+__device__ __forceinline__ void bar_arrive() {
+    static_assert(ID >= 1 && ID < 16 && COUNT % 32 == 0, "named barrier");
+    asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
@@ -203,6 +225,17 @@ __device__ __forceinline__ void gemm_dgrad(uint32_t tmem_d, uint32_t dz_addr, in
 // X's real column count are garbage and must be ignored), N = number of Y columns.
 __device__ __forceinline__ void gemm_wgrad(uint32_t tmem_d, uint32_t x_addr, uint32_t y_addr, int N, bool accumulate) {
     const uint32_t idesc = make_idesc(N, 1, 1);
+    for (int kk = 0; kk < kRows / 16; ++kk) {
+        const uint64_t da = make_desc(x_addr + kk * 256, 128, kRows * 16);
+        const uint64_t db = make_desc(y_addr + kk * 256, 128, kRows * 16);
+        umma_bf16(tmem_d, da, db, idesc, (accumulate || kk > 0) ? 1u : 0u);
+    }
+}
+
+// Weight gradient with M = 64 (out features <= 64): D[m][n] (+)= sum_p X[p][m] * Y[p][n] over the 128 rows of two
+// chunk-major tiles; reads exactly 64 columns of X.  tmem_d may carry kLaneHi.
+__device__ __forceinline__ void gemm_wgrad64(uint32_t tmem_d, uint32_t x_addr, uint32_t y_addr, int N, bool accumulate) {
+    const uint32_t idesc = make_idesc_m(64, N, 1, 1);
     for (int kk = 0; kk < kRows / 16; ++kk) {
         const uint64_t da = make_desc(x_addr + kk * 256, 128, kRows * 16);
         const uint64_t db = make_desc(y_addr + kk * 256, 128, kRows * 16);

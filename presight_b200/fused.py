@@ -38,7 +38,7 @@ def set_overlap_prop_bwd(on: bool) -> bool:
     global OVERLAP_PROP_BWD
     prev, OVERLAP_PROP_BWD = OVERLAP_PROP_BWD, bool(on)
     return prev
-FIELD_CHUNKS = max(1, int(os.environ.get("PS_FIELD_CHUNKS", "3")))
+FIELD_CHUNKS = max(1, int(os.environ.get("PS_FIELD_CHUNKS", "1")))
 
 
 @dataclass(frozen=True)

@@ -60,10 +60,15 @@ def timed(fns):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     s1.wait_stream(torch.cuda.current_stream()); s2.wait_stream(torch.cuda.current_stream())
+    ends = []
     for fn, st in fns:
         fn(st)
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(st)
+        ends.append(e)
     torch.cuda.current_stream().wait_stream(s1); torch.cuda.current_stream().wait_stream(s2)
     b.record(); torch.cuda.synchronize()
+    timed.ends = [a.elapsed_time(e) for e in ends]          # when each kernel finished
     return a.elapsed_time(b)
 
 
@@ -74,4 +79,4 @@ for name, fns in [("field_fwd", [(field_fwd, s1)]), ("hash_fwd", [(hash_fwd, s2)
                   ("field_bwd", [(field_bwd, s1)]), ("hash_bwd", [(hash_bwd, s2)]), ("field_bwd || hash_bwd", [(field_bwd, s1), (hash_bwd, s2)]),
                   ("hash_bwd || field_bwd (hash first)", [(hash_bwd, s2), (field_bwd, s1)])]:
     ts = [timed(fns) for _ in range(3)]
-    print(f"{name:40s} {min(ts):.3f} ms")
+    print(f"{name:40s} {min(ts):.3f} ms   (kernel end times of the last run: {', '.join(f'{t:.3f}' for t in timed.ends)})")
