@@ -9,6 +9,8 @@
 // x-neighbour merge: the hash multiplies x by 1, so for an even floor coordinate the two x-corners of a (y,z)
 // pair are rows r and r^1 — one aligned 2F-float slot.  Backward then issues ONE vector reduction
 // (red.global.add.v4.f32 for F=2, .v2 for F=1) for both corners.
+#include <stdlib.h>
+
 #include "hash_grid.cuh"
 
 namespace ps {

@@ -19,11 +19,11 @@ from presight_b200.model import VIDEO_ID
 lib = _lib.load()
 dev = torch.device("cuda", 0)
 bufs = {}
-for name in ("ps_debug_phase_buf_bwd", "ps_debug_phase_buf_fwd"):
+for name in ("ps_debug_phase_buf_bwd2", "ps_debug_phase_buf_bwd", "ps_debug_phase_buf_fwd"):
     if hasattr(lib, name):
         fn = getattr(lib, name)
         fn.argtypes = [C.c_void_p]
-        bufs[name] = torch.zeros(512, dtype=torch.int64, device=dev)
+        bufs[name] = torch.zeros(1024, dtype=torch.int64, device=dev)
         assert fn(bufs[name].data_ptr()) == 0
 cfg = bench.build_config("c2", "b200")
 torch.manual_seed(42)
@@ -46,14 +46,14 @@ names = {9: "tile start", 8: "inputs staged", 0: "epilogue done", 1: "barrier pa
          5: "about to wait", 3: "group complete", 4: "wgrad group complete", 7: "tile done"}
 for name, buf in bufs.items():
     v = buf.cpu().tolist()
-    print(f"== {name}")
-    prev = None
-    t0 = None
-    for i in range(0, len(v), 2):
-        code, clk = v[i], v[i + 1]
-        if clk == 0:
-            break
-        if t0 is None:
-            t0 = clk
-        print(f"{clk - t0:8d}  +{(clk - prev) if prev is not None else 0:6d}  {code} {names.get(code, '?')}")
-        prev = clk
+    roles = [v[i:i + 256] for i in range(0, len(v), 256)] if name.endswith("bwd2") else [v]
+    t0 = min([r[1] for r in roles if r[1]] or [0])
+    for k, rv in enumerate(roles):
+        print(f"== {name}" + (f" role {k} (0 group R, 1 group S, 2 issuing warp 8, 3 issuing warp 9)" if len(roles) > 1 else ""))
+        prev = None
+        for i in range(0, len(rv), 2):
+            code, clk = rv[i], rv[i + 1]
+            if clk == 0:
+                break
+            print(f"{clk - t0:8d}  +{(clk - prev) if prev is not None else 0:6d}  {code} {names.get(code, '?')}")
+            prev = clk
