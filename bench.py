@@ -421,12 +421,24 @@ def main() -> None:
         return main_c5(args, model, cfg, host, dev, rank, world)
     model.train()
     params = [p for p in model.parameters() if p.requires_grad]
-    sync = GradSynchronizer(params, overlap=True) if world > 1 else None
+    sync = None
     if world > 1:
-        # the 512 MiB main-table all-reduce hides under the proposal levels' backward only if that runs AFTER the final
-        # level (main stream) instead of early on the single-GPU side stream
+        # The 512 MiB main-table gradient is complete only when its last level has been scattered, at the very end of the
+        # backward.  It is exchanged level group by level group from inside the backward (parallel.py), so all but the last
+        # group travel under the remaining scatter and the proposal levels' backward, which keep their single-GPU schedule.
+        # PS_PARTIAL_AR=0: whole-table all-reduce, hidden under the proposal levels' backward run after the final level.
         from presight_b200 import fused
-        fused.set_overlap_prop_bwd(False)
+        from presight_b200.parallel import level_groups
+        partial = []
+        if os.environ.get("PS_PARTIAL_AR", "1") == "1":
+            cuts = os.environ.get("PS_AR_CUTS")
+            for n, m in model.named_modules():
+                if n.endswith("mlp_base_grid") and hasattr(m, "hash_table") and "proposal" not in n:
+                    partial.append((m.hash_table, level_groups(m.num_levels, None if cuts is None else
+                                                               [int(c) for c in cuts.split(",")])))
+        sync = GradSynchronizer(params, overlap=True, partial_tables=partial)
+        if not partial:
+            fused.set_overlap_prop_bwd(False)
     optimizer = None
     if args.optimizer == "torch":
         optimizer = torch.optim.Adam(params, lr=1e-2, eps=1e-15, weight_decay=1e-5)

@@ -40,6 +40,21 @@ def set_overlap_prop_bwd(on: bool) -> bool:
     return prev
 FIELD_CHUNKS = max(1, int(os.environ.get("PS_FIELD_CHUNKS", "1")))
 
+# Partial-gradient sinks (data-parallel training, presight_b200/parallel.py): the main hash table is ONE parameter of 512 MiB
+# whose gradient is complete only when the last level has been scattered — the last kernel of the backward.  A sink registered
+# for the table receives every level group's rows as soon as that group's scatter has been launched (called with the scatter's
+# stream current, so a collective issued inside it is ordered behind exactly that kernel) and can start reducing them while
+# the remaining levels and the proposal networks are still being differentiated.
+_PARTIAL_SINKS = {}          # table.data_ptr() -> (callable(dtable, row_lo, row_hi), level groups [(l0, l1), ...])
+
+
+def register_partial_grad_sink(table: Tensor, fn, level_groups) -> None:
+    _PARTIAL_SINKS[table.data_ptr()] = (fn, [tuple(g) for g in level_groups])
+
+
+def unregister_partial_grad_sink(table: Tensor) -> None:
+    _PARTIAL_SINKS.pop(table.data_ptr(), None)
+
 
 @dataclass(frozen=True)
 class GridMeta:
@@ -515,10 +530,22 @@ class _FieldLevelTc5(torch.autograd.Function):
                 ev = torch.cuda.Event()
                 ev.record(main)
                 side.wait_event(ev)
+            sink = _PARTIAL_SINKS.get(table.data_ptr()) if nc == 1 else None
             with torch.cuda.stream(side):
-                with ops._probe(f"hash_bwd_L{grid.L}F{grid.F}T{grid.log2_T}"):
-                    call("ps_hash_bwd_lm", ptr(x01[c0 * S:c1 * S]), (c1 - c0) * S, None, host_floats(grid.scalings), grid.L,
-                         grid.F, grid.log2_T, ptr(dfeat), ptr(dtable), None, side.cuda_stream)
+                if sink is None:
+                    with ops._probe(f"hash_bwd_L{grid.L}F{grid.F}T{grid.log2_T}"):
+                        call("ps_hash_bwd_lm", ptr(x01[c0 * S:c1 * S]), (c1 - c0) * S, None, host_floats(grid.scalings),
+                             grid.L, grid.F, grid.log2_T, ptr(dfeat), ptr(dtable), None, side.cuda_stream)
+                else:
+                    # one scatter per level group (the kernel is level-major anyway), each handed to the sink at once
+                    fn, groups = sink
+                    T, Pc = 1 << grid.log2_T, (c1 - c0) * S
+                    dfl, dtl = dfeat.view(grid.L, Pc * grid.F), dtable.view(grid.L, T * grid.F)
+                    for (l0, l1) in groups:
+                        with ops._probe(f"hash_bwd_L{grid.L}F{grid.F}T{grid.log2_T}"):
+                            call("ps_hash_bwd_lm", ptr(x01[c0 * S:c1 * S]), Pc, None, host_floats(grid.scalings[l0:l1]),
+                                 l1 - l0, grid.F, grid.log2_T, ptr(dfl[l0:l1]), ptr(dtl[l0:l1]), None, side.cuda_stream)
+                        fn(dtable, l0 * T, l1 * T)
         if piped:
             main.wait_stream(side)   # join (see _PropLevelTc5.backward for why no record_stream is needed)
         del keep

@@ -44,7 +44,7 @@ class GradSynchronizer:
     """Average gradients across ranks.   sync = GradSynchronizer(params); loss.backward(); sync.finish()"""
 
     def __init__(self, params: Iterable[nn.Parameter], group: Optional[dist.ProcessGroup] = None,
-                 overlap: bool = True, min_async_numel: int = 1 << 16) -> None:
+                 overlap: bool = True, min_async_numel: int = 1 << 16, partial_tables=()) -> None:
         self.params: List[nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -56,6 +56,8 @@ class GradSynchronizer:
         self._pending = []       # (work, grad)
         self._done = set()
         self._handles = []
+        self._partial = {}
+        self._partial_tables = []
         if self.world > 1 and overlap:
             # (Scheduling note: the main table's all-reduce can only hide under compute that runs after the final level's
             # backward, so a data-parallel caller wants the proposal levels' backward on the main stream —
@@ -63,9 +65,33 @@ class GradSynchronizer:
             for p in self.params:
                 if p.numel() >= min_async_numel:
                     self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad_ready))
+            # `partial_tables`: (hash-table parameter, level groups) pairs whose gradient is reduced level group by level
+            # group from inside the backward (fused.register_partial_grad_sink).  Needs `p.grad is None` before backward,
+            # so that autograd adopts the kernel's gradient buffer instead of accumulating into an older one.
+            for p, groups in partial_tables:
+                from . import fused
+                fused.register_partial_grad_sink(p, lambda dtable, lo, hi, p=p: self._on_partial(p, dtable, lo, hi), groups)
+                self._partial_tables.append(p)
+
+    def _on_partial(self, p: nn.Parameter, dtable: torch.Tensor, row_lo: int, row_hi: int) -> None:
+        # (runs with the scatter's stream current: NCCL orders the collective behind the kernel that produced these rows)
+        # (a fresh tensor over the same storage, not a view: a view would keep a reference to `dtable` and autograd would
+        # then copy the gradient instead of adopting the buffer)
+        F = dtable.shape[1]
+        piece = torch.empty(0, device=dtable.device, dtype=dtable.dtype).set_(
+            dtable.untyped_storage(), dtable.storage_offset() + row_lo * F, (row_hi - row_lo, F), (F, 1))
+        self._pending.append((dist.all_reduce(piece, op=self._op, group=self.group, async_op=True), piece))
+        self._partial[id(p)] = dtable.data_ptr()
 
     def _on_grad_ready(self, p: nn.Parameter) -> None:
         if p.grad is None:
+            return
+        if id(p) in self._partial:
+            # already travelling piece by piece; the pieces were reduced in place in the buffer autograd must have adopted
+            if p.grad.data_ptr() != self._partial.pop(id(p)):
+                raise RuntimeError("partial gradient exchange: set the hash table's .grad to None before backward "
+                                   "(its gradient was accumulated into an older buffer, the reduced pieces are lost)")
+            self._done.add(id(p))
             return
         self._pending.append((dist.all_reduce(p.grad, op=self._op, group=self.group, async_op=True), p.grad))
         self._done.add(id(p))
@@ -106,6 +132,18 @@ class GradSynchronizer:
         for h in self._handles:
             h.remove()
         self._handles.clear()
+        for p in getattr(self, "_partial_tables", []):
+            from . import fused
+            fused.unregister_partial_grad_sink(p)
+
+
+def level_groups(num_levels: int, cuts=None):
+    """Level groups of the partial exchange of a hash-table gradient: shrinking groups, so that what is still in flight when
+    the backward ends (the last group) is small.  `cuts`: explicit group boundaries, e.g. (6, 11, 14) for 16 levels."""
+    if cuts is None:
+        cuts = sorted({round(num_levels * f) for f in (0.375, 0.6875, 0.875)} - {0, num_levels})
+    edges = [0, *[c for c in cuts if 0 < c < num_levels], num_levels]
+    return [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
 
 
 def shard_range(n_units: int, rank: int, world: int):

@@ -3,6 +3,8 @@
   grads     data-parallel parity: every rank runs the C2-shaped step on its shard of the rays and the
             gradients are averaged by GradSynchronizer (NCCL all-reduce); rank 0 then runs the CONCATENATED batch alone
             and the two sets of gradients must agree.
+  partial   the same parity with the main hash table's gradient exchanged level group by level group from inside the backward
+            (GradSynchronizer(partial_tables=...), proposal levels on their single-GPU side-stream schedule).
   sharded   ShardedFusedAdam (reduce-scatter -> Adam on the shard -> all-gather) against GradSynchronizer + FusedAdam:
             same parameters after several steps, on every rank.
 """
@@ -68,7 +70,7 @@ def main():
     from presight_b200 import fused
     from presight_b200.parallel import GradSynchronizer, init_nccl, shard_range
     init_nccl(dev)
-    fused.set_overlap_prop_bwd(False)
+    fused.set_overlap_prop_bwd(mode == "partial")
     n = 4096
     model, cfg, host = make(n)
     model = model.to(dev).train()
@@ -77,8 +79,13 @@ def main():
     jit = [torch.rand(n, 1, generator=g) for _ in range(3)]
     lo, hi = shard_range(n, rank, world)
     ok = True
-    if mode == "grads":
-        sync = GradSynchronizer(params, overlap=True)
+    if mode in ("grads", "partial"):
+        partial = []
+        if mode == "partial":
+            from presight_b200.parallel import level_groups
+            enc = model.field.fields[0].mlp_base_grid
+            partial = [(enc.hash_table, level_groups(enc.num_levels))]
+        sync = GradSynchronizer(params, overlap=True, partial_tables=partial)
         step_grads(model, host, lo, hi, jit, dev)
         sync.finish()
         torch.cuda.synchronize()
@@ -94,7 +101,7 @@ def main():
                 e = rel_l2(dp[k], p.grad)
                 if e > worst[1]:
                     worst = (k, e)
-            print(f"MULTI grads world={world} worst rel-L2 {worst[1]:.3e} ({worst[0]}) over {len(dp)} tensors", flush=True)
+            print(f"MULTI {mode} world={world} worst rel-L2 {worst[1]:.3e} ({worst[0]}) over {len(dp)} tensors", flush=True)
             ok = worst[1] < 1e-4
     elif mode == "sharded":
         from presight_b200.optim import FusedAdam, ShardedFusedAdam

@@ -25,5 +25,9 @@ def test_two_nccl_ranks_match_the_concatenated_batch():
     assert "MULTI grads" in run("grads")
 
 
+def test_partial_table_exchange_matches_the_concatenated_batch():
+    assert "MULTI partial" in run("partial")
+
+
 def test_sharded_adam_matches_allreduce_plus_adam():
     assert "MULTI sharded" in run("sharded")
