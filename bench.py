@@ -436,7 +436,9 @@ def main() -> None:
                 if n.endswith("mlp_base_grid") and hasattr(m, "hash_table") and "proposal" not in n:
                     partial.append((m.hash_table, level_groups(m.num_levels, None if cuts is None else
                                                                [int(c) for c in cuts.split(",")])))
-        sync = GradSynchronizer(params, overlap=True, partial_tables=partial)
+        # PS_EXCHANGE=nccl: the pieces as NCCL all-reduces; default: copy engines between IPC-mapped buffers (peer_exchange.py)
+        sync = GradSynchronizer(params, overlap=True, partial_tables=partial,
+                                peer=os.environ.get("PS_EXCHANGE", "peer") == "peer")
         if not partial:
             fused.set_overlap_prop_bwd(False)
     optimizer = None

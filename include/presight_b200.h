@@ -17,6 +17,7 @@
 #ifndef PRESIGHT_B200_H
 #define PRESIGHT_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -446,6 +447,34 @@ int ps_field_level_bwd_ms(const ps_field_net_dev* nets_dev, int app_dim, const f
                           const uint8_t* sel_sorted, const int32_t* perm, const uint8_t* tile_sf, int64_t rows, int S,
                           const float* dirs, const float* app, const float* d_density, const float* d_rgb,
                           const float* d_sem, float* dfeat_lm_sorted, float* dapp, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Data-parallel exchange step over peer memory (one node, NVLink / NVSwitch), copy engines instead of collective kernels.
+ * Replaces the all-reduce DDP performs for the reference (pipelines/PreSight/my_pipeline.py:121-124) for the large
+ * gradients; host protocol in presight_b200/peer_exchange.py.
+ *   ps_peer_alloc / free     device buffer that can be exported to the other ranks of the node (plain cudaMalloc)
+ *   ps_peer_export           handle64_host[64] <- cudaIpcMemHandle of the buffer
+ *   ps_peer_open / close     map a buffer exported by another rank (peer access enabled lazily)
+ *   ps_peer_copy             stream-ordered copy between any two (local or mapped) device buffers, on the copy engines
+ *   ps_peer_wait_flags       block the stream until flags[i * stride] == value for all i < n (one polling warp)
+ *   ps_peer_exchange_range   push + reduce + broadcast of one row range as two kernels (see below)
+ *   ps_peer_reduce           dst[i] = scale * (dst[i] + sum_k srcs_host[k][i]), n a multiple of 4, n_src <= PS_MAX_FIELDS
+ */
+int ps_peer_alloc(size_t bytes, void** ptr);
+int ps_peer_free(void* ptr);
+int ps_peer_export(void* ptr, void* handle64_host);
+int ps_peer_open(const void* handle64_host, void** ptr);
+int ps_peer_close(void* ptr);
+int ps_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
+int ps_peer_wait_flags(const uint32_t* flags, int n, int stride, uint32_t value, void* stream);
+int ps_peer_reduce(float* dst, const float* const* srcs_host, int n_src, int64_t n, float scale, void* stream);
+/* The same three phases for one row range with P2P stores from `ctas` small CTAs (push kernel, then wait + average +
+ * broadcast kernel) — no per-copy latency.  peer_bases_host[world]: every rank's allocation as mapped in this process
+ * (this rank's own included); offsets are bytes inside an allocation; flag*_off: [world] uint32 phase flags of the range;
+ * counters: two zero-initialised uint32 in local device memory private to the range. */
+int ps_peer_exchange_range(void* const* peer_bases_host, int world, int rank, size_t g_off, size_t s_off, size_t range_off,
+                           size_t shard_bytes, size_t flag1_off, size_t flag2_off, uint32_t step, float scale,
+                           unsigned int* counters, int ctas, void* stream);
 
 #ifdef __cplusplus
 }

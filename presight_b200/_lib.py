@@ -73,6 +73,16 @@ SIGNATURES = {
     "ps_voxel_finalize": [_p, _i64, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p],
     "ps_hits_quantile": [_p, _i64, C.c_double, _p, _i64, _p, _p, _p],
     "ps_generate_rays": [_p, _p, _p, _p, _p, _i, _p, _i64, _f, _p, _p, _p, _p, _p],
+    "ps_peer_alloc": [C.c_size_t, _p],
+    "ps_peer_free": [_p],
+    "ps_peer_export": [_p, _p],
+    "ps_peer_open": [_p, _p],
+    "ps_peer_close": [_p],
+    "ps_peer_copy": [_p, _p, C.c_size_t, _p],
+    "ps_peer_wait_flags": [_p, _i, _i, C.c_uint32, _p],
+    "ps_peer_reduce": [_p, _p, _i, _i64, _f, _p],
+    "ps_peer_exchange_range": [_p, _i, _i, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint32, _f,
+                               _p, _i, _p],
     "ps_adam_step": [_p, _p, _p, _p, _i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _i64, _p],
     "ps_tc5_probe": [_p, _p, _p, _p, _p, _p, _p, _p],
     "ps_field_level_fwd": [_p, _p, _i, _i, _p, _p, _p, _p, _i64, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p],

@@ -45,11 +45,21 @@ FIELD_CHUNKS = max(1, int(os.environ.get("PS_FIELD_CHUNKS", "1")))
 # for the table receives every level group's rows as soon as that group's scatter has been launched (called with the scatter's
 # stream current, so a collective issued inside it is ordered behind exactly that kernel) and can start reducing them while
 # the remaining levels and the proposal networks are still being differentiated.
-_PARTIAL_SINKS = {}          # table.data_ptr() -> (callable(dtable, row_lo, row_hi), level groups [(l0, l1), ...])
+# device index -> [event recorded behind the step's (last) field backward kernel, proposal backwards launched since]
+# (autograd runs the field level's backward first).  PS_PROP_BWD_ORDER: "second" = the first proposal backward of a step starts
+# at once, later ones wait for the field kernel; "all" = all wait; "free" = no ordering (which of two kernels launched
+# microseconds apart on different streams gets the SMs first is then a race).
+_FIELD_BWD_ORDER = {}
+PROP_BWD_ORDER = os.environ.get("PS_PROP_BWD_ORDER", "free")
+PROP_BWD_PRIO = os.environ.get("PS_PROP_BWD_PRIO", "0") == "1"      # proposal backwards on a high-priority stream
+
+_PARTIAL_SINKS = {}          # table.data_ptr() -> (callable(dtable, row_lo, row_hi), level groups [(l0, l1), ...], alloc)
 
 
-def register_partial_grad_sink(table: Tensor, fn, level_groups) -> None:
-    _PARTIAL_SINKS[table.data_ptr()] = (fn, [tuple(g) for g in level_groups])
+def register_partial_grad_sink(table: Tensor, fn, level_groups, alloc=None) -> None:
+    """`alloc` (optional): () -> the zero-filled gradient buffer to scatter into (called with the scatter's stream current),
+    for exchanges that need the gradient in memory of their own (peer_exchange.py); default torch.zeros_like(table)."""
+    _PARTIAL_SINKS[table.data_ptr()] = (fn, [tuple(g) for g in level_groups], alloc)
 
 
 def unregister_partial_grad_sink(table: Tensor) -> None:
@@ -218,10 +228,20 @@ class _PropLevelTc5(torch.autograd.Function):
         # the producer of `dw` published its completion event, run this backward on a side stream so that it overlaps
         # the field kernels / main hash scatter already queued on the main stream.
         ev_in = ops.pop_grad_event(dw, ctx.grad_key) if OVERLAP_PROP_BWD else None
-        run_on = ops.side_stream(eu.device, 1) if ev_in is not None else main
+        run_on = ops.side_stream(eu.device, 1, high_priority=PROP_BWD_PRIO) if ev_in is not None else main
         with torch.cuda.stream(run_on):
             if ev_in is not None:
                 run_on.wait_event(ev_in)
+                # Order against the final level's backward (see _FIELD_BWD_ORDER): a proposal backward that autograd runs
+                # before the field level's (it finds the SMs idle while the main stream is still busy with the loss
+                # gradients) starts at once; one that comes after it starts when the field kernel — which needs whole SMs
+                # and all of tensor memory, so cannot share them with this kernel's persistent CTAs — has finished, and then
+                # co-runs with the main hash scatter.
+                order = _FIELD_BWD_ORDER.get(eu.device.index)
+                if order is not None and PROP_BWD_ORDER != "free":
+                    if order[1] >= 1 or PROP_BWD_ORDER == "all":
+                        run_on.wait_event(order[0])
+                    order[1] += 1
             dwc = _f32c(dw).view(N, S)
             zs = _zeros_like_many([*ws, *bs])
             dws, dbs = zs[:2], zs[2:]
@@ -515,8 +535,10 @@ class _FieldLevelTc5(torch.autograd.Function):
         side = ops.side_stream(dev, 0) if piped else main
         if piped:
             side.wait_stream(main)                    # fork (also what makes the side stream part of a graph capture)
+        sink = _PARTIAL_SINKS.get(table.data_ptr()) if nc == 1 else None
         with torch.cuda.stream(side):
-            dtable = torch.zeros_like(table)          # (the 512 MiB memset runs under the first field slice)
+            # (the 512 MiB memset runs under the first field slice)
+            dtable = sink[2]() if (sink is not None and sink[2] is not None) else torch.zeros_like(table)
         keep = []            # main-stream buffers read on the side stream: alive until the join below
         for i, (c0, c1) in enumerate(bounds):
             dfeat = torch.empty_like(feats[i])
@@ -526,11 +548,13 @@ class _FieldLevelTc5(torch.autograd.Function):
                      ptr(eu[c0:c1]), ptr(d[c0:c1]), None if app_c is None else ptr(app_c[c0:c1]), c1 - c0, S,
                      ptr(acc[c0:c1]), ptr(dexp[c0:c1]), sl(dwc, c0, c1), sl(drgbc, c0, c1), sl(daccc, c0, c1),
                      sl(ddexpc, c0, c1), sl(dsemc, c0, c1), ptr(dfeat), sl(dapp, c0, c1), stream())
-            if piped:
+            if piped or i == nc - 1:
                 ev = torch.cuda.Event()
                 ev.record(main)
-                side.wait_event(ev)
-            sink = _PARTIAL_SINKS.get(table.data_ptr()) if nc == 1 else None
+                if piped:
+                    side.wait_event(ev)
+                if i == nc - 1:
+                    _FIELD_BWD_ORDER[dev.index] = [ev, 0]      # [field backward done, proposal backwards launched since]
             with torch.cuda.stream(side):
                 if sink is None:
                     with ops._probe(f"hash_bwd_L{grid.L}F{grid.F}T{grid.log2_T}"):
@@ -538,7 +562,7 @@ class _FieldLevelTc5(torch.autograd.Function):
                              grid.L, grid.F, grid.log2_T, ptr(dfeat), ptr(dtable), None, side.cuda_stream)
                 else:
                     # one scatter per level group (the kernel is level-major anyway), each handed to the sink at once
-                    fn, groups = sink
+                    fn, groups = sink[0], sink[1]
                     T, Pc = 1 << grid.log2_T, (c1 - c0) * S
                     dfl, dtl = dfeat.view(grid.L, Pc * grid.F), dtable.view(grid.L, T * grid.F)
                     for (l0, l1) in groups:

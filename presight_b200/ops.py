@@ -467,10 +467,13 @@ def pop_grad_event(t: Tensor, key):
 _SIDE_STREAMS = {}
 
 
-def side_stream(device, idx: int = 0) -> "torch.cuda.Stream":
+def side_stream(device, idx: int = 0, high_priority: bool = False) -> "torch.cuda.Stream":
+    """Cached side streams.  `high_priority` (honoured when the stream is first created): among kernels that become runnable
+    at the same moment the block scheduler serves the older launch first and a later one only gets what is left — a kernel
+    meant to co-run from the start has to outrank the one launched before it."""
     key = (torch.device(device).index, idx)
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device, priority=-1 if high_priority else 0)
     return _SIDE_STREAMS[key]
 
 

@@ -44,7 +44,7 @@ class GradSynchronizer:
     """Average gradients across ranks.   sync = GradSynchronizer(params); loss.backward(); sync.finish()"""
 
     def __init__(self, params: Iterable[nn.Parameter], group: Optional[dist.ProcessGroup] = None,
-                 overlap: bool = True, min_async_numel: int = 1 << 16, partial_tables=()) -> None:
+                 overlap: bool = True, min_async_numel: int = 1 << 16, partial_tables=(), peer: bool = False) -> None:
         self.params: List[nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -58,6 +58,8 @@ class GradSynchronizer:
         self._handles = []
         self._partial = {}
         self._partial_tables = []
+        self._peer = None
+        self._peer_names = {}
         if self.world > 1 and overlap:
             # (Scheduling note: the main table's all-reduce can only hide under compute that runs after the final level's
             # backward, so a data-parallel caller wants the proposal levels' backward on the main stream —
@@ -68,13 +70,36 @@ class GradSynchronizer:
             # `partial_tables`: (hash-table parameter, level groups) pairs whose gradient is reduced level group by level
             # group from inside the backward (fused.register_partial_grad_sink).  Needs `p.grad is None` before backward,
             # so that autograd adopts the kernel's gradient buffer instead of accumulating into an older one.
+            # `peer=True`: those pieces travel on the copy engines between IPC-mapped buffers (peer_exchange.py) instead of
+            # NCCL all-reduces, and the table's gradient lives in the exchange's own buffer.
+            if peer and partial_tables:
+                from .peer_exchange import PeerExchange
+                specs = {}
+                for i, (p, groups) in enumerate(partial_tables):
+                    T = p.shape[0] // max(g[1] for g in groups)       # rows per level
+                    specs[f"t{i}"] = (p.shape[0], p.shape[1], [(l0 * T, l1 * T) for l0, l1 in groups])
+                    self._peer_names[id(p)] = f"t{i}"
+                self._peer = PeerExchange(specs, self.params[0].device, group)
             for p, groups in partial_tables:
                 from . import fused
-                fused.register_partial_grad_sink(p, lambda dtable, lo, hi, p=p: self._on_partial(p, dtable, lo, hi), groups)
+                alloc = None
+                if self._peer is not None:
+                    def alloc(name=self._peer_names[id(p)]):
+                        buf = self._peer.grad_buffer(name)
+                        buf.zero_()
+                        return buf
+                fused.register_partial_grad_sink(p, lambda dtable, lo, hi, p=p: self._on_partial(p, dtable, lo, hi), groups, alloc)
                 self._partial_tables.append(p)
 
     def _on_partial(self, p: nn.Parameter, dtable: torch.Tensor, row_lo: int, row_hi: int) -> None:
-        # (runs with the scatter's stream current: NCCL orders the collective behind the kernel that produced these rows)
+        # (runs with the scatter's stream current: the exchange is ordered behind the kernel that produced these rows)
+        if self._peer is not None:
+            name = self._peer_names[id(p)]
+            assert dtable.data_ptr() == self._peer.grad_ptr(name), "peer exchange: gradient not in the exchange's buffer"
+            k = [g[0] for g in self._peer.specs[name][2]].index(row_lo)
+            self._peer.exchange(name, k)
+            self._partial[id(p)] = dtable.data_ptr()
+            return
         # (a fresh tensor over the same storage, not a view: a view would keep a reference to `dtable` and autograd would
         # then copy the gradient instead of adopting the buffer)
         F = dtable.shape[1]
@@ -121,6 +146,8 @@ class GradSynchronizer:
                     p.grad = torch.empty_like(p)
                 p.grad.copy_(flat[off:off + n].view_as(p))
                 off += n
+        if getattr(self, "_peer", None) is not None:
+            self._peer.finish()
         for work, grad in self._pending:
             work.wait()
             if not self._avg:
@@ -135,13 +162,17 @@ class GradSynchronizer:
         for p in getattr(self, "_partial_tables", []):
             from . import fused
             fused.unregister_partial_grad_sink(p)
+        if getattr(self, "_peer", None) is not None:
+            self._peer.close()
+            self._peer = None
 
 
 def level_groups(num_levels: int, cuts=None):
-    """Level groups of the partial exchange of a hash-table gradient: shrinking groups, so that what is still in flight when
-    the backward ends (the last group) is small.  `cuts`: explicit group boundaries, e.g. (6, 11, 14) for 16 levels."""
+    """Level groups of the partial exchange of a hash-table gradient: a small first group (the exchange starts early), small
+    last groups (little is still in flight when the backward ends).  `cuts`: explicit group boundaries; the default for 16
+    levels is (2, 5, 9, 13, 15) — 13.02 ms/step at 8 GPUs against 13.28 with (6, 11, 14), profiles/r2_e_n8_variants.txt."""
     if cuts is None:
-        cuts = sorted({round(num_levels * f) for f in (0.375, 0.6875, 0.875)} - {0, num_levels})
+        cuts = sorted({round(num_levels * f) for f in (0.125, 0.3125, 0.5625, 0.8125, 0.9375)} - {0, num_levels})
     edges = [0, *[c for c in cuts if 0 < c < num_levels], num_levels]
     return [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
 

@@ -29,5 +29,9 @@ def test_partial_table_exchange_matches_the_concatenated_batch():
     assert "MULTI partial" in run("partial")
 
 
+def test_peer_memory_exchange_matches_the_concatenated_batch():
+    assert "MULTI peer" in run("peer")
+
+
 def test_sharded_adam_matches_allreduce_plus_adam():
     assert "MULTI sharded" in run("sharded")
