@@ -436,9 +436,10 @@ def main() -> None:
                 if n.endswith("mlp_base_grid") and hasattr(m, "hash_table") and "proposal" not in n:
                     partial.append((m.hash_table, level_groups(m.num_levels, None if cuts is None else
                                                                [int(c) for c in cuts.split(",")])))
-        # PS_EXCHANGE=nccl: the pieces as NCCL all-reduces; default: copy engines between IPC-mapped buffers (peer_exchange.py)
+        # PS_EXCHANGE=peer: the pieces on the copy engines between IPC-mapped buffers (peer_exchange.py) instead of NCCL
+        # all-reduces (parity-tested; at 2 GPUs no faster than NCCL, profiles/r2_e_n2_variants.txt, so not the default)
         sync = GradSynchronizer(params, overlap=True, partial_tables=partial,
-                                peer=os.environ.get("PS_EXCHANGE", "peer") == "peer")
+                                peer=os.environ.get("PS_EXCHANGE", "nccl") == "peer")
         if not partial:
             fused.set_overlap_prop_bwd(False)
     optimizer = None

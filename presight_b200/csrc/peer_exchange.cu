@@ -19,7 +19,8 @@ namespace ps {
 // all `n` flags (stride in elements) equal `value`: one warp polls, lane i the flags i, i + 32, ...
 __global__ void peer_wait_flags_kernel(const volatile uint32_t* flags, int n, int stride, uint32_t value) {
     for (int i = threadIdx.x; i < n; i += 32) {
-        while (flags[(size_t)i * stride] != value) __nanosleep(200);
+        // (step numbers only grow: a flag that has already moved on also satisfies the wait)
+        while ((int32_t)(flags[(size_t)i * stride] - value) < 0) __nanosleep(200);
     }
     __threadfence_system();
 }
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(256) peer_push_kernel(PeerRange a) {
 __global__ void __launch_bounds__(256) peer_reduce_bcast_kernel(PeerRange a) {
     if (threadIdx.x < a.world) {
         const volatile uint32_t* f = reinterpret_cast<const volatile uint32_t*>(a.base[a.rank] + a.flag1_off) + threadIdx.x;
-        while (*f != a.step) __nanosleep(200);
+        while ((int32_t)(*f - a.step) < 0) __nanosleep(200);
         __threadfence_system();
     }
     __syncthreads();

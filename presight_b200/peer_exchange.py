@@ -124,6 +124,9 @@ class PeerExchange:
     def _begin(self) -> None:
         if not self._open_step:
             self.step += 1
+            # (the previous step's flag copies read `cur`: finish() made the caller's stream wait for them, so order the
+            # update behind the caller's stream — a flag that carried the next step's number would never match)
+            self.comm.wait_stream(torch.cuda.current_stream(self.dev))
             with torch.cuda.stream(self.comm):
                 self.cur.fill_(self.step)
             filled = torch.cuda.Event()

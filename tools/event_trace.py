@@ -38,7 +38,7 @@ if world > 1:
                    if n.endswith("mlp_base_grid") and hasattr(m, "hash_table") and "proposal" not in n]
     else:
         fused.set_overlap_prop_bwd(False)
-    sync = GradSynchronizer(params, overlap=True, partial_tables=partial, peer=os.environ.get("PS_EXCHANGE", "peer") == "peer")
+    sync = GradSynchronizer(params, overlap=True, partial_tables=partial, peer=os.environ.get("PS_EXCHANGE", "nccl") == "peer")
 keys = ("origins", "directions", "camera_indices", "video_ids", "rgb", "features", "sky")
 b = {k: host[k].to(dev) for k in keys}
 
