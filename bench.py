@@ -435,7 +435,7 @@ def main() -> None:
             for n, m in model.named_modules():
                 if n.endswith("mlp_base_grid") and hasattr(m, "hash_table") and "proposal" not in n:
                     partial.append((m.hash_table, level_groups(m.num_levels, None if cuts is None else
-                                                               [int(c) for c in cuts.split(",")])))
+                                                               [int(c) for c in cuts.split(",")], world)))
         # PS_EXCHANGE=peer: the pieces on the copy engines between IPC-mapped buffers (peer_exchange.py) instead of NCCL
         # all-reduces (parity-tested; at 2 GPUs no faster than NCCL, profiles/r2_e_n2_variants.txt, so not the default)
         sync = GradSynchronizer(params, overlap=True, partial_tables=partial,

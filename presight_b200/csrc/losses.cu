@@ -130,8 +130,9 @@ __global__ void __launch_bounds__(128) zaa_interlevel_kernel(const float* __rest
 
 // The default kernel (B200, 65 536 rays, S = 64, Sp = 128: 0.24 ms per level against 0.91 ms for the thread-per-ray
 // kernel above, gpurun_out/r2_zaa_exp.txt; both pass the reference fixture): the same loss with one WARP per ray, following the loop-free formulation that tools/zaa_parallel_prototype.py checks
-// against the reference's fixture — merge by rank (two binary searches per knot; "c - r first on ties"), fp64-carried
-// warp scans over the knots in chunks of 32, interval lookup and flat-run lookup by binary search per query.
+// against the reference's fixture — merge by rank ("c - r first on ties"; ranks found by short walks from the knot's own
+// index), fp64 running sums over the knots (blocked per lane, one warp scan per pass), interval lookup by a branch-free
+// binary search per query, flat-run lookup only where the integral is flat.
 // Shared memory per warp (floats): c[S+1] | wn[S+1] | xr[K] | y2[K] | yr[K] | cdf[K] | ret[Sp+1],  K = 2S + 2.
 constexpr int kZaaWarps = 4;
 
@@ -152,7 +153,7 @@ __device__ __forceinline__ int zaa_count_lt(const float* a, int n, float v) {   
     return lo;
 }
 
-__global__ void __launch_bounds__(kZaaWarps * 32) zaa_interlevel_warp_kernel(
+__global__ void __launch_bounds__(kZaaWarps * 32, 12) zaa_interlevel_warp_kernel(
     const float* __restrict__ c, const float* __restrict__ w, int64_t N, int S, const float* __restrict__ cp,
     const float* __restrict__ wp, int Sp, double r, float* __restrict__ loss_sum, float* __restrict__ grad_wp) {
     extern __shared__ float smem[];
@@ -173,58 +174,73 @@ __global__ void __launch_bounds__(kZaaWarps * 32) zaa_interlevel_warp_kernel(
     for (int k = lane; k <= S; k += 32) wn[k] = k < S ? __fdiv_rn(__ldg(w + n * S + k), __fsub_rn(cs[k + 1], cs[k])) : 0.f;
     __syncwarp();
     // ---- merge by rank ----------------------------------------------------------------------------------------------
+    // knot a_e = c[e] - r goes behind the a-knots before it and the b-knots c[k] + r < a_e — all of which have k < e, and
+    // (c sorted) form a prefix: walk down from e - 1 instead of searching (the pulse is narrower than most bins: 0-2 steps).
+    // Likewise b_e = c[e] + r goes behind all a-knots c[k] - r <= b_e: every k <= e, and a run of k > e.
     for (int e = lane; e <= S; e += 32) {
         const float a = __fsub_rn(cs[e], rf), b = __fadd_rn(cs[e], rf);
-        int lo = 0, hi = S + 1;                              // #{k : c[k] + r < a}
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (__fadd_rn(cs[mid], rf) < a) lo = mid + 1; else hi = mid;
-        }
-        const int pos_a = e + lo;
-        lo = 0; hi = S + 1;                                  // #{k : c[k] - r <= b}
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (__fsub_rn(cs[mid], rf) <= b) lo = mid + 1; else hi = mid;
-        }
-        const int pos_b = e + lo;
+        int k = e - 1;
+        while (k >= 0 && !(__fadd_rn(cs[k], rf) < a)) --k;
+        const int pos_a = e + (k + 1);
+        k = e + 1;
+        while (k <= S && __fsub_rn(cs[k], rf) <= b) ++k;
+        const int pos_b = e + k;
         const float y1 = __fdiv_rn(__fsub_rn(wn[e], e > 0 ? wn[e - 1] : 0.f), two_r);     // wn[S] = 0 is the right pad
         xr[pos_a] = a; y2[pos_a] = y1;
         xr[pos_b] = b; y2[pos_b] = -y1;
     }
     __syncwarp();
     // ---- the two nested running sums (fp64 carry, fp32 outputs), then the running integral -------------------------------
-    double carry1 = 0.0, carry2 = 0.0;
+    // Blocked: lane l owns the `per` consecutive intervals [l * per, (l + 1) * per) (per odd: conflict-free strides), sums
+    // them serially and ONE warp scan per pass turns the lane totals into offsets (3 scans instead of 3 per chunk of 32).
+    int per = (K - 1 + 31) / 32;
+    per |= 1;
+    const int k0 = lane * per, k1 = min(k0 + per, K - 1);
     if (lane == 0) { yr[0] = 0.f; cdf[0] = 0.f; }
-    for (int base = 0; base < K - 1; base += 32) {
-        const int k = base + lane;
-        const bool on = k < K - 1;
-        const double in1 = warp_scan_incl(on ? (double)y2[k] : 0.0, lane) + carry1;
-        const float prod = on ? __fmul_rn(__fsub_rn(xr[k + 1], xr[k]), (float)in1) : 0.f;
-        const double in2 = warp_scan_incl((double)prod, lane) + carry2;
-        if (on) yr[k + 1] = fmaxf((float)in2, 0.f);
-        carry1 = __shfl_sync(0xffffffffu, in1, 31);
-        carry2 = __shfl_sync(0xffffffffu, in2, 31);
+    {
+        double t = 0.0;
+        for (int k = k0; k < k1; ++k) t += (double)y2[k];
+        double run = warp_scan_incl(t, lane) - t;            // exclusive offset of this lane's block
+        double t2 = 0.0;
+        for (int k = k0; k < k1; ++k) {
+            run += (double)y2[k];
+            const float prod = __fmul_rn(__fsub_rn(xr[k + 1], xr[k]), (float)run);
+            cdf[k + 1] = prod;                               // parked here until the third pass overwrites it
+            t2 += (double)prod;
+        }
+        double run2 = warp_scan_incl(t2, lane) - t2;
+        for (int k = k0; k < k1; ++k) {
+            run2 += (double)cdf[k + 1];
+            yr[k + 1] = fmaxf((float)run2, 0.f);
+        }
     }
     __syncwarp();
-    double carry3 = 0.0;
-    for (int base = 0; base < K - 1; base += 32) {
-        const int k = base + lane;
-        const bool on = k < K - 1;
-        const float area = on ? __fmul_rn(__fmul_rn(0.5f, __fadd_rn(yr[k + 1], yr[k])), __fsub_rn(xr[k + 1], xr[k])) : 0.f;
-        const double in3 = warp_scan_incl((double)area, lane) + carry3;
-        if (on) cdf[k + 1] = (float)in3;
-        carry3 = __shfl_sync(0xffffffffu, in3, 31);
+    {
+        double t = 0.0;
+        for (int k = k0; k < k1; ++k)
+            t += (double)__fmul_rn(__fmul_rn(0.5f, __fadd_rn(yr[k + 1], yr[k])), __fsub_rn(xr[k + 1], xr[k]));
+        double run = warp_scan_incl(t, lane) - t;
+        for (int k = k0; k < k1; ++k) {
+            run += (double)__fmul_rn(__fmul_rn(0.5f, __fadd_rn(yr[k + 1], yr[k])), __fsub_rn(xr[k + 1], xr[k]));
+            cdf[k + 1] = (float)run;
+        }
     }
     __syncwarp();
     // ---- sorted_interp_quad at the proposal bin edges -------------------------------------------------------------------
     const float cdf_last = cdf[K - 1], yr_first = yr[0];
+    const int top = 1 << (31 - __clz(K));
     for (int m = lane; m <= Sp; m += 32) {
         const float x = __ldg(cp + n * (Sp + 1) + m);
-        const int j = zaa_count_le(xr, K, x) - 1;            // last knot <= x
+        int j = 0;                                           // #{knots <= x} by a branch-free descent, then - 1
+        for (int step = top; step >= 1; step >>= 1)
+            if (j + step <= K && xr[j + step - 1] <= x) j += step;
+        j -= 1;                                              // last knot <= x
         float v = 0.f;
         if (j >= 0) {
             const float x0 = xr[j], c0 = cdf[j];
-            const float f0 = yr[zaa_count_lt(cdf, K, c0)];   // first knot of the flat run of the integral (argmax on ties)
+            // first knot of the flat run of the integral (argmax on ties): the knot itself unless the integral is flat here
+            const int jf = (j == 0 || cdf[j - 1] < c0) ? j : zaa_count_lt(cdf, K, c0);
+            const float f0 = yr[jf];
             float f1, o;
             if (j + 1 < K) {
                 f1 = cdf_last == cdf[j + 1] ? yr_first : yr[j + 1];

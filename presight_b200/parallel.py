@@ -167,12 +167,14 @@ class GradSynchronizer:
             self._peer = None
 
 
-def level_groups(num_levels: int, cuts=None):
+def level_groups(num_levels: int, cuts=None, world: int = 8):
     """Level groups of the partial exchange of a hash-table gradient: a small first group (the exchange starts early), small
-    last groups (little is still in flight when the backward ends).  `cuts`: explicit group boundaries; the default for 16
-    levels is (2, 5, 9, 13, 15) — 13.02 ms/step at 8 GPUs against 13.28 with (6, 11, 14), profiles/r2_e_n8_variants.txt."""
+    last groups (little is still in flight when the backward ends).  `cuts`: explicit group boundaries.  Defaults for 16
+    levels: (2, 5, 9, 13, 15) — 13.02 ms/step at 8 GPUs against 13.28 with (6, 11, 14), profiles/r2_e_n8_variants.txt; at 2
+    ranks (NCCL's LL protocol, few large messages are better) the coarser (6, 11, 14): 11.94 against 12.3 ms."""
     if cuts is None:
-        cuts = sorted({round(num_levels * f) for f in (0.125, 0.3125, 0.5625, 0.8125, 0.9375)} - {0, num_levels})
+        fr = (0.375, 0.6875, 0.875) if world <= 2 else (0.125, 0.3125, 0.5625, 0.8125, 0.9375)
+        cuts = sorted({round(num_levels * f) for f in fr} - {0, num_levels})
     edges = [0, *[c for c in cuts if 0 < c < num_levels], num_levels]
     return [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
 

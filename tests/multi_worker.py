@@ -85,7 +85,7 @@ def main():
         if mode in ("partial", "peer"):
             from presight_b200.parallel import level_groups
             enc = model.field.fields[0].mlp_base_grid
-            partial = [(enc.hash_table, level_groups(enc.num_levels))]
+            partial = [(enc.hash_table, level_groups(enc.num_levels, world=world))]
         sync = GradSynchronizer(params, overlap=True, partial_tables=partial, peer=mode == "peer")
         step_grads(model, host, lo, hi, jit, dev)
         sync.finish()

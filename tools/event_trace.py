@@ -34,7 +34,7 @@ if world > 1:
     init_nccl(dev)
     partial = []
     if os.environ.get("PS_PARTIAL_AR", "1") == "1":
-        partial = [(m.hash_table, level_groups(m.num_levels)) for n, m in model.named_modules()
+        partial = [(m.hash_table, level_groups(m.num_levels, world=world)) for n, m in model.named_modules()
                    if n.endswith("mlp_base_grid") and hasattr(m, "hash_table") and "proposal" not in n]
     else:
         fused.set_overlap_prop_bwd(False)
