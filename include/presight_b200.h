@@ -449,6 +449,20 @@ int ps_field_level_bwd_ms(const ps_field_net_dev* nets_dev, int app_dim, const f
                           const float* d_sem, float* dfeat_lm_sorted, float* dapp, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Batch assembly on the device.  Replaces ImageChunk.__getitem__ + the DataLoader's collate + the host->device
+ * copies of next_train_image (data/PreSight/my_dataset.py:52-73, my_datamanager.py:257-285) for a chunk that is resident in
+ * HBM: row idx[b] of every field -> row b of the batch, ray_index[b] = (image_index, pixel_index / width, pixel_index % width).
+ *   chunk fields [n_chunk, ...]: rgbs [.,3] f32, segs u8 (nullable), skies f32, depths f32, features [.,C] f32 (nullable),
+ *                pixel_indices / image_indices / video_ids / widths i64
+ *   idx [B] i64 (the sampler's indices); bad_index_flag: set to 1 if an index falls outside the chunk
+ */
+int ps_assemble_batch(const float* rgbs, const uint8_t* segs, const float* skies, const float* depths, const float* features,
+                      int C, const int64_t* pixel_indices, const int64_t* image_indices, const int64_t* video_ids,
+                      const int64_t* widths, int64_t n_chunk, const int64_t* idx, int64_t B, float* rgb, uint8_t* seg,
+                      float* sky, float* depth, float* feat, int64_t* image_index, int64_t* video_id, int64_t* ray_index,
+                      int* bad_index_flag, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Data-parallel exchange step over peer memory (one node, NVLink / NVSwitch), copy engines instead of collective kernels.
  * Replaces the all-reduce DDP performs for the reference (pipelines/PreSight/my_pipeline.py:121-124) for the large
  * gradients; host protocol in presight_b200/peer_exchange.py.

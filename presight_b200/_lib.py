@@ -73,6 +73,7 @@ SIGNATURES = {
     "ps_voxel_finalize": [_p, _i64, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p],
     "ps_hits_quantile": [_p, _i64, C.c_double, _p, _i64, _p, _p, _p],
     "ps_generate_rays": [_p, _p, _p, _p, _p, _i, _p, _i64, _f, _p, _p, _p, _p, _p],
+    "ps_assemble_batch": [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "ps_peer_alloc": [C.c_size_t, _p],
     "ps_peer_free": [_p],
     "ps_peer_export": [_p, _p],
