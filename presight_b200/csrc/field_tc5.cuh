@@ -73,7 +73,8 @@ struct FieldArgs {
 // shared-memory weight tiles (bf16 chunk-major, rows = out features).  Every layer also has a 16-column "bias tile"
 // [N x 16]: column 0 = bf16(b), column 1 = bf16(b - bf16(b)) — one extra K step of the forward GEMM against a constant
 // A operand whose first two columns are 1 adds the bias (to ~2^-17 relative) on the tensor core, so no epilogue touches
-// it.  `ones`: that constant A operand as one 128-byte core-matrix block {1,1,0,..} x 8 rows + a zero block (the
+// it.  Only the tile's first 8-column chunk is stored per layer; the second (all zeros) is ONE chunk shared by all layers —
+// the descriptor's distance between K chunks simply points at it (6.4 KB less shared memory).  `ones`: that constant A operand as one 128-byte core-matrix block {1,1,0,..} x 8 rows + a zero block (the
 // descriptor's row-group stride is 0, so all 128 rows alias the block).
 template <int K0>
 struct WLayout {
@@ -85,8 +86,9 @@ struct WLayout {
     static constexpr uint32_t r0 = s2 + cm_bytes(kSem, kHid);
     static constexpr uint32_t r1 = r0 + cm_bytes(kHid, kRgbIn);
     static constexpr uint32_t r2 = r1 + cm_bytes(kHid, kHid);
-    static constexpr uint32_t bt0 = r2 + cm_bytes(kRgbOut, kHid);            // bias tiles, layer order B0..R2
-    static constexpr uint32_t ones = bt0 + 480 * 32;                          // 256 B
+    static constexpr uint32_t bt0 = r2 + cm_bytes(kRgbOut, kHid);            // bias chunks [N x 8], layer order B0..R2
+    static constexpr uint32_t btz = bt0 + 480 * 16;                           // the zero chunk all bias tiles share (80 rows)
+    static constexpr uint32_t ones = btz + kBaseOut * 16;                     // 256 B
     static constexpr uint32_t onehot = ones + 256;                            // kLayers x 256 B (backward: bias gradients)
     static constexpr uint32_t end = onehot + kLayers * 256;
     __host__ __device__ static constexpr int rows(int l) {
@@ -94,7 +96,7 @@ struct WLayout {
     }
     __host__ __device__ static constexpr uint32_t bt(int l) {
         uint32_t off = bt0;
-        for (int i = 0; i < l; ++i) off += rows(i) * 32;
+        for (int i = 0; i < l; ++i) off += rows(i) * 16;
         return off;
     }
 };
@@ -116,8 +118,8 @@ __device__ __forceinline__ void gemm_bias_grad(uint32_t tmem_d, uint32_t dz_addr
 }
 
 // D[128 x N] = 1 * bias^T : the first K step of every forward GEMM (accumulate = false)
-__device__ __forceinline__ void gemm_bias(uint32_t tmem_d, uint32_t ones_addr, uint32_t bias_tile, int b_rows, int N) {
-    umma_bf16(tmem_d, make_desc(ones_addr, 128, 0), make_desc(bias_tile, b_rows * 16, 128), make_idesc(N, 0, 0), 0u);
+__device__ __forceinline__ void gemm_bias(uint32_t tmem_d, uint32_t ones_addr, uint32_t bias_tile, uint32_t zero_chunk, int N) {
+    umma_bf16(tmem_d, make_desc(ones_addr, 128, 0), make_desc(bias_tile, zero_chunk - bias_tile, 128), make_idesc(N, 0, 0), 0u);
 }
 
 template <int K0>
@@ -144,8 +146,8 @@ __device__ __forceinline__ void load_all_weights(const FieldNet& net, unsigned c
     for (int l = 0; l < kLayers; ++l) {
         const int N = WL::rows(l);
         unsigned char* bt = wbase + WL::bt(l);
-        for (int i = tid; i < N * 16; i += nthreads) {
-            const int n = i >> 4, k = i & 15;
+        for (int i = tid; i < N * 8; i += nthreads) {
+            const int n = i >> 3, k = i & 7;
             float v = 0.f;
             if (k < 2 && n < nreal[l] && net.B[l]) {
                 const float b = __ldg(net.B[l] + n);
@@ -155,6 +157,7 @@ __device__ __forceinline__ void load_all_weights(const FieldNet& net, unsigned c
             *reinterpret_cast<__nv_bfloat16*>(bt + cm_off(N, n, k)) = __float2bfloat16_rn(v);
         }
     }
+    for (int i = tid; i < kBaseOut * 8; i += nthreads) reinterpret_cast<__nv_bfloat16*>(wbase + WL::btz)[i] = __float2bfloat16_rn(0.f);
     // constant blocks: element e of a 128-byte block = row e / 8, column e % 8
     for (int i = tid; i < 128; i += nthreads) {
         reinterpret_cast<__nv_bfloat16*>(wbase + WL::ones)[i] = __float2bfloat16_rn((i < 64 && (i & 7) < 2) ? 1.f : 0.f);

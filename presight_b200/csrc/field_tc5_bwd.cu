@@ -396,19 +396,19 @@ constexpr int kBarR = 1, kBarW = 2, kBarD = 3, kBarEnd = 4, kBarBase = 5, kBarCR
             // =========================== the two issuing warps =====================================================
             if (warp_u == 8) {
                 // base network, forward
-                B2_ISSUE(kBarBase, kB2Epi + 64, gemm_bias(tmem + TM::accR, ones, wb + WL::bt(B0), kHid, kHid);
+                B2_ISSUE(kBarBase, kB2Epi + 64, gemm_bias(tmem + TM::accR, ones, wb + WL::bt(B0), wb + WL::btz, kHid);
                          gemm_kk(tmem + TM::accR, aX0, kRows, wb + WL::b0, kHid, kHid, K0, true); umma_commit(barBd))
-                B2_ISSUE(kBarBase, kB2Epi + 64, gemm_bias(tmem + TM::accR, ones, wb + WL::bt(B1), kBaseOut, kBaseOut);
+                B2_ISSUE(kBarBase, kB2Epi + 64, gemm_bias(tmem + TM::accR, ones, wb + WL::bt(B1), wb + WL::btz, kBaseOut);
                          gemm_kk(tmem + TM::accR, aH1, kRows, wb + WL::b1, kBaseOut, kBaseOut, kHid, true); umma_commit(barBd))
                 // colour head, forward
-                B2_ISSUE(kBarBase, kB2Epi + 64, gemm_bias(tmem + TM::accR, ones, wb + WL::bt(R0), kHid, kHid);
+                B2_ISSUE(kBarBase, kB2Epi + 64, gemm_bias(tmem + TM::accR, ones, wb + WL::bt(R0), wb + WL::btz, kHid);
                          gemm_kk(tmem + TM::accR, aSH, kRows, wb + WL::r0, kHid, kHid, 16, true);
                          gemm_kk(tmem + TM::accR, aH, kRows, wb + WL::r0 + 2 * kHid * 16, kHid, kHid, 16, true);
                          gemm_kk(tmem + TM::accR, aSH + 2 * CH, kRows, wb + WL::r0 + 4 * kHid * 16, kHid, kHid, 16, true);
                          umma_commit(barRd))
-                B2_ISSUE(kBarCR, 128 + 32, gemm_bias(tmem + TM::accR, ones, wb + WL::bt(R1), kHid, kHid);
+                B2_ISSUE(kBarCR, 128 + 32, gemm_bias(tmem + TM::accR, ones, wb + WL::bt(R1), wb + WL::btz, kHid);
                          gemm_kk(tmem + TM::accR, aA1r, kRows, wb + WL::r1, kHid, kHid, kHid, true); umma_commit(barRd))
-                B2_ISSUE(kBarCR, 128 + 32, gemm_bias(tmem + TM::accR, ones, wb + WL::bt(R2), kRgbOut, kRgbOut);
+                B2_ISSUE(kBarCR, 128 + 32, gemm_bias(tmem + TM::accR, ones, wb + WL::bt(R2), wb + WL::btz, kRgbOut);
                          gemm_kk(tmem + TM::accR, aA2r, kRows, wb + WL::r2, kRgbOut, kRgbOut, kHid, true); umma_commit(barRd))
                 // colour head, backward: input gradient first (its epilogue starts under the weight / bias gradient GEMMs)
                 B2_ISSUE(kBarCR, 128 + 32, gemm_dgrad(tmem + TM::accR, aDH, kRows, wb + WL::r2, kRgbOut, kHid, 16, false);
@@ -464,12 +464,12 @@ constexpr int kBarR = 1, kBarW = 2, kBarD = 3, kBarEnd = 4, kBarBase = 5, kBarCR
                 }
                 bar_sync<kBarBase, kB2Epi + 64>();
                 // semantic head, forward (sub-field mode: the output layer is linear and its dZ is an input, no recompute)
-                B2_ISSUE(kBarBase, kB2Epi + 64, gemm_bias(tmem + TM::accS, ones, wb + WL::bt(S0), kHid, kHid);
+                B2_ISSUE(kBarBase, kB2Epi + 64, gemm_bias(tmem + TM::accS, ones, wb + WL::bt(S0), wb + WL::btz, kHid);
                          gemm_kk(tmem + TM::accS, aH + 2 * CH, kRows, wb + WL::s0, kHid, kHid, kSem, true); umma_commit(barSd))
-                B2_ISSUE(kBarCS, 128 + 32, gemm_bias(tmem + TM::accS, ones, wb + WL::bt(S1), kHid, kHid);
+                B2_ISSUE(kBarCS, 128 + 32, gemm_bias(tmem + TM::accS, ones, wb + WL::bt(S1), wb + WL::btz, kHid);
                          gemm_kk(tmem + TM::accS, aA1s, kRows, wb + WL::s1, kHid, kHid, kHid, true); umma_commit(barSd))
                 if constexpr (!MS) {
-                    B2_ISSUE(kBarCS, 128 + 32, gemm_bias(tmem + TM::accS, ones, wb + WL::bt(S2), kSem, kSem);
+                    B2_ISSUE(kBarCS, 128 + 32, gemm_bias(tmem + TM::accS, ones, wb + WL::bt(S2), wb + WL::btz, kSem);
                              gemm_kk(tmem + TM::accS, aA2s, kRows, wb + WL::s2, kSem, kSem, kHid, true); umma_commit(barSd))
                 }
                 // semantic head, backward
