@@ -236,21 +236,19 @@ class SkyFieldMS(nn.Module):
         ray keeps the output of the sub-field nearest to its origin — the values the routed loop of the reference
         computes and, through the selection's gradient (zero rows for the rays of other sub-fields), the same parameter
         gradients.  Costs nf x the sky arithmetic (about 2 ms at 65 536 rays and 16 sub-fields) and buys a step without
-        any device->host read; the routed loop (`batched = False`) needs one read of the bucket sizes per call."""
-        nf = len(self.fields)
+        any device->host read; the routed loop (`batched = False`) needs one read of the bucket sizes per call.
+        One autograd node per head (ops.mlp_select): the first version's nf nodes and 4 nf element-wise launches per head
+        were 5 ms of host time per step at 16 sub-fields (tools/host_profile.py)."""
         sf = ops.nearest_centroid(origins, self.centroids).long()                     # [N]
         d = self.fields[0].direction_encoding.forward_raw(directions)                 # [N,16], no gradient
         x = d if app is None else torch.cat([d, app], dim=-1)
-        pick = torch.nn.functional.one_hot(sf, nf).to(torch.float32)                  # [N,nf]
-        rgb = sem = None
-        for k, f in enumerate(self.fields):
-            m = pick[:, k:k + 1]
-            r = f.rgb_head(x) * m                                                     # exact: x1 for its own rays, x0 else
-            rgb = r if rgb is None else rgb + r
-            if f.use_semantics:
-                q = f.semantic_head(d) * m
-                sem = q if sem is None else sem + q
-        out = {FieldHeadNames.RGB: rgb}
-        if sem is not None:
-            out[FieldHeadNames.SEMANTICS] = sem
+
+        def head(name, inp):      # one autograd node for the nf networks of this head (ops._MlpSelect)
+            mods = [getattr(f, name) for f in self.fields]
+            nets = [([l.weight for l in m.layers], [l.bias for l in m.layers]) for m in mods]
+            return ops.mlp_select(inp, sf, nets, mods[0]._out_act, mods[0].precision)
+
+        out = {FieldHeadNames.RGB: head("rgb_head", x)}
+        if all(f.use_semantics for f in self.fields):
+            out[FieldHeadNames.SEMANTICS] = head("semantic_head", d)
         return out

@@ -224,6 +224,65 @@ class _Mlp(torch.autograd.Function):
         return (None if dx is None else dx.view(xshape), None, None, None, *dW, *db)
 
 
+class _MlpSelect(torch.autograd.Function):
+    """y[n] = MLP_{sf[n]}(x[n]) for nf networks of one shape: every network runs on all rows (the per-ray sky networks are
+    tiny) and each row keeps its own network's output — one autograd node, one gather, instead of nf nodes and 4 nf
+    element-wise launches.  params: the networks' weights, then their biases, network by network."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, sf: Tensor, out_act: int, precision: int, n_layers: int, nf: int, *params: Tensor):
+        xs = _f32c(x.detach())
+        x2 = xs.view(-1, xs.shape[-1])
+        N = x2.shape[0]
+        per = 2 * n_layers
+        nets = [([p.detach().contiguous() for p in params[k * per:k * per + n_layers]],
+                 [p.detach().contiguous() for p in params[k * per + n_layers:(k + 1) * per]]) for k in range(nf)]
+        dims = [x2.shape[1]] + [w.shape[0] for w in nets[0][0]]
+        Y = torch.empty(nf, N, dims[-1], device=x2.device, dtype=torch.float32)
+        hd, st = host_ints(dims), stream()
+        with _probe("mlp_fwd_" + "x".join(map(str, dims))):
+            for k, (ws, bs) in enumerate(nets):
+                call("ps_mlp_fwd", ptr(x2), N, host_ptrs(ws), host_ptrs(bs), hd, n_layers, out_act, fwd_precision(precision),
+                     ptr(Y[k]), st)
+        idx = sf.view(1, N, 1).expand(1, N, dims[-1])
+        y = Y.gather(0, idx).squeeze(0)
+        ctx.save_for_backward(x2, sf, *params)
+        ctx.meta = (out_act, precision, n_layers, nf, dims, x.shape)
+        return y.view(*x.shape[:-1], dims[-1])
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        out_act, precision, n_layers, nf, dims, xshape = ctx.meta
+        x2, sf, *params = ctx.saved_tensors
+        N, per = x2.shape[0], 2 * n_layers
+        nets = [([p.detach().contiguous() for p in params[k * per:k * per + n_layers]],
+                 [p.detach().contiguous() for p in params[k * per + n_layers:(k + 1) * per]]) for k in range(nf)]
+        idx = sf.view(1, N, 1).expand(1, N, dims[-1])
+        dY = torch.zeros(nf, N, dims[-1], device=x2.device, dtype=torch.float32)
+        dY.scatter_(0, idx, _f32c(dy).view(1, N, dims[-1]))              # rows of other networks' rays stay zero
+        zs = zeros_like_many([t for ws, bs in nets for t in (*ws, *bs)])     # one fill for every gradient
+        need_dx = ctx.needs_input_grad[0]
+        dX = torch.empty(nf, N, dims[0], device=x2.device, dtype=torch.float32) if need_dx else None
+        hd, st = host_ints(dims), stream()
+        with _probe("mlp_bwd_" + "x".join(map(str, dims))):
+            for k, (ws, bs) in enumerate(nets):
+                g = zs[k * per:(k + 1) * per]
+                call("ps_mlp_bwd", ptr(x2), None, ptr(dY[k]), N, host_ptrs(ws), host_ptrs(bs), hd, n_layers, out_act, precision,
+                     None if dX is None else ptr(dX[k]), host_ptrs(g[:n_layers]), host_ptrs(g[n_layers:]), st)
+        dx = None
+        if need_dx:
+            dx = dX.gather(0, sf.view(1, N, 1).expand(1, N, dims[0])).squeeze(0).view(xshape)
+        return (dx, None, None, None, None, None, *zs)
+
+
+def mlp_select(x: Tensor, sf: Tensor, nets: Sequence[Tuple[Sequence[Tensor], Sequence[Tensor]]], out_act: int = ACT_NONE,
+               precision: int = PREC_BF16) -> Tensor:
+    """Row n through network sf[n] (all networks of one shape, biases present): see _MlpSelect."""
+    n_layers = len(nets[0][0])
+    flat = [t for ws, bs in nets for t in (*ws, *bs)]
+    return _MlpSelect.apply(x, sf, int(out_act), int(precision), n_layers, len(nets), *flat)
+
+
 def mlp(x: Tensor, weights: Sequence[Tensor], biases: Sequence[Optional[Tensor]], out_act: int = ACT_NONE,
         precision: int = PREC_BF16) -> Tensor:
     """Linear+ReLU stack with optional output activation (mlp.py:157-174) in ONE kernel per direction."""
