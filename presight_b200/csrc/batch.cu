@@ -35,8 +35,12 @@ __global__ void __launch_bounds__(256) assemble_batch_kernel(BatchFields f, cons
     const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (b >= B) return;
     const int64_t i = idx[b];
-    if (i < 0 || i >= n_chunk) {            // the reference's indexing would raise: report, leave the row untouched
-        if (lane == 0) atomicExch(bad, 1);
+    if (i < 0 || i >= n_chunk) {            // the reference's indexing would raise: report; the row gets a harmless ray index
+        if (lane == 0) {
+            atomicExch(bad, 1);
+            f.ray_index[b * 3] = 0; f.ray_index[b * 3 + 1] = 0; f.ray_index[b * 3 + 2] = 0;
+            f.image_index[b] = 0; f.video_id[b] = 0;
+        }
         return;
     }
     if (f.features) {

@@ -65,9 +65,11 @@ def test_device_loader_reports_bad_index_and_feeds_ray_generator():
     assert rb.origins.shape == (256, 3) and rb.metadata["video_id"].shape == (256, 1)
     assert float(rb.metadata["pose_scale_factor"][0]) == pytest.approx(0.01)
     assert torch.equal(rb.camera_indices.view(-1), batch["ray_index"][:, 0])
-    loader.indices[3] = 10 ** 9
+    loader.check()
+    loader.indices[3] = 10 ** 9            # an index outside the chunk: flagged, and the row still yields a valid camera index
     loader._b = 0
-    next(loader)
+    rb, batch = next(loader)
+    assert int(batch["ray_index"][3].abs().sum()) == 0
     with pytest.raises(IndexError):
         loader.check()
 
