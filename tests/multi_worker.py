@@ -6,6 +6,7 @@
   partial   the same parity with the main hash table's gradient exchanged level group by level group from inside the backward
             (GradSynchronizer(partial_tables=...), proposal levels on their single-GPU side-stream schedule).
   peer      the partial exchange on the copy engines between IPC-mapped buffers (peer_exchange.py) instead of NCCL.
+  peerk     the same exchange as two kernels with P2P stores (PS_PEER_MODE=kernel).
   sharded   ShardedFusedAdam (reduce-scatter -> Adam on the shard -> all-gather) against GradSynchronizer + FusedAdam:
             same parameters after several steps, on every rank.
 """
@@ -71,7 +72,7 @@ def main():
     from presight_b200 import fused
     from presight_b200.parallel import GradSynchronizer, init_nccl, shard_range
     init_nccl(dev)
-    fused.set_overlap_prop_bwd(mode in ("partial", "peer"))
+    fused.set_overlap_prop_bwd(mode in ("partial", "peer", "peerk"))
     n = 4096
     model, cfg, host = make(n)
     model = model.to(dev).train()
@@ -80,13 +81,15 @@ def main():
     jit = [torch.rand(n, 1, generator=g) for _ in range(3)]
     lo, hi = shard_range(n, rank, world)
     ok = True
-    if mode in ("grads", "partial", "peer"):
+    if mode in ("grads", "partial", "peer", "peerk"):
         partial = []
-        if mode in ("partial", "peer"):
+        if mode == "peerk":
+            os.environ["PS_PEER_MODE"] = "kernel"
+        if mode in ("partial", "peer", "peerk"):
             from presight_b200.parallel import level_groups
             enc = model.field.fields[0].mlp_base_grid
             partial = [(enc.hash_table, level_groups(enc.num_levels, world=world))]
-        sync = GradSynchronizer(params, overlap=True, partial_tables=partial, peer=mode == "peer")
+        sync = GradSynchronizer(params, overlap=True, partial_tables=partial, peer=mode in ("peer", "peerk"))
         step_grads(model, host, lo, hi, jit, dev)
         sync.finish()
         torch.cuda.synchronize()

@@ -33,5 +33,9 @@ def test_peer_memory_exchange_matches_the_concatenated_batch():
     assert "MULTI peer" in run("peer")
 
 
+def test_peer_memory_exchange_with_p2p_store_kernels():
+    assert "MULTI peerk" in run("peerk")
+
+
 def test_sharded_adam_matches_allreduce_plus_adam():
     assert "MULTI sharded" in run("sharded")
