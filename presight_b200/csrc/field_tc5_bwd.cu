@@ -7,7 +7,7 @@
 //
 // Here the colour head and the semantic head — independent once the base network's output H exists — run as two
 // concurrent chains on the same 128-point tile: warps 0-3 (group R, one thread per point) drive the colour head and the
-// compositing, warps 4-7 (group S) the semantic head.  Each group has its own MMA-issuing lane, commit barriers, named
+// compositing, warps 4-7 (group S) the semantic head.  Each chain has its own issuing warp, commit barriers, named
 // barrier and 64-column accumulator, so one head's epilogue runs under the other head's GEMMs: 2 + 6 + 2 dependent phases
 // per tile instead of 16.  What makes both heads' tiles fit in 227 KB of shared memory:
 //   * gradients are written IN PLACE: dZ_{k-1} = dA_{k-1} * relu'(A_{k-1}) overwrites the activation tile A_{k-1} (row-local);
@@ -19,7 +19,8 @@
 // on the chain's critical path (first two-chain version: no faster than the single chain).  Epilogue threads only ARRIVE on
 // the "operands ready" named barrier and go straight to the commit barrier of the result they need.
 // What makes the accumulators fit in 512 TMEM columns: weight gradients of the 64-row layers are M = 64 GEMMs, two
-// accumulators per column range (tc5.cuh:kLaneHi) — 256 columns instead of 432 — which also cost 25 % less tensor time.
+// accumulators per column range where both are fed by the same issuing thread (tc5.cuh:kLaneHi) — 352 columns for all
+// weight / bias gradients beside the two 64-column working accumulators (B2Tmem) — which also cost 25 % less tensor time.
 #include <type_traits>
 
 #include "field_tc5.cuh"
@@ -66,7 +67,7 @@ struct B2Smem {
     static constexpr uint32_t tails = dsem + 128 * 4;                    // double [2][4]
     static constexpr uint32_t bars = tails + 2 * 4 * 8;                  // 7 mbarriers + tmem slot
     // next tile's hash features, fp32 level-major [L][128][F] as they lie in global memory: filled by bulk copies (TMA)
-    // issued one tile ahead.  Only when it fits (K0 = 32: 16 KB -> 225.6 KB in all); otherwise the rows are loaded directly.
+    // issued one tile ahead.  Only when it fits (K0 = 32: 16 KB -> 219 KB in all); otherwise the rows are loaded directly.
     static constexpr bool prefetch = K0 <= 32;
     static constexpr uint32_t stage = ((bars + 64 + 127) / 128) * 128;
     static constexpr uint32_t total = prefetch ? stage + kRows * K0 * 4 : bars + 64;
