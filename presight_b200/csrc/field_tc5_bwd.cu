@@ -66,11 +66,12 @@ struct B2Smem {
     static constexpr uint32_t dsem = wbuf + 128 * 4;                     // float [128]: <sem, d_sem>, group S -> group R
     static constexpr uint32_t tails = dsem + 128 * 4;                    // double [2][4]
     static constexpr uint32_t bars = tails + 2 * 4 * 8;                  // 7 mbarriers + tmem slot
-    // next tile's hash features, fp32 level-major [L][128][F] as they lie in global memory: filled by bulk copies (TMA)
-    // issued one tile ahead.  Only when it fits (K0 = 32: 16 KB -> 219 KB in all); otherwise the rows are loaded directly.
-    static constexpr bool prefetch = K0 <= 32;
-    static constexpr uint32_t stage = ((bars + 64 + 127) / 128) * 128;
-    static constexpr uint32_t total = prefetch ? stage + kRows * K0 * 4 : bars + 64;
+    // The next tile's hash features (fp32, level-major [L][128][F] as they lie in global memory: L * F * 512 bytes) are copied
+    // by bulk copies (TMA) into the semantic chain's two activation tiles, which are dead from the join to the next tile's
+    // semantic forward: no shared memory of their own, for any K0.
+    static constexpr uint32_t stage = a1s;
+    static constexpr uint32_t stage_cap = 2 * cm_bytes(kRows, 64);
+    static constexpr uint32_t total = bars + 64;
 };
 
 // TMEM columns.  Working accumulators first; the base network uses accR .. accR + 80.
@@ -226,11 +227,12 @@ __global__ void __maxnreg__(128) field_bwd2_kernel(Args a) {
     int cur = -1;           // MS: sub-field whose weights are staged
 
     // ---- feature prefetch: one lane of warp 9 copies tile t's rows of every level (contiguous in the level-major layout)
-    // into the staging buffer while tile t - gridDim.x is being processed -------------------------------------------------
+    // into the staging area (B2Smem::stage) during the base-network backward of tile t - gridDim.x ------------------------
     int64_t feat_rows;      // rows per level of the feature array
     if constexpr (MS) feat_rows = a.rows;
     else feat_rows = P;
-    const bool use_pref = SM::prefetch && (reinterpret_cast<uintptr_t>(a.feat) & 15) == 0 && ((feat_rows * a.F * 4) & 15) == 0;
+    const bool use_pref = (uint32_t)(a.L * a.F) * kRows * 4 <= SM::stage_cap && (reinterpret_cast<uintptr_t>(a.feat) & 15) == 0 &&
+                          ((feat_rows * a.F * 4) & 15) == 0;
     auto prefetch_tile = [&](int64_t t) {        // called by ONE thread
         if (t >= ntiles) return;
         int64_t p0;
@@ -437,13 +439,9 @@ constexpr int kBarR = 1, kBarW = 2, kBarD = 3, kBarEnd = 4, kBarBase = 5, kBarCR
             } else {
                 // (the base network's operand barrier counts both issuing warps: pass its two forward generations)
                 bar_sync<kBarBase, kB2Epi + 64>();
-                // every epilogue thread has staged this tile's inputs: the staging buffer is free for the next tile's features
-                if (use_pref) {
-                    if (elect_one()) prefetch_tile(tile + gridDim.x);
-                    __syncwarp();
-                }
                 if constexpr (!MS) {
-                    // ... and its small per-ray / per-sample inputs are pulled into L2 (one line per lane)
+                    // every epilogue thread has staged this tile's inputs: the next tile's small per-ray / per-sample inputs
+                    // are pulled into L2 (one line per lane)
                     const int64_t nt = tile + gridDim.x;
                     if (nt < ntiles) {
                         const int64_t ray0 = nt * rpt, p0 = ray0 * S;
@@ -487,6 +485,12 @@ constexpr int kBarR = 1, kBarW = 2, kBarD = 3, kBarEnd = 4, kBarBase = 5, kBarCR
                          gemm_wgrad64(tmem + TM::p1, aA1s, aH + 2 * CH, kSem, acc_dw);
                          gemm_bias_grad_m(tmem + TM::bs, aA1s, onehot + S0 * 256, 64, true); umma_commit(barSw))
                 bar_sync<kBarBase, kB2Epi + 64>();      // ... and the two backward generations of the base network
+                // (join passed: every epilogue thread has seen the semantic chain's last commit, A1s / A2s are dead — the next
+                // tile's features land there while the base network's backward runs)
+                if (use_pref) {
+                    if (elect_one()) prefetch_tile(tile + gridDim.x);
+                    __syncwarp();
+                }
                 bar_sync<kBarBase, kB2Epi + 64>();
             }
             continue;
