@@ -47,10 +47,11 @@ FIELD_CHUNKS = max(1, int(os.environ.get("PS_FIELD_CHUNKS", "1")))
 # the remaining levels and the proposal networks are still being differentiated.
 # device index -> [event recorded behind the step's (last) field backward kernel, proposal backwards launched since]
 # (autograd runs the field level's backward first).  PS_PROP_BWD_ORDER: "second" = the first proposal backward of a step starts
-# at once, later ones wait for the field kernel; "all" = all wait; "free" = no ordering (which of two kernels launched
-# microseconds apart on different streams gets the SMs first is then a race).
+# at once, later ones wait for the field kernel; "all" = all wait; "before" = they wait for the point where the field kernel
+# becomes launchable (and so queue behind it without waiting for its end); "free" = no ordering (which of two kernels
+# launched microseconds apart on different streams gets the SMs first is then a race).
 _FIELD_BWD_ORDER = {}
-PROP_BWD_ORDER = os.environ.get("PS_PROP_BWD_ORDER", "free")
+PROP_BWD_ORDER = os.environ.get("PS_PROP_BWD_ORDER", "before")
 PROP_BWD_PRIO = os.environ.get("PS_PROP_BWD_PRIO", "0") == "1"      # proposal backwards on a high-priority stream
 
 _PARTIAL_SINKS = {}          # table.data_ptr() -> (callable(dtable, row_lo, row_hi), level groups [(l0, l1), ...], alloc)
@@ -540,6 +541,12 @@ class _FieldLevelTc5(torch.autograd.Function):
             # (the 512 MiB memset runs under the first field slice)
             dtable = sink[2]() if (sink is not None and sink[2] is not None) else torch.zeros_like(table)
         keep = []            # main-stream buffers read on the side stream: alive until the join below
+        ev_ready = None
+        if PROP_BWD_ORDER == "before":
+            # recorded where the field kernel's inputs are complete: a proposal backward launched later this step waits for it,
+            # i.e. it cannot reach the GPU before the field kernel is launchable and queues behind it
+            ev_ready = torch.cuda.Event()
+            ev_ready.record(main)
         for i, (c0, c1) in enumerate(bounds):
             dfeat = torch.empty_like(feats[i])
             keep.append(dfeat)
@@ -554,7 +561,8 @@ class _FieldLevelTc5(torch.autograd.Function):
                 if piped:
                     side.wait_event(ev)
                 if i == nc - 1:
-                    _FIELD_BWD_ORDER[dev.index] = [ev, 0]      # [field backward done, proposal backwards launched since]
+                    # [field backward done (or, "before": launchable), proposal backwards launched since]
+                    _FIELD_BWD_ORDER[dev.index] = [ev if ev_ready is None else ev_ready, 0]
             with torch.cuda.stream(side):
                 if sink is None:
                     with ops._probe(f"hash_bwd_L{grid.L}F{grid.F}T{grid.log2_T}"):
